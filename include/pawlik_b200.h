@@ -1,0 +1,144 @@
+/* pawlik_b200.h — C ABI of the B200-native PawlikMorph-LSST morphology hot path.
+ *
+ * One shared object (libpawlik_b200.so), extern "C", plain pointers and sizes.
+ * The reference (lewisfish/PawlikMorph-LSST) is pure Python and has no FFI layer;
+ * its drop-in boundary is the Python module API of
+ *   pawlikMorphLSST/pixmap.py, apertures.py, asymmetry.py, casgm.py
+ * as called from main.py:421-495.  Each entry point below names the reference
+ * function(s) it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - All data pointers are CALLER-OWNED DEVICE memory (e.g. torch tensors) unless
+ *    marked HOST.  The library allocates nothing persistent and frees nothing.
+ *  - Calls are asynchronous on `cuda_stream` (a cudaStream_t passed as void*).
+ *  - Return value: 0 on success, a negative PM_E* code for argument / launch
+ *    errors.  Per-cutout failures never abort a batch: they are reported in
+ *    pm_row_t.status and the statistics of that row stay at the reference's
+ *    sentinel -99 (result.py:26-54).
+ *  - Segmaps, star masks and aperture masks are binary {0,1} uint8 [B, n, n].
+ *  - Images are [B, n, n] row-major, float32 (PM_F32) or float64 (PM_F64), WITH the
+ *    sky still in them; `sky[b]` is subtracted on the fly in float64 exactly where
+ *    main.py:442 does `img -= sky`.  Pass sky = 0 for already-subtracted images.
+ *  - Re-entrant, no global state.  n <= PM_MAX_N.
+ */
+#ifndef PAWLIK_B200_H
+#define PAWLIK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1
+#define PM_MAX_N 640
+
+/* dtype of `images` */
+#define PM_F32 0
+#define PM_F64 1
+
+/* error codes */
+#define PM_OK 0
+#define PM_EINVAL (-1)     /* bad argument (null pointer, n out of range, even filter size, ...) */
+#define PM_ENOSPC (-2)     /* workspace too small: call pm_workspace_bytes() */
+#define PM_ECUDA (-3)      /* CUDA launch / runtime error; see pm_last_cuda_error() */
+#define PM_ENODEV (-4)     /* no CUDA device / not an sm_100 device */
+
+/* which statistics to compute (flags).  Mirrors the CLI switches of imganalysis.py:8-70
+ * as main.py:470-495 uses them: A is computed for -A/-Aall/-cas, As+As90 for -As/-Aall,
+ * r20/r80/C/gini/m20 for -cas.  PM_DO_S adds the smoothness S that main.py:494 leaves
+ * commented out (casgm.py:276-406). */
+#define PM_DO_A 1u
+#define PM_DO_AS 2u
+#define PM_DO_CAS 4u
+#define PM_DO_S 8u
+#define PM_DO_ALL 15u
+/* debugging / test switches */
+#define PM_FORCE_EXACT_FILTER 0x100u /* pixelmap: take the sequential scipy-recurrence path for every pixel */
+/* stage control, used by the per-cutout Python functions (pixmap.pixelmap, pixmap.calcRmax, ...) */
+#define PM_STOP_AFTER_PIXELMAP 0x200u /* only pixelmap + checkPixelmapEdges */
+#define PM_STOP_AFTER_RMAX 0x400u     /* ... + calcRmax + aperpixmap */
+#define PM_A_ANGLE90 0x800u           /* calcA on the image with angle = 90 instead of 180 (asymmetry.py:132) */
+#define PM_NO_NOISECORRECT 0x1000u    /* calcA(..., noisecorrect=False): Abgr = 0, A not corrected */
+
+/* pm_row_t.status */
+#define PM_ST_OK 0
+#define PM_ST_FAINT_CENTRE 1 /* pixmap.py:178-179 "Central pixel too faint" -> default Result (main.py:420-424) */
+#define PM_ST_NO_CANDIDATE 2 /* no positive pixel in image*segmap: np.argmin([]) upstream (asymmetry.py:127) */
+#define PM_ST_BAD_BRACKET 3  /* casgm.py:65-76 would raise (radius walked to <= 0 / no sign change) */
+#define PM_ST_EMPTY_SEGMAP 4 /* supplied segmap has no pixel set: calcRmax would raise (pixmap.py:51-53) */
+#define PM_ST_WORKSPACE 5    /* per-CTA scratch exhausted (cannot happen with pm_workspace_bytes()) */
+
+/* One result row per cutout: the fields of result.Result (result.py:26-76) this path fills.
+ * 16 x float64 = 128 bytes.  Unset statistics hold -99. */
+typedef struct {
+    double apix_col, apix_row; /* Result.apix = [col, row]            asymmetry.py:129 */
+    double rmax;               /* Result.rmax                         pixmap.py:26-55 */
+    double r20, r80, C;        /* casgm.py:124-184 */
+    double A, Abgr;            /* Result.A = [A, Abgr]                asymmetry.py:132-257 */
+    double S;                  /* casgm.py:276-338 */
+    double As, As90;           /* Result.As[0], Result.As90[0] */
+    double gini, m20;          /* casgm.py:187-273 */
+    double object_edge;        /* Result.objectEdge (0/1)             pixmap.py:91-127 */
+    double status;             /* PM_ST_* */
+    double n_candidates;       /* number of centroid candidates tried by minapix (asymmetry.py:101-108) */
+} pm_row_t;
+
+/* Optional per-cutout overrides that turn the fused pipeline into the reference's individual
+ * functions (used by the per-cutout Python API; all nullable, all DEVICE pointers). */
+typedef struct {
+    const uint8_t *segmap_in;   /* [B,n,n]  skip pixelmap, use this map (main.py:428-439 -segmap path) */
+    const uint8_t *starmask;    /* [B,n,n]  star mask, 1 = keep (pixmap.py:156-158, asymmetry.py:82-86,:182-191) */
+    const uint8_t *apermask_in; /* [B,n,n]  aperture mask instead of aperpixmap(n, rmax, 9, 0.1) */
+    const double *centroid_in;  /* [B,2]    (col,row): skip minapix, use this centre (calcA / calcR20_R80 / smoothness) */
+    const double *radius_in;    /* [B]      use this radius instead of calcRmax (calcR20_R80 / smoothness / aperpixmap) */
+    const double *r20_in;       /* [B]      use this r20 in smoothness */
+    const double *threshold_in; /* [B]      pixelmap threshold instead of sky + sky_err (pixmap.py:130) */
+    const double *smooth_sky_in; /* [B]     the `sky` argument of casgm.smoothness (casgm.py:276) when it differs from
+                                            the value subtracted from the image (already-subtracted images: sky = 0) */
+} pm_overrides_t;
+
+/* Optional outputs beyond the rows (all nullable, DEVICE). */
+typedef struct {
+    uint8_t *segmap_out;     /* [B,n,n]  pixmap.pixelmap result (0/1) */
+    int32_t *sorted_idx_out; /* [B,n*n]  parity aid: flat indices of image*segmap in the canonical descending order
+                                (value desc, index desc) for the POSITIVE prefix; the rest is -1.  asymmetry.py:94-95 */
+    int32_t *n_positive_out; /* [B]      length of that prefix */
+    uint8_t *apermask_out;   /* [B,n,n]  the aperture mask used (apertures.aperpixmap) */
+    double *cand_a_out;      /* [B,cand_cap] parity aid: asymmetry of each candidate in order (asymmetry.py:125) */
+    int32_t cand_cap;
+} pm_outputs_t;
+
+/* Bytes of device scratch pm_analyse_batch needs for (B, n, dtype).  HOST call, no CUDA work. */
+size_t pm_workspace_bytes(int64_t B, int n, int dtype);
+
+/* The whole hot path for a batch of cutouts, one CTA per cutout, image read from HBM once:
+ *   pixmap.pixelmap + checkPixelmapEdges  (pixmap.py:130-213, :91-127)       main.py:421,427
+ *   pixmap.calcRmax, apertures.aperpixmap (pixmap.py:26-55, apertures.py:42-128) main.py:463-464
+ *   asymmetry.minapix                     (asymmetry.py:50-129)               main.py:467
+ *   asymmetry.calcA x3                    (asymmetry.py:132-257)              main.py:470-478
+ *   casgm.calcR20_R80, concentration, gini, m20, smoothness (casgm.py)        main.py:490-495
+ * images  [B,n,n] dtype;  sky, sky_err [B] float64;  filter_size odd in 1..15;
+ * ov / out may be NULL;  rows [B];  workspace >= pm_workspace_bytes(B,n,dtype). */
+int pm_analyse_batch(const void *images, int dtype, int64_t B, int n, const double *sky,
+                     const double *sky_err, int filter_size, uint32_t flags,
+                     const pm_overrides_t *ov, const pm_outputs_t *out, pm_row_t *rows,
+                     void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* apertures.aperpixmap(npix, rad, nsubpix, frac) for B radii at once (apertures.py:42-128):
+ * mask_out [B,n,n] uint8.  General float radius / nsubpix / frac (the float64 sub-sample test). */
+int pm_aperpixmap_batch(int n, const double *rad, int64_t B, int nsubpix, double frac,
+                        uint8_t *mask_out, void *cuda_stream);
+
+/* Library / device introspection (HOST). */
+int pm_abi_version(void);
+int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
+const char *pm_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (bench.py reports it) */
+uint64_t pm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAWLIK_B200_H */

@@ -1,0 +1,315 @@
+// pm_block.cuh — block-wide building blocks of the per-cutout kernel: deterministic
+// reductions and scans, the stable LSD radix sort, the per-cutout scratch arena and
+// the exact circle/pixel overlap geometry.  All reductions use a fixed combination
+// order so that results do not depend on scheduling (and therefore not on the number
+// of GPUs a batch is sharded over).
+#pragma once
+#include "pm_platform.cuh"
+
+namespace pmk {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kRedSlots = 8;
+
+// Block-shared scalars.  Lives at offset 0 of the dynamic shared memory.
+struct Sh {
+    double red[kWarps * kRedSlots];  // per-warp partials of block reductions
+    double bc[16];                   // broadcast slots
+    double rk[132];                  // walk radii of casgm.py:55-73
+    double fk[132];                  // F(rk)
+    unsigned scan_tmp[kWarps + 2];
+    unsigned colmask[24];            // OR of all segmap rows (PM_MAX_N / 32 words)
+    int ia[8];                       // integer reductions (atomics)
+    int status;
+};
+
+PM_DEV unsigned lt_mask() { return (1u << pm::lane()) - 1u; }
+
+// ---- reductions ------------------------------------------------------------------------
+template <int K> PM_DEV void block_sum(Sh& sh, double (&v)[K]) {
+    static_assert(K <= kRedSlots, "too many reduction slots");
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = pm::warp_sum(v[k]);
+    if (pm::lane() == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) sh.red[pm::warp() * K + k] = v[k];
+    }
+    pm::sync();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double s = 0.0;
+        for (int w = 0; w < kWarps; w++) s += sh.red[w * K + k];
+        v[k] = s;
+    }
+    pm::sync();
+}
+PM_DEV double block_sum1(Sh& sh, double v) {
+    double a[1] = {v};
+    block_sum<1>(sh, a);
+    return a[0];
+}
+PM_DEV double block_max(Sh& sh, double v) {
+    v = pm::warp_max(v);
+    if (pm::lane() == 0) sh.red[pm::warp()] = v;
+    pm::sync();
+    double s = sh.red[0];
+    for (int w = 1; w < kWarps; w++) s = fmax(s, sh.red[w]);
+    pm::sync();
+    return s;
+}
+PM_DEV double block_min(Sh& sh, double v) {
+    v = pm::warp_min(v);
+    if (pm::lane() == 0) sh.red[pm::warp()] = v;
+    pm::sync();
+    double s = sh.red[0];
+    for (int w = 1; w < kWarps; w++) s = fmin(s, sh.red[w]);
+    pm::sync();
+    return s;
+}
+PM_DEV int block_min_i(Sh& sh, int v) {
+    v = pm::warp_min(v);
+    if (pm::lane() == 0) sh.scan_tmp[pm::warp()] = (unsigned)v;
+    pm::sync();
+    int s = (int)sh.scan_tmp[0];
+    for (int w = 1; w < kWarps; w++) s = min(s, (int)sh.scan_tmp[w]);
+    pm::sync();
+    return s;
+}
+PM_DEV int block_max_i(Sh& sh, int v) {
+    v = pm::warp_max(v);
+    if (pm::lane() == 0) sh.scan_tmp[pm::warp()] = (unsigned)v;
+    pm::sync();
+    int s = (int)sh.scan_tmp[0];
+    for (int w = 1; w < kWarps; w++) s = max(s, (int)sh.scan_tmp[w]);
+    pm::sync();
+    return s;
+}
+PM_DEV unsigned block_sum_u(Sh& sh, unsigned v) {
+    v = pm::warp_sum(v);
+    if (pm::lane() == 0) sh.scan_tmp[pm::warp()] = v;
+    pm::sync();
+    unsigned s = 0;
+    for (int w = 0; w < kWarps; w++) s += sh.scan_tmp[w];
+    pm::sync();
+    return s;
+}
+// exclusive prefix of one value per thread (thread order); *total gets the block total
+PM_DEV unsigned block_excl_prefix_u(Sh& sh, unsigned v, unsigned* total) {
+    unsigned inc = pm::warp_incl_scan(v);
+    if (pm::lane() == 31) sh.scan_tmp[pm::warp()] = inc;
+    pm::sync();
+    unsigned base = 0, tot = 0;
+    for (int w = 0; w < kWarps; w++) {
+        unsigned t = sh.scan_tmp[w];
+        if (w < pm::warp()) base += t;
+        tot += t;
+    }
+    pm::sync();
+    *total = tot;
+    return base + inc - v;
+}
+PM_DEV double block_excl_prefix_d(Sh& sh, double v, double* total) {
+    double inc = pm::warp_incl_scan(v);
+    if (pm::lane() == 31) sh.red[pm::warp()] = inc;
+    pm::sync();
+    double base = 0.0, tot = 0.0;
+    for (int w = 0; w < kWarps; w++) {
+        double t = sh.red[w];
+        if (w < pm::warp()) base += t;
+        tot += t;
+    }
+    pm::sync();
+    *total = tot;
+    return base + (inc - v);
+}
+// in-place exclusive scan of arr[0..count) ; arr[count] = total.  count <= 2 * kThreads.
+PM_DEV unsigned block_scan_excl_array(Sh& sh, unsigned* arr, int count) {
+    int t = pm::tid();
+    int i0 = 2 * t, i1 = 2 * t + 1;
+    unsigned a = i0 < count ? arr[i0] : 0u, b = i1 < count ? arr[i1] : 0u;
+    unsigned tot;
+    unsigned ex = block_excl_prefix_u(sh, a + b, &tot);
+    if (i0 < count) arr[i0] = ex;
+    if (i1 < count) arr[i1] = ex + a;
+    if (t == 0) arr[count] = tot;
+    pm::sync();
+    return tot;
+}
+
+// ---- scratch arena: shared memory first, per-CTA global scratch when it does not fit ------
+struct Arena {
+    unsigned char* s_base;
+    unsigned s_cap, s_top;
+    unsigned char* g_base;
+    size_t g_cap, g_top;
+    int overflow;
+    PM_DEV void init(unsigned char* sb, unsigned sc, unsigned char* gb, size_t gc) {
+        s_base = sb; s_cap = sc; s_top = 0; g_base = gb; g_cap = gc; g_top = 0; overflow = 0;
+    }
+    PM_DEV void* alloc(size_t bytes) {
+        bytes = (bytes + 15) & ~(size_t)15;
+        if (bytes <= (size_t)(s_cap - s_top)) {
+            void* p = s_base + s_top;
+            s_top += (unsigned)bytes;
+            return p;
+        }
+        if (bytes <= g_cap - g_top) {
+            void* p = g_base + g_top;
+            g_top += bytes;
+            return p;
+        }
+        overflow = 1;
+        return g_base;  // never dereferenced meaningfully: the caller checks `overflow`
+    }
+    struct Mark { unsigned s; size_t g; };
+    PM_DEV Mark mark() const { Mark m; m.s = s_top; m.g = g_top; return m; }
+    PM_DEV void release(Mark m) { s_top = m.s; g_top = m.g; }
+};
+
+// ---- stable LSD radix sort of (key, value) pairs, ascending, 8 bits per pass ----------------
+// hist: kWarps * 256 counters.  Returns 0 when the sorted data ends in (keyA, valA), 1 for B.
+template <typename K>
+PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* valB, unsigned* hist, int n) {
+    const int w = pm::warp(), l = pm::lane(), t = pm::tid();
+    int tile = (n + kWarps - 1) / kWarps;
+    tile = (tile + 31) & ~31;
+    const int lo = w * tile, hi = min(n, lo + tile);
+    K* src = keyA; unsigned* sv = valA; K* dst = keyB; unsigned* dv = valB;
+    int where = 0;
+    for (int pass = 0; pass < (int)sizeof(K); pass++) {
+        const int shift = pass * 8;
+        for (int i = t; i < kWarps * 256; i += kThreads) hist[i] = 0;
+        pm::sync();
+        for (int base = lo; base < hi; base += 32) {
+            int i = base + l;
+            bool valid = i < hi;
+            unsigned d = valid ? (unsigned)((src[i] >> shift) & 0xff) : 256u + (unsigned)l;
+            unsigned m = pm::match_any(d);
+            if (valid && l == pm::ffs(m) - 1) hist[w * 256 + d] += (unsigned)pm::popc(m);
+            pm::syncwarp();
+        }
+        pm::sync();
+        unsigned total = 0;
+        if (t < 256) {
+            for (int ww = 0; ww < kWarps; ww++) {
+                unsigned c = hist[ww * 256 + t];
+                hist[ww * 256 + t] = total;
+                total += c;
+            }
+        }
+        int skip = pm::sync_or(t < 256 && total == (unsigned)n);
+        if (skip) continue;  // every key has the same digit: the pass is the identity
+        unsigned grand;
+        unsigned basep = block_excl_prefix_u(sh, total, &grand);
+        if (t < 256) {
+            for (int ww = 0; ww < kWarps; ww++) hist[ww * 256 + t] += basep;
+        }
+        pm::sync();
+        for (int base = lo; base < hi; base += 32) {
+            int i = base + l;
+            bool valid = i < hi;
+            K k = valid ? src[i] : (K)0;
+            unsigned d = valid ? (unsigned)((k >> shift) & 0xff) : 256u + (unsigned)l;
+            unsigned m = pm::match_any(d);
+            unsigned pos = 0;
+            if (valid) pos = hist[w * 256 + d] + (unsigned)pm::popc(m & lt_mask());
+            pm::syncwarp();
+            if (valid) {
+                dst[pos] = k;
+                dv[pos] = sv[i];
+                if (l == pm::ffs(m) - 1) hist[w * 256 + d] += (unsigned)pm::popc(m);
+            }
+            pm::syncwarp();
+        }
+        pm::sync();
+        K* tk = src; src = dst; dst = tk;
+        unsigned* tv = sv; sv = dv; dv = tv;
+        where ^= 1;
+    }
+    return where;
+}
+
+// ---- exact area of circle(0, r) ∩ rectangle — photutils geometry -------------------
+// Restates photutils/geometry/circular_overlap.pyx + core.pyx (photutils 0.7.x; the reference calls
+// CircularAperture(...).do_photometry(method="exact") at casgm.py:51-52, :66-67, :116-117, :333-336).
+PM_DEV double fsqrt0(double v) { return v > 0.0 ? sqrt(v) : 0.0; }
+PM_DEV double area_arc(double x1, double y1, double x2, double y2, double r) {
+    double a = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+    double theta = 2.0 * asin(0.5 * a / r);
+    return 0.5 * r * r * (theta - sin(theta));
+}
+PM_DEV double area_tri(double x1, double y1, double x2, double y2, double x3, double y3) {
+    return 0.5 * fabs(x1 * (y2 - y3) + x2 * (y3 - y1) + x3 * (y1 - y2));
+}
+// rectangle in the first quadrant (0 <= xmin, 0 <= ymin)
+PM_DEV_NOINLINE double overlap_core(double xmin, double ymin, double xmax, double ymax, double r) {
+    const double r2 = r * r;
+    if (xmin * xmin + ymin * ymin > r2) return 0.0;
+    if (xmax * xmax + ymax * ymax < r2) return (xmax - xmin) * (ymax - ymin);
+    const double d1 = fsqrt0(xmax * xmax + ymin * ymin);
+    const double d2 = fsqrt0(xmin * xmin + ymax * ymax);
+    if (d1 < r && d2 < r) {
+        double x1 = fsqrt0(r2 - ymax * ymax), y1 = ymax;
+        double x2 = xmax, y2 = fsqrt0(r2 - xmax * xmax);
+        return (xmax - xmin) * (ymax - ymin) - area_tri(x1, y1, x2, y2, xmax, ymax) + area_arc(x1, y1, x2, y2, r);
+    }
+    if (d1 < r) {
+        double x1 = xmin, y1 = fsqrt0(r2 - xmin * xmin);
+        double x2 = xmax, y2 = fsqrt0(r2 - xmax * xmax);
+        return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, x1, ymin, xmax, ymin) + area_tri(x1, y1, x2, ymin, x2, y2);
+    }
+    if (d2 < r) {
+        double x1 = fsqrt0(r2 - ymin * ymin), y1 = ymin;
+        double x2 = fsqrt0(r2 - ymax * ymax), y2 = ymax;
+        return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, xmin, y1, xmin, ymax) + area_tri(x1, y1, xmin, y2, x2, y2);
+    }
+    double x1 = fsqrt0(r2 - ymin * ymin), y1 = ymin;
+    double x2 = xmin, y2 = fsqrt0(r2 - xmin * xmin);
+    return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, x2, y2, xmin, ymin);
+}
+// unit pixel centred at (px, py) relative to the circle centre; any quadrant
+PM_DEV double overlap_pixel(double px, double py, double r) {
+    const double xmin = px - 0.5, xmax = px + 0.5, ymin = py - 0.5, ymax = py + 0.5;
+    double total = 0.0;
+#pragma unroll
+    for (int ix = 0; ix < 2; ix++) {
+        double xa, xb;
+        if (ix == 0) {
+            if (xmin >= 0.0) continue;
+            xa = xmin; xb = fmin(xmax, 0.0);
+        } else {
+            if (xmax <= 0.0) continue;
+            xa = fmax(xmin, 0.0); xb = xmax;
+        }
+#pragma unroll
+        for (int iy = 0; iy < 2; iy++) {
+            double ya, yb;
+            if (iy == 0) {
+                if (ymin >= 0.0) continue;
+                ya = ymin; yb = fmin(ymax, 0.0);
+            } else {
+                if (ymax <= 0.0) continue;
+                ya = fmax(ymin, 0.0); yb = ymax;
+            }
+            if (xa >= 0.0) {
+                if (ya >= 0.0) total += overlap_core(xa, ya, xb, yb, r);
+                else total += overlap_core(-yb, xa, -ya, xb, r);
+            } else {
+                if (ya >= 0.0) total += overlap_core(-xb, ya, -xa, yb, r);
+                else total += overlap_core(-xb, -yb, -xa, -ya, r);
+            }
+        }
+    }
+    return total;
+}
+// photutils weight of the pixel at integer offset (dx, dy) from the circle centre
+PM_DEV double circle_weight(int dx, int dy, double r) {
+    const double pr = 0.5 * sqrt(2.0);
+    double d = sqrt((double)(dx * dx + dy * dy));
+    if (d < r - pr) return 1.0;
+    if (d < r + pr) return overlap_pixel((double)dx, (double)dy, r);
+    return 0.0;
+}
+
+}  // namespace pmk

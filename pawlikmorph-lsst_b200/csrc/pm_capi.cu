@@ -1,0 +1,192 @@
+// pm_capi.cu — the C ABI of libpawlik_b200.so (include/pawlik_b200.h) and the kernel launches.
+//
+// Built by nvcc for sm_100a (the product).  The same file is also compiled by g++ with
+// -DPM_EMULATE against tests/emul (CPU test-suite only): then "launching" runs every CTA on the
+// fibre emulator and all pointers are host pointers.  The product library contains no CPU path.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "pm_kernels.cuh"
+
+using namespace pmk;
+
+#define PM_MAX_GRID 592   /* 148 SMs x 4: upper bound on resident CTAs, sizes the workspace */
+#define PM_WS_HEADER 256
+
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local char g_err[256] = "";
+
+#ifndef PM_EMULATE
+template <typename T> __global__ void __launch_bounds__(kThreads, 1) pm_analyse_kernel(const __grid_constant__ Params p) {
+    analyse_body<T>(p);
+}
+__global__ void __launch_bounds__(kThreads, 1)
+pm_aperpixmap_kernel(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out, unsigned smem_bytes) {
+    aperpixmap_body(n, rad, B, ns, frac, mask_out, smem_bytes);
+}
+static int g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
+static size_t g_smem_optin = 0;
+static int device_props() {
+    if (g_sm_count) return PM_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaGetDevice: %s", cudaGetErrorString(e)); return PM_ENODEV; }
+    int sm = 0, maj = 0, mnr = 0, optin = 0;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&mnr, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (sm <= 0) { snprintf(g_err, sizeof g_err, "no CUDA device"); return PM_ENODEV; }
+    g_cc_major = maj; g_cc_minor = mnr; g_smem_optin = (size_t)optin; g_sm_count = sm;
+    return PM_OK;
+}
+#else
+static int g_sm_count = 2, g_cc_major = 10, g_cc_minor = 0;
+static size_t g_smem_optin = 232448;
+static int device_props() { return PM_OK; }
+#endif
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// shared-memory size and CTAs per SM for (n, fs)
+static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
+    const unsigned fixed = smem_fixed_bytes(n, fs);
+    const unsigned cap1 = (unsigned)(g_smem_optin ? g_smem_optin : 232448);   // 227 KB
+    const unsigned cap2 = (cap1 + 1024) / 2 - 1024;                            // two CTAs per SM
+    int ctas = (fixed + 64 * 1024 <= cap2) ? 2 : 1;
+    ctas = env_int("PM_CTAS_PER_SM", ctas);
+    if (ctas < 1) ctas = 1;
+    unsigned per = (cap1 + 1024) / (unsigned)ctas - 1024;
+    per &= ~15u;
+    const int forced = env_int("PM_SMEM_BYTES", 0);
+    if (forced > 0) per = (unsigned)forced & ~15u;
+    if (per > cap1) per = cap1;
+    *smem = per;
+    *ctas_per_sm = ctas;
+}
+
+extern "C" {
+
+int pm_abi_version(void) { return PM_ABI_VERSION; }
+const char* pm_last_cuda_error(void) { return g_err; }
+uint64_t pm_launch_count(void) { return g_launches.load(); }
+
+int pm_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
+    int rc = device_props();
+    if (rc != PM_OK) return rc;
+    if (sm_count) *sm_count = g_sm_count;
+    if (cc_major) *cc_major = g_cc_major;
+    if (cc_minor) *cc_minor = g_cc_minor;
+    if (smem_optin) *smem_optin = g_smem_optin;
+    return PM_OK;
+}
+
+size_t pm_workspace_bytes(int64_t B, int n, int dtype) {
+    (void)dtype;
+    if (B <= 0 || n <= 0 || n > PM_MAX_N) return 0;
+    const unsigned long long grid = (unsigned long long)(B < PM_MAX_GRID ? B : PM_MAX_GRID);
+    return (size_t)(PM_WS_HEADER + grid * scratch_bytes_per_cta(n));
+}
+
+int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const double* sky, const double* sky_err,
+                     int filter_size, uint32_t flags, const pm_overrides_t* ov, const pm_outputs_t* out,
+                     pm_row_t* rows, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    g_err[0] = 0;
+    if (B == 0) return PM_OK;
+    if (!images || !rows || !workspace || B < 0) { snprintf(g_err, sizeof g_err, "null pointer / negative batch"); return PM_EINVAL; }
+    if (dtype != PM_F32 && dtype != PM_F64) { snprintf(g_err, sizeof g_err, "dtype must be PM_F32 or PM_F64"); return PM_EINVAL; }
+    if (n < 8 || n > PM_MAX_N) { snprintf(g_err, sizeof g_err, "n must be in [8, %d]", PM_MAX_N); return PM_EINVAL; }
+    if (filter_size < 1 || filter_size > 15 || (filter_size & 1) == 0 || n / filter_size < 1) {
+        snprintf(g_err, sizeof g_err, "filter_size must be odd, in 1..15 and <= n");   // pixmap.py:160-162
+        return PM_EINVAL;
+    }
+    if (ov && ov->starmask) { snprintf(g_err, sizeof g_err, "star masks are not supported yet"); return PM_EINVAL; }
+    if (B > 0x7fffffffLL) { snprintf(g_err, sizeof g_err, "batch too large"); return PM_EINVAL; }
+    if (workspace_bytes < pm_workspace_bytes(B, n, dtype)) { snprintf(g_err, sizeof g_err, "workspace too small"); return PM_ENOSPC; }
+    if (((uintptr_t)workspace & 15) != 0) { snprintf(g_err, sizeof g_err, "workspace must be 16-byte aligned"); return PM_EINVAL; }
+    int rc = device_props();
+    if (rc != PM_OK) return rc;
+
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.images = images; p.B = B; p.n = n; p.fs = filter_size; p.flags = flags;
+    p.sky = sky; p.sky_err = sky_err;
+    if (ov) p.ov = *ov;
+    if (out) p.out = *out;
+    p.rows = rows;
+    p.counter = (unsigned long long*)workspace;
+    p.scratch = (unsigned char*)workspace + PM_WS_HEADER;
+    p.scratch_per_cta = scratch_bytes_per_cta(n);
+    unsigned smem = 0;
+    int ctas = 1;
+    launch_shape(n, filter_size, &smem, &ctas);
+    if (smem < smem_fixed_bytes(n, filter_size) + 4096) { snprintf(g_err, sizeof g_err, "shared memory too small for n"); return PM_EINVAL; }
+    p.smem_bytes = smem;
+    long long grid = (long long)g_sm_count * ctas;
+    if (grid > PM_MAX_GRID) grid = PM_MAX_GRID;
+    if (grid > B) grid = B;
+    const int g_env = env_int("PM_GRID", 0);
+    if (g_env > 0 && g_env < grid) grid = g_env;
+
+#ifndef PM_EMULATE
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e = cudaMemsetAsync(p.counter, 0, PM_WS_HEADER, st);
+    if (e == cudaSuccess) {
+        if (dtype == PM_F32) {
+            e = cudaFuncSetAttribute(pm_analyse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) pm_analyse_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>(p);
+        } else {
+            e = cudaFuncSetAttribute(pm_analyse_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) pm_analyse_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>(p);
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_analyse_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
+#else
+    (void)cuda_stream;
+    memset(p.counter, 0, PM_WS_HEADER);
+    for (long long blk = 0; blk < grid; blk++) {
+        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { analyse_body<float>(p); });
+        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { analyse_body<double>(p); });
+    }
+#endif
+    g_launches.fetch_add(1);
+    return PM_OK;
+}
+
+int pm_aperpixmap_batch(int n, const double* rad, int64_t B, int nsubpix, double frac, uint8_t* mask_out,
+                        void* cuda_stream) {
+    g_err[0] = 0;
+    if (B == 0) return PM_OK;
+    if (!rad || !mask_out || B < 0 || n < 1 || n > PM_MAX_N || nsubpix < 1 || nsubpix > 32) {
+        snprintf(g_err, sizeof g_err, "bad argument");
+        return PM_EINVAL;
+    }
+    int rc = device_props();
+    if (rc != PM_OK) return rc;
+    const unsigned smem = aperpixmap_smem_bytes(n, nsubpix);
+    long long grid = B < 4LL * g_sm_count ? B : 4LL * g_sm_count;
+#ifndef PM_EMULATE
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e = cudaFuncSetAttribute(pm_aperpixmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        pm_aperpixmap_kernel<<<(unsigned)grid, kThreads, smem, st>>>(n, rad, B, nsubpix, frac, mask_out, smem);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_aperpixmap_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
+#else
+    (void)cuda_stream;
+    for (long long blk = 0; blk < grid; blk++)
+        pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { aperpixmap_body(n, rad, B, nsubpix, frac, mask_out, smem); });
+#endif
+    g_launches.fetch_add(1);
+    return PM_OK;
+}
+
+}  // extern "C"

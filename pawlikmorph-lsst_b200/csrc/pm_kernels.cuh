@@ -1,0 +1,1449 @@
+// pm_kernels.cuh — the per-cutout morphology kernel: one CTA per galaxy, persistent CTAs
+// pulling galaxy indices from a work counter.  Phases follow the dataflow of the reference's
+// main.py:421-495 (pixelmap -> rmax/aperture -> minapix -> calcA x3 -> r20/r80/C -> gini/m20 -> S).
+//
+// Data layout in shared memory (per CTA): three n x n bit planes (segmap, its 9x9 dilation,
+// the aperture disc), the (n, filterSize) index tables, and an arena that holds the per-cutout
+// working set (raster list of segmap pixels, sort buffers, the masked window of the image over
+// the segmap bounding box, the folded radial table).  Anything that does not fit the arena
+// spills to a per-CTA slice of the caller's workspace in HBM (L2-resident in practice).
+// The image itself stays in global memory: it is streamed once from HBM by the pixelmap phase
+// and later phases re-touch only small parts of it through L1/L2.
+#pragma once
+#include "../../include/pawlik_b200.h"
+#include "pm_block.cuh"
+
+namespace pmk {
+
+struct Params {
+    const void* images;
+    long long B;
+    int n, fs;
+    unsigned flags;
+    const double* sky;
+    const double* sky_err;
+    pm_overrides_t ov;
+    pm_outputs_t out;
+    pm_row_t* rows;
+    unsigned char* scratch;       // per-CTA global scratch, scratch_per_cta bytes each
+    unsigned long long scratch_per_cta;
+    unsigned long long* counter;  // work counter (zeroed by the host before the launch)
+    unsigned smem_bytes;          // dynamic shared memory given to the kernel
+};
+
+struct Geo {
+    int n, m, fs, h, nw, mw, half, N;
+};
+PM_HOSTDEV Geo make_geo(int n, int fs) {
+    Geo g;
+    g.n = n; g.fs = fs; g.h = fs / 2;
+    g.m = n / fs;                    // int(n / filterSize), pixmap.py:171
+    g.nw = (n + 31) / 32;
+    g.mw = (g.m + 31) / 32;
+    g.half = n / 2;
+    g.N = n * n;
+    return g;
+}
+struct SmemMap {
+    unsigned sh, seg, dil, aper, rowoff, i0, tw, ri, rstart, arena, arena_bytes;
+};
+PM_HOSTDEV unsigned align16(unsigned v) { return (v + 15u) & ~15u; }
+PM_HOSTDEV SmemMap make_smem_map(const Geo& g, unsigned total) {
+    SmemMap s;
+    unsigned o = 0;
+    s.sh = o; o = align16(o + (unsigned)sizeof(Sh));
+    unsigned plane = (unsigned)(g.n * g.nw * 4);
+    unsigned zplane = (unsigned)(g.m * g.mw * 4);
+    if (zplane > plane) plane = zplane;   // cannot happen (m <= n) but keep the aliasing safe
+    s.seg = o; o += plane;
+    s.dil = o; o += plane;
+    s.aper = o; o += plane;
+    s.rowoff = o; o = align16(o + (unsigned)(g.n + 1) * 4);
+    s.tw = o; o = align16(o + (unsigned)g.m * 8);
+    s.i0 = o; o = align16(o + (unsigned)g.m * 2);
+    s.ri = o; o = align16(o + (unsigned)g.n * 2);
+    s.rstart = o; o = align16(o + (unsigned)(g.m + 1) * 2);
+    s.arena = o;
+    s.arena_bytes = total > o ? total - o : 0;
+    return s;
+}
+PM_HOSTDEV unsigned smem_fixed_bytes(int n, int fs) {
+    Geo g = make_geo(n, fs);
+    return make_smem_map(g, 0).arena;
+}
+// per-CTA global scratch: exact-filter planes (2 x 8 n^2), or list/sort/window spill, or the folded table
+PM_HOSTDEV unsigned long long scratch_bytes_per_cta(int n) {
+    return 64ull * (unsigned long long)n * (unsigned long long)n + 65536ull;
+}
+
+PM_DEV int refl(int i, int L) {  // scipy "reflect" (d c b a | a b c d | d c b a), any distance
+    if (i >= 0 && i < L) return i;
+    int p = 2 * L;
+    i %= p;
+    if (i < 0) i += p;
+    return i < L ? i : p - 1 - i;
+}
+
+// order-preserving integer keys -------------------------------------------------------------------
+PM_DEV uint32_t key_of(float x, double) {
+    if (x == 0.0f) x = 0.0f;  // -0.0 -> +0.0 (numpy compares them equal; asymmetry.py:94-95)
+    uint32_t b = pm::f2bits(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+PM_DEV uint64_t key_of(double x, double sky) {
+    double v = x - sky;
+    if (v == 0.0) v = 0.0;
+    uint64_t b = (uint64_t)pm::d2bits(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+PM_DEV double val_of_key(uint32_t k, double sky) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return (double)pm::bits2f(b) - sky;
+}
+PM_DEV double val_of_key(uint64_t k, double) {
+    uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return pm::bits2d((long long)b);
+}
+template <typename T> struct KeyT;
+template <> struct KeyT<float> { typedef uint32_t type; };
+template <> struct KeyT<double> { typedef uint64_t type; };
+PM_DEV float nan_of(float) { return pm::bits2f(0x7fc00000u); }
+PM_DEV double nan_of(double) { return pm::bits2d(0x7ff8000000000000ll); }
+
+// Per-cutout context (registers / local; identical in every thread) ---------------------------------
+template <typename T> struct Ctx {
+    Geo g;
+    Sh* sh;
+    unsigned* seg; unsigned* dil; unsigned* aper; unsigned* rowoff;
+    double* tw; uint16_t* i0; uint16_t* ri; uint16_t* rstart;
+    Arena ar;
+    const T* img;        // this cutout, [n, n]
+    double sky, thr;
+    unsigned flags;
+    // segmap statistics
+    int n_g, r0, r1, c0, c1;   // pixel count, bounding box (inclusive)
+    unsigned* posR;      // raster list of segmap pixels, (row << 16) | col
+    T* mw;               // masked window over the bounding box (NaN outside the segmap)
+    int bw;              // window width
+};
+
+template <typename T> PM_DEV double ld(const Ctx<T>& c, int r, int col) {
+    return (double)pm::ldg(c.img + (size_t)r * c.g.n + col);
+}
+PM_DEV bool bit_at(const unsigned* plane, int nw, int r, int c) {
+    return (plane[r * nw + (c >> 5)] >> (c & 31)) & 1u;
+}
+template <typename T> PM_DEV T mw_raw(const Ctx<T>& c, int r, int col) {
+    if (r < c.r0 || r > c.r1 || col < c.c0 || col > c.c1) return nan_of(T());
+    return c.mw[(r - c.r0) * c.bw + (col - c.c0)];
+}
+// masked, sky-subtracted value M[r, col] = (img - sky) * segmap (asymmetry.py:82-86, casgm.py:151)
+template <typename T> PM_DEV double mval(const Ctx<T>& c, int r, int col) {
+    T w = mw_raw(c, r, col);
+    return (w != w) ? 0.0 : (double)w - c.sky;
+}
+
+// ====================================================================================================
+// Phase 0 — tables that depend only on (n, filterSize): built once per CTA
+// ====================================================================================================
+template <typename T> PM_DEV void build_tables(Ctx<T>& c) {
+    const Geo& g = c.g;
+    // skimage.transform.resize (pixmap.py:171-173) == scipy.ndimage.zoom(order=1, grid_mode=True):
+    // source coordinate of output i:  cc = (i + 0.5) * (n / m) - 0.5 ; taps floor(cc), floor(cc) + 1
+    const double zoom = pm::ddiv((double)g.n, (double)g.m);
+    for (int i = pm::tid(); i < g.m; i += kThreads) {
+        double cc = pm::dsub(pm::dmul((double)i + 0.5, zoom), 0.5);
+        double f = floor(cc);
+        int a = (int)f;
+        if (a < 0) a = 0;
+        if (a > g.n - 1) a = g.n - 1;
+        c.i0[i] = (uint16_t)a;
+        c.tw[i] = pm::dsub(cc, f);
+    }
+    // skimage.transform.resize(order=0, mode="edge") (pixmap.py:211-212): nearest source index
+    const double zin = pm::ddiv((double)g.m, (double)g.n);
+    for (int i = pm::tid(); i < g.n; i += kThreads) {
+        double cc = pm::dsub(pm::dmul((double)i + 0.5, zin), 0.5);
+        int a = (int)floor(pm::dadd(cc, 0.5));
+        if (a < 0) a = 0;
+        if (a > g.m - 1) a = g.m - 1;
+        c.ri[i] = (uint16_t)a;
+    }
+    pm::sync();
+    // rstart[k] = first image row whose source row is >= k   (ri is non-decreasing)
+    for (int k = pm::tid(); k <= g.m; k += kThreads) {
+        int lo = 0, hi = g.n;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if ((int)c.ri[mid] >= k) hi = mid; else lo = mid + 1;
+        }
+        c.rstart[k] = (uint16_t)lo;
+    }
+    pm::sync();
+}
+
+// ====================================================================================================
+// Phase 1 — pixmap.pixelmap (pixmap.py:130-213)
+// ====================================================================================================
+// Bilinear combination exactly as scipy's NI_ZoomShift accumulates it (tap order, product order).
+PM_DEV double zoom_taps(double f00, double f01, double f10, double f11, double ta, double tb) {
+    const double wa0 = pm::dsub(1.0, ta), wb0 = pm::dsub(1.0, tb);
+    double s = 0.0;
+    s = pm::dadd(s, pm::dmul(pm::dmul(f00, wa0), wb0));
+    s = pm::dadd(s, pm::dmul(pm::dmul(f01, wa0), tb));
+    s = pm::dadd(s, pm::dmul(pm::dmul(f10, ta), wb0));
+    s = pm::dadd(s, pm::dmul(pm::dmul(f11, ta), tb));
+    return s;
+}
+
+// fast path: direct fs x fs sums.  Returns (through sh) min |Z - thr| and max |x| for the band test.
+template <typename T> PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* minabs, double* maxabs) {
+    const Geo& g = c.g;
+    const int fs = g.fs, h = g.h, n = g.n, m = g.m;
+    const double dfs = (double)fs;
+    double mn = 1e300, mx = 0.0;
+    int faint = 0, bad = 0;
+    const int cm = m / 2;
+    for (int task = pm::warp(); task < m * g.mw; task += kWarps) {
+        const int i = task / g.mw, w = task - i * g.mw;
+        const int j = w * 32 + pm::lane();
+        bool above = false;
+        if (j < m) {
+            const int a0 = c.i0[i], b0 = c.i0[j];
+            const int a1 = min(a0 + 1, n - 1), b1 = min(b0 + 1, n - 1);
+            const bool ra = (a1 != a0), rb = (b1 != b0);
+            double faa = 0.0, fab = 0.0, fba = 0.0, fbb = 0.0;
+            for (int k = 0; k <= fs; k++) {
+                const int rr = refl(a0 - h + k, n);
+                const bool inA = k < fs, inB = ra ? (k >= 1) : (k < fs);
+                double sa = 0.0, sb = 0.0;  // row sums over the b0 / b1 windows
+                for (int q = 0; q <= fs; q++) {
+                    const int cc = refl(b0 - h + q, n);
+                    const double x = ld(c, rr, cc);
+                    mx = fmax(mx, fabs(x));
+                    if (!(fabs(x) <= 1.7e308)) bad = 1;
+                    if (q < fs) sa += x;
+                    if (rb ? (q >= 1) : (q < fs)) sb += x;
+                }
+                if (inA) { faa += sa; fab += sb; }
+                if (inB) { fba += sa; fbb += sb; }
+            }
+            faa = (faa / dfs) / dfs; fab = (fab / dfs) / dfs; fba = (fba / dfs) / dfs; fbb = (fbb / dfs) / dfs;
+            const double z = zoom_taps(faa, fab, fba, fbb, c.tw[i], c.tw[j]);
+            const double d = z - c.thr;
+            above = z > c.thr;
+            if (!(fabs(d) >= 0.0)) bad = 1;
+            mn = fmin(mn, fabs(d));
+            if (i == cm && j == cm) faint = (z < c.thr) ? 1 : 0;
+        }
+        unsigned bits = pm::ballot(above);
+        if (pm::lane() == 0) zb[i * g.mw + w] = bits;
+    }
+    if (bad) mn = 0.0;  // non-finite input: let the exact path decide
+    *minabs = block_min(*c.sh, mn);
+    *maxabs = block_max(*c.sh, mx);
+    *centre_faint = pm::sync_or(faint);
+}
+
+// exact path: scipy.ndimage.uniform_filter's running-sum recurrence, axis 0 then axis 1,
+// bit-for-bit.  G and F are n x n float64 planes in the per-CTA global scratch.
+template <typename T> PM_DEV void pixelmap_exact(Ctx<T>& c, unsigned* zb, int* centre_faint, double* G, double* F) {
+    const Geo& g = c.g;
+    const int fs = g.fs, h = g.h, n = g.n, m = g.m;
+    const double dfs = (double)fs;
+    for (int col = pm::tid(); col < n; col += kThreads) {       // pass 1: along axis 0
+        double s = 0.0;
+        for (int l = 0; l < fs; l++) s = pm::dadd(s, ld(c, refl(l - h, n), col));
+        G[col] = pm::ddiv(s, dfs);
+        for (int k = 1; k < n; k++) {
+            const double pn = ld(c, refl(k + fs - 1 - h, n), col), po = ld(c, refl(k - 1 - h, n), col);
+            s = pm::dadd(s, pm::dsub(pn, po));
+            G[(size_t)k * n + col] = pm::ddiv(s, dfs);
+        }
+    }
+    pm::sync();
+    for (int row = pm::tid(); row < n; row += kThreads) {       // pass 2: along axis 1
+        const double* gr = G + (size_t)row * n;
+        double* fr = F + (size_t)row * n;
+        double s = 0.0;
+        for (int l = 0; l < fs; l++) s = pm::dadd(s, gr[refl(l - h, n)]);
+        fr[0] = pm::ddiv(s, dfs);
+        for (int k = 1; k < n; k++) {
+            s = pm::dadd(s, pm::dsub(gr[refl(k + fs - 1 - h, n)], gr[refl(k - 1 - h, n)]));
+            fr[k] = pm::ddiv(s, dfs);
+        }
+    }
+    pm::sync();
+    int faint = 0;
+    const int cm = m / 2;
+    for (int task = pm::warp(); task < m * g.mw; task += kWarps) {
+        const int i = task / g.mw, w = task - i * g.mw;
+        const int j = w * 32 + pm::lane();
+        bool above = false;
+        if (j < m) {
+            const int a0 = c.i0[i], b0 = c.i0[j];
+            const int a1 = min(a0 + 1, n - 1), b1 = min(b0 + 1, n - 1);
+            const double z = zoom_taps(F[(size_t)a0 * n + b0], F[(size_t)a0 * n + b1], F[(size_t)a1 * n + b0],
+                                       F[(size_t)a1 * n + b1], c.tw[i], c.tw[j]);
+            above = z > c.thr;
+            if (i == cm && j == cm) faint = (z < c.thr) ? 1 : 0;
+        }
+        unsigned bits = pm::ballot(above);
+        if (pm::lane() == 0) zb[i * g.mw + w] = bits;
+    }
+    *centre_faint = pm::sync_or(faint);
+}
+
+// 8-connected grow from the centre of the m x m grid (pixmap.py:182-208), bit-parallel
+PM_DEV unsigned fill_runs(unsigned A, unsigned S) {
+    unsigned up = (((A + S) ^ A) & A) | S;
+    unsigned rA = pm::brev(A), rS = pm::brev(S);
+    unsigned dn = pm::brev((((rA + rS) ^ rA) & rA) | rS);
+    return up | dn;
+}
+PM_DEV unsigned spread_row(const unsigned* gb, int mw, int i, int w) {
+    const unsigned* row = gb + i * mw;
+    unsigned v = row[w];
+    unsigned s = v | (v << 1) | (v >> 1);
+    if (w > 0) s |= row[w - 1] >> 31;
+    if (w + 1 < mw) s |= row[w + 1] << 31;
+    return s;
+}
+PM_DEV void region_grow(const Geo& g, unsigned* zb, unsigned* gb) {
+    const int m = g.m, mw = g.mw, cm = m / 2;
+    for (int i = pm::tid(); i < m * mw; i += kThreads) gb[i] = 0;
+    pm::sync();
+    if (pm::tid() == 0) {
+        zb[cm * mw + (cm >> 5)] |= 1u << (cm & 31);   // the centre is always set (pixmap.py:184)
+        gb[cm * mw + (cm >> 5)] = 1u << (cm & 31);
+    }
+    pm::sync();
+    for (;;) {
+        int changed = 0;
+        for (int task = pm::tid(); task < m * mw; task += kThreads) {
+            const int i = task / mw, w = task - i * mw;
+            const unsigned A = zb[task];
+            if (A == 0) continue;
+            const unsigned cur = gb[task];
+            unsigned s = spread_row(gb, mw, i, w);
+            if (i > 0) s |= spread_row(gb, mw, i - 1, w);
+            if (i + 1 < m) s |= spread_row(gb, mw, i + 1, w);
+            s = (s & A) | cur;
+            if (s == 0) continue;
+            const unsigned nw_ = fill_runs(A, s);
+            if (nw_ != cur) { gb[task] = nw_; changed = 1; }
+        }
+        if (!pm::sync_or(changed)) break;
+    }
+}
+// nearest-neighbour upsample of the grown mask to n x n bits (pixmap.py:211-212)
+template <typename T> PM_DEV void upsample_mask(Ctx<T>& c, const unsigned* gb) {
+    const Geo& g = c.g;
+    for (int task = pm::tid(); task < g.m * g.nw; task += kThreads) {
+        const int mi = task / g.nw, w = task - mi * g.nw;
+        const unsigned* row = gb + mi * g.mw;
+        unsigned bits = 0;
+        const int cend = min(32, g.n - w * 32);
+        for (int b = 0; b < cend; b++) {
+            const int mj = c.ri[w * 32 + b];
+            bits |= ((row[mj >> 5] >> (mj & 31)) & 1u) << b;
+        }
+        for (int r = c.rstart[mi]; r < (int)c.rstart[mi + 1]; r++) c.seg[r * g.nw + w] = bits;
+    }
+    pm::sync();
+}
+// uint8 [n, n] plane <-> bit plane
+PM_DEV void load_plane_u8(const Geo& g, const uint8_t* src, unsigned* plane) {
+    for (int task = pm::warp(); task < g.n * g.nw; task += kWarps) {
+        const int r = task / g.nw, w = task - r * g.nw;
+        const int col = w * 32 + pm::lane();
+        int v = 0;
+        if (col < g.n) v = pm::ldg(src + (size_t)r * g.n + col) != 0;
+        unsigned bits = pm::ballot(v);
+        if (pm::lane() == 0) plane[task] = bits;
+    }
+    pm::sync();
+}
+PM_DEV void store_plane_u8(const Geo& g, const unsigned* plane, uint8_t* dst) {
+    // 4 pixels per thread-step; word stores when the destination is 4-byte aligned
+    const size_t total = (size_t)g.N;
+    const uintptr_t addr = (uintptr_t)dst;
+    const int head = (int)((4 - (addr & 3)) & 3);
+    for (int i = pm::tid(); i < head && (size_t)i < total; i += kThreads) {
+        int r = i / g.n, col = i - r * g.n;
+        dst[i] = bit_at(plane, g.nw, r, col) ? 1 : 0;
+    }
+    const size_t nwords = total > (size_t)head ? (total - head) / 4 : 0;
+    uint32_t* d32 = (uint32_t*)(dst + head);
+    for (size_t k = pm::tid(); k < nwords; k += kThreads) {
+        size_t f = head + 4 * k;
+        int r = (int)(f / g.n), col = (int)(f - (size_t)r * g.n);
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            v |= (bit_at(plane, g.nw, r, col) ? 1u : 0u) << (8 * b);
+            if (++col == g.n) { col = 0; r++; }
+        }
+        d32[k] = v;
+    }
+    for (size_t f = head + 4 * nwords + pm::tid(); f < total; f += kThreads) {
+        int r = (int)(f / g.n), col = (int)(f - (size_t)r * g.n);
+        dst[f] = bit_at(plane, g.nw, r, col) ? 1 : 0;
+    }
+}
+
+// returns status (PM_ST_OK or PM_ST_FAINT_CENTRE); fills c.seg
+template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
+    const Geo& g = c.g;
+    unsigned* zb = c.dil;   // the two m x m planes alias the dilation / aperture planes (not yet in use)
+    unsigned* gb = c.aper;
+    int faint = 0;
+    bool exact = (c.flags & PM_FORCE_EXACT_FILTER) != 0;
+    if (!exact) {
+        double mn, mx;
+        pixelmap_fast(c, zb, &faint, &mn, &mx);
+        // |Z_fast - Z_scipy| <= (2 n + fs^2 + 8) * max|x| * 2^-52 (running-sum error growth); x4 margin
+        const double band = 4.0 * (2.0 * g.n + (double)(g.fs * g.fs) + 8.0) * mx * 2.220446049250313e-16;
+        if (!(mn > band)) exact = true;
+    }
+    if (exact) {
+        pm::sync();
+        double* G = (double*)c.ar.g_base;
+        double* F = G + (size_t)g.N;
+        pixelmap_exact(c, zb, &faint, G, F);
+    }
+    if (faint) return PM_ST_FAINT_CENTRE;
+    region_grow(g, zb, gb);
+    upsample_mask(c, gb);
+    return PM_ST_OK;
+}
+
+// ====================================================================================================
+// Phase 2 — segmap statistics, raster list, keys; pixmap.checkPixelmapEdges, pixmap.calcRmax
+// ====================================================================================================
+struct SegStats {
+    double sum, m10, m01;   // Σ v, Σ row·v, Σ col·v  over segmap pixels (v = img - sky)
+    double vmax;            // max v over segmap pixels
+    int argmax;             // flat index of the first pixel attaining it
+    int edge;
+};
+
+template <typename T>
+PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    // per-row counts -> exclusive offsets
+    for (int r = pm::tid(); r < g.n; r += kThreads) {
+        unsigned cnt = 0;
+        for (int w = 0; w < g.nw; w++) cnt += (unsigned)pm::popc(c.seg[r * g.nw + w]);
+        c.rowoff[r] = cnt;
+    }
+    pm::sync();
+    block_scan_excl_array(sh, c.rowoff, g.n);
+    double s = 0.0, m10 = 0.0, m01 = 0.0, vmax = -1.7976931348623157e308;
+    int amax = 0x7fffffff;
+    for (int r = pm::warp(); r < g.n; r += kWarps) {
+        unsigned off = c.rowoff[r];
+        if (c.rowoff[r + 1] == off) continue;
+        for (int w = 0; w < g.nw; w++) {
+            const unsigned bits = c.seg[r * g.nw + w];
+            if (bits == 0) continue;
+            if ((bits >> pm::lane()) & 1u) {
+                const int col = w * 32 + pm::lane();
+                const unsigned o = off + (unsigned)pm::popc(bits & lt_mask());
+                const T x = pm::ldg(c.img + (size_t)r * g.n + col);
+                c.posR[o] = ((unsigned)r << 16) | (unsigned)col;
+                keys[o] = key_of(x, c.sky);
+                const double v = (double)x - c.sky;
+                s += v; m10 += (double)r * v; m01 += (double)col * v;
+                const int flat = r * g.n + col;
+                if (v > vmax || (v == vmax && flat < amax)) { vmax = v; amax = flat; }
+            }
+            off += (unsigned)pm::popc(bits);
+        }
+    }
+    double red[3] = {s, m10, m01};
+    block_sum<3>(sh, red);
+    st->sum = red[0]; st->m10 = red[1]; st->m01 = red[2];
+    const double bm = block_max(sh, vmax);
+    st->vmax = bm;
+    st->argmax = block_min_i(sh, (vmax == bm) ? amax : 0x7fffffff);
+}
+
+// bounding box + edge flag from the bit plane
+template <typename T> PM_DEV void phase_bbox(Ctx<T>& c, int* edge) {
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    for (int w = pm::tid(); w < g.nw; w += kThreads) sh.colmask[w] = 0;
+    pm::sync();
+    int rmin = 0x7fffffff, rmaxv = -1;
+    for (int task = pm::tid(); task < g.n * g.nw; task += kThreads) {
+        const unsigned bits = c.seg[task];
+        if (bits) {
+            const int r = task / g.nw, w = task - r * g.nw;
+            pm::atomic_or(&sh.colmask[w], bits);
+            rmin = min(rmin, r); rmaxv = max(rmaxv, r);
+        }
+    }
+    c.r0 = block_min_i(sh, rmin);
+    c.r1 = block_max_i(sh, rmaxv);   // the syncs inside also publish colmask
+    int c0 = 0x7fffffff, c1 = -1;
+    for (int w = 0; w < g.nw; w++) {
+        const unsigned bits = sh.colmask[w];
+        if (bits) {
+            if (c0 == 0x7fffffff) c0 = w * 32 + pm::ffs(bits) - 1;
+            c1 = w * 32 + 31 - pm::clz(bits);
+        }
+    }
+    c.c0 = c0; c.c1 = c1;
+    *edge = (c.r1 >= 0) && (c.r0 == 0 || c.r1 == g.n - 1 || c0 == 0 || c1 == g.n - 1);  // pixmap.py:91-127
+    pm::sync();
+}
+
+// first pixel (raster order) that is NOT in the segmap; N if none
+template <typename T> PM_DEV int first_nonseg(const Ctx<T>& c) {
+    const Geo& g = c.g;
+    for (int r = 0; r < g.n; r++) {
+        if (c.rowoff[r + 1] - c.rowoff[r] == (unsigned)g.n) continue;
+        for (int w = 0; w < g.nw; w++) {
+            unsigned z = ~c.seg[r * g.nw + w];
+            if (w == g.nw - 1 && (g.n & 31)) z &= (1u << (g.n & 31)) - 1u;
+            if (z) return r * g.n + w * 32 + pm::ffs(z) - 1;
+        }
+    }
+    return g.N;
+}
+
+// pixmap.calcRmax (pixmap.py:26-55): returns rmax^2 (integer) and the brightest pixel
+template <typename T> PM_DEV int phase_rmax2(Ctx<T>& c, const SegStats& st, int* cen_flat) {
+    const Geo& g = c.g;
+    int cen = st.argmax;
+    if (!(st.vmax > 0.0) && c.n_g < g.N) {   // np.argmax(image * segmap): zeros outside the map compete
+        const int fz = first_nonseg(c);
+        if (st.vmax < 0.0) cen = fz;
+        else cen = min(cen, fz);              // vmax == 0: first of {zero-valued map pixel, outside pixel}
+    }
+    const int cr = cen / g.n, cc = cen - cr * g.n;
+    int d2 = 0;
+    for (int i = pm::tid(); i < c.n_g; i += kThreads) {
+        const unsigned p = c.posR[i];
+        const int dr = (int)(p >> 16) - cr, dc = (int)(p & 0xffff) - cc;
+        d2 = max(d2, dr * dr + dc * dc);
+    }
+    *cen_flat = cen;
+    return block_max_i(*c.sh, d2);
+}
+
+// ====================================================================================================
+// apertures.aperpixmap (apertures.py:42-128) — float64 sub-sample test, as the reference evaluates it
+// ====================================================================================================
+// |coordinate| of sub-sample k (0..ns-1, counted outward) of the pixel at distance d >= 1 from index n//2:
+// the reference's vector is  q / ns - (n//2 + 1)  for q < (n//2) * ns,  zeros(ns),  and the mirrored copy.
+PM_DEV double sub_coord_sq(int d, int k, int ns, int half) {
+    if (d == 0) return 0.0;
+    const int i = half - d;                  // pixel index on the negative side
+    const int q = i * ns + (ns - 1 - k);     // k = 0 is the sample nearest the centre
+    const double v = pm::dsub(pm::ddiv((double)q, (double)ns), (double)(half + 1));
+    return pm::dmul(v, v);
+}
+// count of sub-sample pairs (k, l) with sqrt(x_k^2 + y_l^2) <= rad, via the squared threshold `a_star`
+PM_DEV int sub_count(const double* sq, int d, int e, int ns, double a_star) {
+    int cnt = 0;
+    for (int k = 0; k < ns; k++) {
+        const double a = sq[d * ns + k];
+        for (int l = 0; l < ns; l++) cnt += (pm::dadd(a, sq[e * ns + l]) <= a_star) ? 1 : 0;
+    }
+    return cnt;
+}
+// largest double `a` with sqrt(a) <= rad (sqrt is monotone and correctly rounded)
+PM_DEV double sqrt_threshold(double rad) {
+    if (!(rad >= 0.0)) return -1.0;
+    double a = pm::dmul(rad, rad);
+    if (!(a < 1.7e308)) return 1.7e308;
+    for (int it = 0; it < 8 && pm::dsqrt(a) > rad; it++) a = pm::bits2d(pm::d2bits(a) - 1);
+    for (int it = 0; it < 8; it++) {
+        const double nx = pm::bits2d(pm::d2bits(a) + 1);
+        if (pm::dsqrt(nx) <= rad) a = nx; else break;
+    }
+    return a;
+}
+// Builds the n x n aperture plane for radius `rad`.  `sq` ((dmax+1)*ns doubles) and `hw` (dmax+1 ints) are scratch.
+PM_DEV void build_aperture(const Geo& g, double rad, int ns, double frac, unsigned* plane, double* sq, int* hw) {
+    const int half = g.half;
+    const int dmax = half;   // |i - n//2| <= n//2
+    for (int i = pm::tid(); i < (dmax + 1) * ns; i += kThreads) sq[i] = sub_coord_sq(i / ns, i % ns, ns, half);
+    pm::sync();
+    const double a_star = sqrt_threshold(rad);
+    int need = 0;   // smallest count with count / ns^2 >= frac (apertures.py:122-123)
+    {
+        const double den = (double)(ns * ns);
+        while (need <= ns * ns && !(pm::ddiv((double)need, den) >= frac)) need++;
+    }
+    for (int d = pm::tid(); d <= dmax; d += kThreads) {
+        // the count is non-increasing in e: binary search for the largest e that still qualifies
+        int lo = -1, hi = dmax;   // invariant: qualifies(lo) (or lo == -1), !qualifies(hi + 1)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sub_count(sq, d, mid, ns, a_star) >= need) lo = mid; else hi = mid - 1;
+        }
+        hw[d] = lo;
+    }
+    pm::sync();
+    for (int task = pm::tid(); task < g.n * g.nw; task += kThreads) {
+        const int r = task / g.nw, w = task - r * g.nw;
+        const int d = r > half ? r - half : half - r;
+        const int e = hw[d];
+        unsigned bits = 0;
+        if (e >= 0) {
+            // columns [half - e, half + e] ∩ [0, n)
+            const int lo = max(half - e, 0), hi = min(half + e, g.n - 1);
+            const int a = max(lo - w * 32, 0), b = min(hi - w * 32, 31);
+            if (a <= b) bits = (b - a == 31) ? 0xffffffffu : (((1u << (b - a + 1)) - 1u) << a);
+        }
+        plane[task] = bits;
+    }
+    pm::sync();
+}
+
+// ====================================================================================================
+// Phase 3 — sort, gini / m20 (casgm.py:187-273), centroid candidates (asymmetry.py:89-108)
+// ====================================================================================================
+struct SortOut {
+    double gini, m20;
+    int n_cand, n_pos;
+};
+
+// sorted keys/positions ascending in (sk, sp); st = segmap statistics
+template <typename T>
+PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, const unsigned* sp, const SegStats& st,
+                                 SortOut* out) {
+    Sh& sh = *c.sh;
+    const Geo& g = c.g;
+    const int n = c.n_g;
+    const int chunk = (n + kThreads - 1) / kThreads;
+    const int lo = min(n, pm::tid() * chunk), hi = min(n, lo + chunk);
+    // ---- gini: Σ (2i - n - 1)|x_i| / (|mean| n (n - 1)), i = 1..n ascending (photutils.morphology.gini)
+    double gs = 0.0, loc = 0.0;
+    int npos = 0;
+    for (int i = lo; i < hi; i++) {
+        const double v = val_of_key(sk[i], c.sky);
+        gs += (double)(2 * (i + 1) - n - 1) * fabs(v);
+        loc += v;
+        npos += v > 0.0;
+    }
+    out->n_pos = (int)block_sum_u(sh, (unsigned)npos);
+    gs = block_sum1(sh, gs);
+    const double mean = st.sum / (double)n;
+    out->gini = gs / (fabs(mean) * (double)n * (double)(n - 1));
+    // ---- m20 threshold: first element of the ascending order of ALL N values (zeros outside the map
+    //      included) whose cumulative fraction exceeds 0.8  (casgm.py:261-263)
+    double tot_seq;
+    const double pre = block_excl_prefix_d(sh, loc, &tot_seq);
+    const int nzero = g.N - n;                 // zeros contributed by pixels outside the map
+    int first_rank = 0x7fffffff;
+    {
+        double cum = pre;
+        for (int i = lo; i < hi; i++) {
+            const double v = val_of_key(sk[i], c.sky);
+            cum += v;
+            if (cum / st.sum > 0.8) {
+                const int rank = (v < 0.0) ? i : i + nzero;
+                first_rank = min(first_rank, rank);
+                break;
+            }
+        }
+    }
+    // the block of outside zeros sits after the negatives: cumulative sum there = Σ negatives
+    int nneg = 0;
+    double negsum = 0.0;
+    for (int i = lo; i < hi; i++) {
+        const double v = val_of_key(sk[i], c.sky);
+        if (v < 0.0) { nneg++; negsum += v; }
+    }
+    nneg = (int)block_sum_u(sh, (unsigned)nneg);
+    negsum = block_sum1(sh, negsum);
+    if (nzero > 0 && (negsum / st.sum > 0.8)) first_rank = min(first_rank, nneg);
+    first_rank = block_min_i(sh, first_rank);
+    double thresh;
+    bool have_thresh = first_rank != 0x7fffffff;
+    if (!have_thresh) thresh = 0.0;
+    else if (nzero > 0 && first_rank >= nneg && first_rank < nneg + nzero) thresh = 0.0;
+    else thresh = val_of_key(sk[first_rank < nneg ? first_rank : first_rank - nzero], c.sky);
+    // ---- second moments about the flux centroid (casgm.py:253-271)
+    const double rc = st.m10 / st.sum, cc = st.m01 / st.sum;
+    double mt = 0.0, m2 = 0.0;
+    for (int i = pm::tid(); i < n; i += kThreads) {
+        const double v = val_of_key(sk[i], c.sky);
+        const unsigned p = sp[i];
+        const double dr = (double)(p >> 16) - rc, dc = (double)(p & 0xffff) - cc;
+        const double q = v * (dr * dr + dc * dc);
+        mt += q;
+        if (v >= thresh) m2 += q;
+    }
+    double red[2] = {mt, m2};
+    block_sum<2>(sh, red);
+    out->m20 = have_thresh ? log10(red[1] / red[0]) : nan_of(double());
+    // ---- candidates: walk the DESCENDING order while the running flux is below 20 % (asymmetry.py:101-108)
+    const double t20 = 0.2 * st.sum;
+    double dloc = 0.0;
+    for (int i = lo; i < hi; i++) {          // descending element i  ==  ascending element n - 1 - i
+        const double v = val_of_key(sk[n - 1 - i], c.sky);
+        if (v > 0.0) dloc += v;
+    }
+    double dtot;
+    const double dpre = block_excl_prefix_d(sh, dloc, &dtot);
+    unsigned nc = 0;
+    {
+        double run = dpre;   // flux accumulated BEFORE descending element i
+        for (int i = lo; i < hi; i++) {
+            const double v = val_of_key(sk[n - 1 - i], c.sky);
+            if (!(v > 0.0)) break;
+            if (i == 0 || run < t20) nc++;
+            run += v;
+        }
+    }
+    out->n_cand = (int)block_sum_u(sh, nc);
+}
+
+// ====================================================================================================
+// Phase 4 — asymmetry.minapix (asymmetry.py:50-129)
+// ====================================================================================================
+// disc test for the re-centred aperture of candidate (px, py): apertures.apercentre rolls the mask by
+// pix - (n//2 + 1) on both axes (cyclic), with pix = [col, row]  (asymmetry.py:106,118; apertures.py:231-238)
+PM_DEV bool aper_rolled(const unsigned* aper, const Geo& g, int r, int col, int d0, int d1) {
+    int rr = r - d0, cc = col - d1;
+    if (rr < 0) rr += g.n; else if (rr >= g.n) rr -= g.n;
+    if (cc < 0) cc += g.n; else if (cc >= g.n) cc -= g.n;
+    return bit_at(aper, g.nw, rr, cc);
+}
+
+template <typename T>
+PM_DEV void phase_minapix(Ctx<T>& c, const unsigned* sp_sorted, int n_cand, double* a_out, double* parts, int slices,
+                          int* best) {
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    const int n = c.n_g;
+    const int items = n_cand * slices;
+    for (int item = pm::warp(); item < items; item += kWarps) {
+        const int cand = item / slices, sl = item - cand * slices;
+        const unsigned pp = sp_sorted[n - 1 - cand];
+        const int py = (int)(pp >> 16), px = (int)(pp & 0xffff);
+        const int d0 = px - (g.half + 1), d1 = py - (g.half + 1);
+        double num = 0.0, den = 0.0;
+        for (int i = sl * 32 + pm::lane(); i < n; i += 32 * slices) {
+            const unsigned p = c.posR[i];
+            const int r = (int)(p >> 16), col = (int)(p & 0xffff);
+            const double v = (double)c.mw[(r - c.r0) * c.bw + (col - c.c0)] - c.sky;
+            const int tr = 2 * py - r, tc = 2 * px - col;
+            const bool inb = tr >= 0 && tr < g.n && tc >= 0 && tc < g.n;
+            double mt = 0.0;
+            bool t_in_seg = false;
+            if (inb) {
+                const T w = mw_raw(c, tr, tc);
+                if (w == w) { mt = (double)w - c.sky; t_in_seg = true; }
+            }
+            if (aper_rolled(c.aper, g, r, col, d0, d1)) { num += fabs(v - mt); den += fabs(v); }
+            // the mirrored position is outside the map: there M = 0 and M180 = v
+            if (inb && !t_in_seg && aper_rolled(c.aper, g, tr, tc, d0, d1)) num += fabs(v);
+        }
+        num = pm::warp_sum(num);
+        den = pm::warp_sum(den);
+        if (pm::lane() == 0) { parts[2 * item] = num; parts[2 * item + 1] = den; }
+    }
+    pm::sync();
+    double amin = 1.7976931348623157e308 * 2.0;   // +inf
+    int nan_idx = 0x7fffffff;
+    for (int cand = pm::tid(); cand < n_cand; cand += kThreads) {
+        double num = 0.0, den = 0.0;
+        for (int s = 0; s < slices; s++) { num += parts[2 * (cand * slices + s)]; den += parts[2 * (cand * slices + s) + 1]; }
+        const double a = num / (2.0 * den);
+        a_out[cand] = a;
+        if (a != a) nan_idx = min(nan_idx, cand); else amin = fmin(amin, a);
+    }
+    pm::sync();
+    nan_idx = block_min_i(sh, nan_idx);
+    if (nan_idx != 0x7fffffff) { *best = nan_idx; return; }   // np.argmin returns the first NaN
+    amin = block_min(sh, amin);
+    int idx = 0x7fffffff;
+    for (int cand = pm::tid(); cand < n_cand; cand += kThreads)
+        if (a_out[cand] == amin) { idx = cand; break; }
+    *best = block_min_i(sh, idx);
+}
+
+// ====================================================================================================
+// Phase 5 — asymmetry.calcA x3 (asymmetry.py:132-257): A + Abgr (image), As (180°) and As90 (90°) on the map
+// ====================================================================================================
+PM_DEV void dilate9(const Geo& g, const unsigned* seg, unsigned* dil, unsigned* tmp) {
+    // horizontal OR over offsets -4..+4 (zero border), then vertical OR over 9 rows   (asymmetry.py:220)
+    for (int task = pm::tid(); task < g.n * g.nw; task += kThreads) {
+        const int r = task / g.nw, w = task - r * g.nw;
+        const unsigned v = seg[task];
+        const unsigned lft = w > 0 ? seg[task - 1] : 0u, rgt = w + 1 < g.nw ? seg[task + 1] : 0u;
+        unsigned o = v;
+#pragma unroll
+        for (int s = 1; s <= 4; s++) o |= (v << s) | (lft >> (32 - s)) | (v >> s) | (rgt << (32 - s));
+        if (w == g.nw - 1 && (g.n & 31)) o &= (1u << (g.n & 31)) - 1u;
+        tmp[task] = o;
+        (void)r;
+    }
+    pm::sync();
+    for (int task = pm::tid(); task < g.n * g.nw; task += kThreads) {
+        const int r = task / g.nw, w = task - r * g.nw;
+        unsigned o = 0;
+        for (int dr = -4; dr <= 4; dr++) {
+            const int rr = r + dr;
+            if (rr >= 0 && rr < g.n) o |= tmp[rr * g.nw + w];
+        }
+        dil[task] = o;
+    }
+    pm::sync();
+}
+
+struct BgrCtx {
+    const unsigned* dil;
+    const unsigned* rowoff;   // exclusive prefix of dilated-mask pixels per row, [n + 1]
+    int nb, nm;
+};
+// rank of a mask pixel among mask pixels in raster order
+PM_DEV int mask_rank(const Geo& g, const BgrCtx& b, int r, int col) {
+    int k = (int)b.rowoff[r];
+    const unsigned* row = b.dil + r * g.nw;
+    const int w = col >> 5;
+    for (int i = 0; i < w; i++) k += pm::popc(row[i]);
+    k += pm::popc(row[w] & ((1u << (col & 31)) - 1u));
+    return k;
+}
+// flat index of the j-th (0-based) background pixel in raster order
+PM_DEV int bgr_select(const Geo& g, const BgrCtx& b, int j) {
+    int lo = 0, hi = g.n - 1;      // largest row r with  r*n - rowoff[r] <= j
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (mid * g.n - (int)b.rowoff[mid] <= j) lo = mid; else hi = mid - 1;
+    }
+    int k = j - (lo * g.n - (int)b.rowoff[lo]);
+    const unsigned* row = b.dil + lo * g.nw;
+    for (int w = 0; w < g.nw; w++) {
+        unsigned z = ~row[w];
+        if (w == g.nw - 1 && (g.n & 31)) z &= (1u << (g.n & 31)) - 1u;
+        const int cnt = pm::popc(z);
+        if (k < cnt) return lo * g.n + w * 32 + pm::nth_set_bit(z, k);
+        k -= cnt;
+    }
+    return lo * g.n;   // unreachable
+}
+// background image B of asymmetry.py:214-244 at (r, col)
+template <typename T> PM_DEV double bgr_value(const Ctx<T>& c, const BgrCtx& b, int r, int col) {
+    const Geo& g = c.g;
+    if (!bit_at(b.dil, g.nw, r, col)) return ld(c, r, col) - c.sky;
+    const int k = mask_rank(g, b, r, col) % b.nb;      // :227-239 truncate or tile
+    const int f = bgr_select(g, b, k);
+    const int fr = f / g.n;
+    return ld(c, fr, f - fr * g.n) - c.sky;
+}
+
+struct AsymOut { double A, Abgr, As, As90; };
+
+template <typename T>
+PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_plane) {
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    const bool do_img = (c.flags & (PM_DO_A | PM_DO_CAS)) != 0;
+    const bool do_shape = (c.flags & PM_DO_AS) != 0;
+    const bool noise = do_img && !(c.flags & PM_NO_NOISECORRECT);
+    const bool rot90 = (c.flags & PM_A_ANGLE90) != 0;
+    BgrCtx b;
+    b.dil = c.dil; b.rowoff = c.rowoff; b.nb = 0; b.nm = 0;
+    if (noise) {
+        dilate9(g, c.seg, c.dil, tmp_plane);
+        for (int r = pm::tid(); r < g.n; r += kThreads) {
+            unsigned cnt = 0;
+            for (int w = 0; w < g.nw; w++) cnt += (unsigned)pm::popc(c.dil[r * g.nw + w]);
+            c.rowoff[r] = cnt;
+        }
+        pm::sync();
+        b.nm = (int)block_scan_excl_array(sh, c.rowoff, g.n);
+        b.nb = g.N - b.nm;
+    }
+    const bool bgr_ok = noise && b.nb > 0 && b.nm > 1;      // asymmetry.py:225-226
+    double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};           // numA denA numB numS180 denS numS90
+    for (int task = pm::warp(); task < g.n * g.nw; task += kWarps) {
+        const unsigned bits = c.aper[task];
+        if (bits == 0) continue;
+        if (!((bits >> pm::lane()) & 1u)) continue;
+        const int r = task / g.nw, col = (task - r * g.nw) * 32 + pm::lane();
+        // 180°: (r, c) -> (2cy - r, 2cx - c);  90° (skimage, counter-clockwise): (cy + (c - cx), cx - (r - cy))
+        const int r180 = 2 * cy - r, c180 = 2 * cx - col;
+        const int r90 = cy + (col - cx), c90 = cx - (r - cy);
+        const bool in180 = r180 >= 0 && r180 < g.n && c180 >= 0 && c180 < g.n;
+        const bool in90 = r90 >= 0 && r90 < g.n && c90 >= 0 && c90 < g.n;
+        if (do_img) {
+            const double I = ld(c, r, col) - c.sky;
+            double Ir = 0.0;
+            if (rot90) { if (in90) Ir = ld(c, r90, c90) - c.sky; }
+            else if (in180) Ir = ld(c, r180, c180) - c.sky;
+            s[0] += fabs(I - Ir);
+            s[1] += fabs(I);
+            if (bgr_ok) {
+                // the background image is rotated about the SWAPPED centre (asymmetry.py:245)
+                const int rb = 2 * cx - r, cb = 2 * cy - col;
+                const double B = bgr_value(c, b, r, col);
+                double Br = 0.0;
+                if (rb >= 0 && rb < g.n && cb >= 0 && cb < g.n) Br = bgr_value(c, b, rb, cb);
+                s[2] += fabs(B - Br);
+            }
+        }
+        if (do_shape) {
+            const int v = bit_at(c.seg, g.nw, r, col) ? 1 : 0;
+            const int v180 = in180 && bit_at(c.seg, g.nw, r180, c180) ? 1 : 0;
+            const int v90 = in90 && bit_at(c.seg, g.nw, r90, c90) ? 1 : 0;
+            s[3] += (double)(v != v180);
+            s[4] += (double)v;
+            s[5] += (double)(v != v90);
+        }
+    }
+    block_sum<6>(sh, s);
+    out->A = -99.0; out->Abgr = -99.0; out->As = -99.0; out->As90 = -99.0;
+    if (do_img) {
+        const double den = 2.0 * s[1];
+        double A = s[0] / den, Ab = 0.0;
+        if (noise) {
+            if (bgr_ok) { Ab = s[2] / den; A = A - Ab; }
+            else Ab = -99.0;
+        }
+        out->A = A; out->Abgr = Ab;
+    }
+    if (do_shape) {
+        out->As = s[3] / (2.0 * s[4]);
+        out->As90 = s[5] / (2.0 * s[4]);
+    }
+}
+
+// ====================================================================================================
+// Phase 6 — casgm.calcR20_R80 / concentration (casgm.py:22-184)
+// ====================================================================================================
+// Folded radial table: T[a(a+1)/2 + b] = Σ of M over the (up to 8) pixels at offsets (±a, ±b), (±b, ±a)
+// from the integer centre, 0 <= b <= a <= A;  P = prefix of T along b within a column a.
+struct Fold {
+    double* T;
+    double* P;
+    int A;
+};
+PM_DEV int tri(int a, int b) { return a * (a + 1) / 2 + b; }
+
+template <typename T_> PM_DEV void build_fold(Ctx<T_>& c, int cx, int cy, Fold& f) {
+    const Geo& g = c.g;
+    const int A = f.A;
+    const int entries = (A + 1) * (A + 2) / 2;
+    for (int e = pm::tid(); e < entries; e += kThreads) {
+        // invert the triangular index
+        int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+        while (tri(a + 1, 0) <= e) a++;
+        while (tri(a, 0) > e) a--;
+        const int b = e - tri(a, 0);
+        double s = 0.0;
+        auto at = [&](int dr, int dc) {
+            const int r = cy + dr, col = cx + dc;
+            if (r >= 0 && r < g.n && col >= 0 && col < g.n) s += mval(c, r, col);
+        };
+        if (a == 0) at(0, 0);
+        else if (b == 0) { at(a, 0); at(-a, 0); at(0, a); at(0, -a); }
+        else if (a == b) { at(a, a); at(a, -a); at(-a, a); at(-a, -a); }
+        else { at(a, b); at(a, -b); at(-a, b); at(-a, -b); at(b, a); at(b, -a); at(-b, a); at(-b, -a); }
+        f.T[e] = s;
+    }
+    pm::sync();
+    for (int a = pm::tid(); a <= A; a += kThreads) {
+        double run = 0.0;
+        for (int b = 0; b <= a; b++) { run += f.T[tri(a, b)]; f.P[tri(a, b)] = run; }
+    }
+    pm::sync();
+}
+// exact-overlap aperture sum of M inside radius r: contribution of column a (lane-level work item)
+PM_DEV double fold_column(const Fold& f, int a, double r) {
+    const double pr = 0.5 * sqrt(2.0);
+    const double rin = r - pr, rout = r + pr;
+    // b_lo: first b with d(a, b) >= rin  (entries below are fully inside)
+    int b_lo = 0;
+    if (rin > 0.0) {
+        const double t = rin * rin - (double)a * (double)a;
+        if (t > 0.0) {
+            b_lo = (int)sqrt(t);
+            while (b_lo > 0 && !(sqrt((double)(a * a + (b_lo - 1) * (b_lo - 1))) < rin)) b_lo--;
+            while (sqrt((double)(a * a + b_lo * b_lo)) < rin) b_lo++;
+        }
+    }
+    double s = 0.0;
+    if (b_lo > 0) s = f.P[tri(a, min(b_lo - 1, a))];
+    for (int b = b_lo; b <= a; b++) {
+        const double d = sqrt((double)(a * a + b * b));
+        if (!(d < rout)) break;
+        s += f.T[tri(a, b)] * overlap_pixel((double)a, (double)b, r);
+    }
+    return s;
+}
+// F(r) for `nr` radii at once (nr <= kWarps): warp w evaluates radius w; results in sh.bc[0..nr)
+PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr) {
+    const int w = pm::warp();
+    if (w < nr) {
+        const double r = radii[w];
+        double s = 0.0;
+        const int amax = min(f.A, (int)(r + 2.0));
+        for (int a = pm::lane(); a <= amax; a += 32) s += fold_column(f, a, r);
+        s = pm::warp_sum(s);
+        if (pm::lane() == 0) sh.bc[w] = s;
+    }
+    pm::sync();
+}
+
+// scipy.optimize.brentq (Zeros/brentq.c), xtol = 2e-12, rtol = 4 eps, maxiter = 100, as a resumable state machine
+struct Brent {
+    double xpre, xcur, xblk, fpre, fcur, fblk, spre, scur;
+    double root;
+    int state;   // 0 = needs f(xcur), 1 = converged, 2 = sign error, 3 = no convergence
+    int iter;
+};
+PM_DEV void brent_init(Brent& b, double xa, double xb, double fa, double fb) {
+    b.xpre = xa; b.xcur = xb; b.fpre = fa; b.fcur = fb;
+    b.xblk = 0.0; b.fblk = 0.0; b.spre = 0.0; b.scur = 0.0; b.iter = 0; b.state = 0; b.root = 0.0;
+    if (fa == 0.0) { b.state = 1; b.root = xa; return; }
+    if (fb == 0.0) { b.state = 1; b.root = xb; return; }
+    if (signbit(fa) == signbit(fb)) { b.state = 2; return; }
+}
+// one iteration of the loop body up to (not including) the function evaluation; sets xcur to the next abscissa
+PM_DEV void brent_step(Brent& b) {
+    const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+    if (b.iter >= 100) { b.state = 3; return; }
+    b.iter++;
+    if (b.fpre != 0.0 && b.fcur != 0.0 && (signbit(b.fpre) != signbit(b.fcur))) {
+        b.xblk = b.xpre; b.fblk = b.fpre;
+        b.spre = b.scur = b.xcur - b.xpre;
+    }
+    if (fabs(b.fblk) < fabs(b.fcur)) {
+        b.xpre = b.xcur; b.xcur = b.xblk; b.xblk = b.xpre;
+        b.fpre = b.fcur; b.fcur = b.fblk; b.fblk = b.fpre;
+    }
+    const double delta = (xtol + rtol * fabs(b.xcur)) / 2.0;
+    const double sbis = (b.xblk - b.xcur) / 2.0;
+    if (b.fcur == 0.0 || fabs(sbis) < delta) { b.state = 1; b.root = b.xcur; return; }
+    if (fabs(b.spre) > delta && fabs(b.fcur) < fabs(b.fpre)) {
+        double stry;
+        if (b.xpre == b.xblk) {
+            stry = -b.fcur * (b.xcur - b.xpre) / (b.fcur - b.fpre);
+        } else {
+            const double dpre = (b.fpre - b.fcur) / (b.xpre - b.xcur);
+            const double dblk = (b.fblk - b.fcur) / (b.xblk - b.xcur);
+            stry = -b.fcur * (b.fblk * dblk - b.fpre * dpre) / (dblk * dpre * (b.fblk - b.fpre));
+        }
+        if (2.0 * fabs(stry) < fmin(fabs(b.spre), 3.0 * fabs(sbis) - delta)) { b.spre = b.scur; b.scur = stry; }
+        else { b.spre = sbis; b.scur = sbis; }
+    } else {
+        b.spre = sbis; b.scur = sbis;
+    }
+    b.xpre = b.xcur; b.fpre = b.fcur;
+    if (fabs(b.scur) > delta) b.xcur += b.scur;
+    else b.xcur += (sbis > 0.0 ? delta : -delta);
+}
+
+struct RadiiOut { double r20, r80; int ok; };
+
+template <typename T_>
+PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* out) {
+    Sh& sh = *c.sh;
+    out->ok = 0; out->r20 = -99.0; out->r80 = -99.0;
+    if (!(radius > 0.0) || !(radius < 1e6)) return;   // photutils: "'r' must be a positive scalar"
+    Arena::Mark mk = c.ar.mark();
+    Fold f;
+    f.A = (int)(radius + 0.5 * sqrt(2.0)) + 1;
+    const int entries = (f.A + 1) * (f.A + 2) / 2;
+    f.T = (double*)c.ar.alloc((size_t)entries * 8);
+    f.P = (double*)c.ar.alloc((size_t)entries * 8);
+    if (c.ar.overflow) { c.ar.release(mk); return; }
+    build_fold(c, cx, cy, f);
+    // total flux inside `radius` (casgm.py:51-52)
+    if (pm::tid() == 0) sh.rk[0] = radius;
+    // the walk radii (casgm.py:55-73): r_1 = R - δ, r_{k+1} = r_k - δ, δ = (R / 200) * 2
+    const double delta = (radius / 200.0) * 2.0;
+    int K = 0;   // number of walk radii that are > 0
+    {
+        double r = radius - delta;
+        while (K < 130 && r > 0.0) { K++; if (pm::tid() == 0) sh.rk[K] = r; r -= delta; }
+    }
+    pm::sync();
+    eval_flux(sh, f, sh.rk, 1);
+    const double total = sh.bc[0];
+    pm::sync();
+    // walk down in batches of kWarps radii until both fractions are bracketed
+    int k20 = -1, k80 = -1;     // first k with F(r_k)/total <= fraction
+    for (int base = 1; base <= K && (k20 < 0 || k80 < 0); base += kWarps) {
+        const int nr = min(kWarps, K - base + 1);
+        eval_flux(sh, f, sh.rk + base, nr);
+        for (int i = 0; i < nr; i++) {
+            const double frac = sh.bc[i] / total;
+            if (k80 < 0 && frac <= 0.8) k80 = base + i;
+            if (k20 < 0 && frac <= 0.2) k20 = base + i;
+        }
+        pm::sync();
+    }
+    if (k20 < 0 || k80 < 0) { c.ar.release(mk); return; }   // the reference walks to r <= 0 and raises
+    // brentq on [r_k, r_k + δ] for both fractions, in lock-step
+    Brent b[2];
+    const double fr[2] = {0.2, 0.8};
+    const int kk[2] = {k20, k80};
+    if (pm::tid() == 0) {
+        for (int q = 0; q < 2; q++) { sh.fk[2 * q] = sh.rk[kk[q]]; sh.fk[2 * q + 1] = sh.rk[kk[q]] + delta; }
+    }
+    pm::sync();
+    eval_flux(sh, f, sh.fk, 4);
+    for (int q = 0; q < 2; q++)
+        brent_init(b[q], sh.fk[2 * q], sh.fk[2 * q + 1], sh.bc[2 * q] / total - fr[q], sh.bc[2 * q + 1] / total - fr[q]);
+    pm::sync();
+    for (;;) {
+        int nact = 0;
+        int slot[2] = {-1, -1};
+        for (int q = 0; q < 2; q++) {
+            if (b[q].state == 0) brent_step(b[q]);
+            if (b[q].state == 0) { slot[q] = nact; if (pm::tid() == 0) sh.fk[nact] = b[q].xcur; nact++; }
+        }
+        if (nact == 0) break;
+        pm::sync();
+        eval_flux(sh, f, sh.fk, nact);
+        for (int q = 0; q < 2; q++)
+            if (slot[q] >= 0) b[q].fcur = sh.bc[slot[q]] / total - fr[q];
+        pm::sync();
+    }
+    c.ar.release(mk);
+    if (b[0].state != 1 || b[1].state != 1) return;
+    if (!(fabs(b[0].root) < 1.7e308) || !(fabs(b[1].root) < 1.7e308)) return;
+    out->r20 = b[0].root; out->r80 = b[1].root; out->ok = 1;
+}
+
+// ====================================================================================================
+// Phase 7 — casgm.smoothness (casgm.py:276-406)
+// ====================================================================================================
+// scipy.ndimage.uniform_filter window of size k at index i covers [i - k/2, i - k/2 + k - 1]
+template <typename T_> PM_DEV double box_mean(const Ctx<T_>& c, int r, int col, int k, int r_lo, int r_len, int c_lo, int c_len) {
+    // mean over the k x k window, "reflect" boundary of the sub-image [r_lo, r_lo + r_len) x [c_lo, c_lo + c_len)
+    const int h = k / 2;
+    double s = 0.0;
+    for (int dr = 0; dr < k; dr++) {
+        const int rr = r_lo + refl(r - r_lo - h + dr, r_len);
+        double rs = 0.0;
+        for (int dc = 0; dc < k; dc++) {
+            const int cc = c_lo + refl(col - c_lo - h + dc, c_len);
+            rs += ld(c, rr, cc) - c.sky;
+        }
+        s += rs;
+    }
+    return s / ((double)k * (double)k);
+}
+
+template <typename T_>
+PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r20, double sky_test) {
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    const int k = (int)r20;
+    if (k < 1 || !(rmax > r20)) return -99.0;   // uniform_filter(size=0) / CircularAnnulus(r_out <= r_in) raise upstream
+    // ---- annulus sums (casgm.py:319-336): weights = overlap(r_out) - overlap(r_in), exact
+    const int ixmin = (int)floor((double)cx - rmax + 0.5), ixmax = (int)ceil((double)cx + rmax + 0.5);
+    const int iymin = (int)floor((double)cy - rmax + 0.5), iymax = (int)ceil((double)cy + rmax + 0.5);
+    const int x0 = max(ixmin, 0), x1 = min(ixmax, g.n), y0 = max(iymin, 0), y1 = min(iymax, g.n);
+    const int bwid = x1 - x0, bhgt = y1 - y0;
+    double s[2] = {0.0, 0.0};   // Σ w I ,  Σ w max(I - Is, 0)
+    if (bwid > 0 && bhgt > 0) {
+        for (int i = pm::tid(); i < bwid * bhgt; i += kThreads) {
+            const int r = y0 + i / bwid, col = x0 + i % bwid;
+            const double w = circle_weight(col - cx, r - cy, rmax) - circle_weight(col - cx, r - cy, r20);
+            if (w == 0.0) continue;
+            const double I = ld(c, r, col) - c.sky;
+            const double Is = box_mean(c, r, col, k, 0, g.n, 0, g.n);
+            const double d = I - Is;
+            s[0] += w * I;
+            s[1] += w * (d < 0.0 ? 0.0 : d);
+        }
+    }
+    block_sum<2>(sh, s);
+    // ---- background box search (casgm.py:367-398); one candidate position per thread per round
+    // positions are visited in the order (size 32: y = 0, 2, ..; x = 0, 2, ..), then size 16, then 8.
+    int bx = 0, by = 0, bsz = 32, found = 0;
+    {
+        int size = 32;
+        for (;;) {
+            // candidate grid for this size: x in {0, 2, ..} with x < W - size, y likewise; (0, 0) always
+            const int nx = max(1, (g.n - size + 1) / 2), ny = max(1, (g.n - size + 1) / 2);
+            // number of x positions with 2*i < n - size  ->  ceil((n - size) / 2), at least 1
+            const int total = nx * ny;
+            int first = 0x7fffffff;
+            for (int base = 0; base < total && first == 0x7fffffff; base += kWarps) {
+                const int idx = base + pm::warp();
+                int ok = 0;
+                if (idx < total) {
+                    const int y = (idx / nx) * 2, x = (idx % nx) * 2;
+                    double bs = 0.0;
+                    for (int i = pm::lane(); i < size * size; i += 32) {
+                        const int r = y + i / size, col = x + i % size;
+                        if (r < g.n && col < g.n) {
+                            double v = bit_at(c.seg, g.nw, r, col) ? 0.0 : (ld(c, r, col) - c.sky);
+                            if (v == 0.0) v = -99.0;
+                            bs += v;
+                        }
+                    }
+                    bs = pm::warp_sum(bs);
+                    ok = fabs(sky_test) > fabs(bs / (double)(size * size));
+                }
+                first = block_min_i(sh, ok ? idx : 0x7fffffff);
+            }
+            if (first != 0x7fffffff) { by = (first / nx) * 2; bx = (first % nx) * 2; bsz = size; found = 1; break; }
+            if (size > 8) size /= 2;
+            else {
+                // gave up (casgm.py:397-398): the walk stops with x = 0 and y = first even y >= H - size
+                bsz = size; bx = 0;
+                by = 2 * ny;
+                break;
+            }
+        }
+    }
+    (void)found;
+    const int rows = max(0, min(bsz, g.n - by)), cols = max(0, min(bsz, g.n - bx));
+    double bd = 0.0;
+    for (int i = pm::tid(); i < rows * cols; i += kThreads) {
+        const int r = by + i / cols, col = bx + i % cols;
+        const double d = (ld(c, r, col) - c.sky) - box_mean(c, r, col, k, by, rows, bx, cols);
+        bd += d < 0.0 ? 0.0 : d;
+    }
+    bd = block_sum1(sh, bd);
+    const double bs = bd / (double)(rows * cols);
+    const double area = 3.141592653589793 * (rmax * rmax - r20 * r20);
+    return (s[1] - area * bs) / s[0];
+}
+
+// ====================================================================================================
+// The kernel
+// ====================================================================================================
+PM_DEV void row_defaults(pm_row_t& row) {
+    row.apix_col = row.apix_row = row.rmax = row.r20 = row.r80 = row.C = -99.0;
+    row.A = row.Abgr = row.S = row.As = row.As90 = row.gini = row.m20 = -99.0;
+    row.object_edge = 0.0; row.status = 0.0; row.n_candidates = 0.0;
+}
+
+template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long long b) {
+    typedef typename KeyT<T>::type K;
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    const size_t plane_elems = (size_t)g.N;
+    c.img = (const T*)p.images + (size_t)b * plane_elems;
+    c.sky = p.sky ? p.sky[b] : 0.0;
+    c.thr = p.ov.threshold_in ? p.ov.threshold_in[b] : c.sky + (p.sky_err ? p.sky_err[b] : 0.0);
+    c.flags = p.flags;
+    c.ar.s_top = 0; c.ar.g_top = 0; c.ar.overflow = 0;
+    pm_row_t row;
+    row_defaults(row);
+    uint8_t* seg_out = p.out.segmap_out ? p.out.segmap_out + (size_t)b * plane_elems : nullptr;
+    int32_t* sidx_out = p.out.sorted_idx_out ? p.out.sorted_idx_out + (size_t)b * plane_elems : nullptr;
+
+    // ---- pixelmap (main.py:421) or supplied segmap (main.py:428-439)
+    int status = PM_ST_OK;
+    int edge = 0;
+    if (p.ov.segmap_in) {
+        load_plane_u8(g, p.ov.segmap_in + (size_t)b * plane_elems, c.seg);
+    } else {
+        status = phase_pixelmap(c);
+        if (status != PM_ST_OK) {
+            for (int i = pm::tid(); i < g.n * g.nw; i += kThreads) c.seg[i] = 0;
+            pm::sync();
+        }
+    }
+    if (seg_out) store_plane_u8(g, c.seg, seg_out);
+    if (status == PM_ST_OK) phase_bbox(c, &edge);
+    if (status == PM_ST_OK && !p.ov.segmap_in) row.object_edge = (double)edge;   // main.py:427 (only on the pixelmap path)
+    if (p.ov.segmap_in && (p.flags & PM_STOP_AFTER_PIXELMAP)) row.object_edge = (double)edge;
+    bool done = status != PM_ST_OK || (p.flags & PM_STOP_AFTER_PIXELMAP);
+    if (!done && c.r1 < 0) { status = PM_ST_EMPTY_SEGMAP; done = true; }
+
+    if (!done) {
+        // ---- raster list + keys, statistics
+        for (int r = pm::tid(); r < g.n; r += kThreads) {   // n_g first (for the allocations)
+            unsigned cnt = 0;
+            for (int w = 0; w < g.nw; w++) cnt += (unsigned)pm::popc(c.seg[r * g.nw + w]);
+            c.rowoff[r] = cnt;
+        }
+        pm::sync();
+        unsigned ng = 0;
+        for (int r = pm::tid(); r < g.n; r += kThreads) ng += c.rowoff[r];
+        c.n_g = (int)block_sum_u(sh, ng);
+        const int n_g = c.n_g;
+        c.posR = (unsigned*)c.ar.alloc((size_t)n_g * 4);
+        unsigned* spA = (unsigned*)c.ar.alloc((size_t)n_g * 4);     // sorted positions end up here
+        Arena::Mark mk_sorted = c.ar.mark();
+        K* skA = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
+        Arena::Mark mk_keys = c.ar.mark();
+        K* skB = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
+        unsigned* spB = (unsigned*)c.ar.alloc((size_t)n_g * 4);
+        unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+        if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }   // workspace contract violated
+        SegStats st;
+        st.sum = st.m10 = st.m01 = st.vmax = 0.0; st.argmax = 0; st.edge = edge;
+        int cen_flat = 0, rmax2 = 0;
+        double rmax = 0.0;
+        SortOut so;
+        so.gini = so.m20 = -99.0; so.n_cand = 0; so.n_pos = 0;
+        if (!done) {
+            phase_list(c, skA, &st);
+            rmax2 = phase_rmax2(c, st, &cen_flat);
+            rmax = p.ov.radius_in ? p.ov.radius_in[b] : pm::dsqrt((double)rmax2);
+            row.rmax = rmax;
+            // ---- aperture plane (main.py:464) — uses the key buffers' neighbours as scratch before the sort
+            if (p.ov.apermask_in) {
+                load_plane_u8(g, p.ov.apermask_in + (size_t)b * plane_elems, c.aper);
+            } else {
+                Arena::Mark mk = c.ar.mark();
+                double* sq = (double*)c.ar.alloc((size_t)(g.half + 1) * 9 * 8);
+                int* hw = (int*)c.ar.alloc((size_t)(g.half + 1) * 4);
+                build_aperture(g, rmax, 9, 0.1, c.aper, sq, hw);
+                c.ar.release(mk);
+            }
+            if (p.out.apermask_out) store_plane_u8(g, c.aper, p.out.apermask_out + (size_t)b * plane_elems);
+            if (p.flags & PM_STOP_AFTER_RMAX) done = true;
+        }
+        if (!done) {
+            // ---- sort ascending by (value, flat index); the reverse is the canonical descending order
+            for (int i = pm::tid(); i < n_g; i += kThreads) spA[i] = c.posR[i];
+            pm::sync();
+            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g);
+            if (where) {
+                for (int i = pm::tid(); i < n_g; i += kThreads) { spA[i] = spB[i]; skA[i] = skB[i]; }
+                pm::sync();
+            }
+            c.ar.release(mk_keys);    // drop skB, spB, hist
+            phase_gini_m20_cands(c, skA, spA, st, &so);
+            if (p.flags & PM_DO_CAS) { row.gini = so.gini; row.m20 = so.m20; }
+            row.n_candidates = (double)so.n_cand;
+            if (sidx_out) {
+                for (int i = pm::tid(); i < g.N; i += kThreads) {
+                    int v = -1;
+                    if (i < so.n_pos) { const unsigned q = spA[n_g - 1 - i]; v = (int)(q >> 16) * g.n + (int)(q & 0xffff); }
+                    sidx_out[i] = v;
+                }
+            }
+            if (p.out.n_positive_out && pm::tid() == 0) p.out.n_positive_out[b] = so.n_pos;
+            c.ar.release(mk_sorted);  // drop skA (the sorted positions stay)
+            // ---- masked window over the bounding box
+            c.bw = c.c1 - c.c0 + 1;
+            const int bh = c.r1 - c.r0 + 1;
+            c.mw = (T*)c.ar.alloc((size_t)c.bw * bh * sizeof(T));
+            if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+        }
+        int cx = 0, cy = 0;
+        if (!done) {
+            const int bh = c.r1 - c.r0 + 1;
+            for (int i = pm::tid(); i < c.bw * bh; i += kThreads) {
+                const int r = c.r0 + i / c.bw, col = c.c0 + i % c.bw;
+                c.mw[i] = bit_at(c.seg, g.nw, r, col) ? pm::ldg(c.img + (size_t)r * g.n + col) : nan_of(T());
+            }
+            pm::sync();
+            // ---- minapix (main.py:467) or supplied centroid
+            if (p.ov.centroid_in) {
+                cx = (int)p.ov.centroid_in[2 * b]; cy = (int)p.ov.centroid_in[2 * b + 1];
+            } else if (so.n_cand == 0) {
+                status = PM_ST_NO_CANDIDATE; done = true;
+            } else {
+                Arena::Mark mk = c.ar.mark();
+                int slices = 1;
+                if (so.n_cand < kWarps) slices = kWarps / so.n_cand;
+                double* a_arr = (double*)c.ar.alloc((size_t)so.n_cand * 8);
+                double* parts = (double*)c.ar.alloc((size_t)so.n_cand * slices * 16);
+                int best = 0;
+                if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+                else {
+                    phase_minapix(c, spA, so.n_cand, a_arr, parts, slices, &best);
+                    if (p.out.cand_a_out) {
+                        for (int i = pm::tid(); i < p.out.cand_cap; i += kThreads)
+                            p.out.cand_a_out[(size_t)b * p.out.cand_cap + i] = i < so.n_cand ? a_arr[i] : -99.0;
+                    }
+                    const unsigned q = spA[n_g - 1 - best];
+                    cy = (int)(q >> 16); cx = (int)(q & 0xffff);
+                }
+                pm::sync();
+                c.ar.release(mk);
+            }
+        }
+        if (!done) {
+            row.apix_col = (double)cx; row.apix_row = (double)cy;
+            // ---- calcA x3 (main.py:470-478)
+            if (p.flags & (PM_DO_A | PM_DO_AS | PM_DO_CAS)) {
+                Arena::Mark mk = c.ar.mark();
+                unsigned* tmp = (unsigned*)c.ar.alloc((size_t)g.n * g.nw * 4);
+                AsymOut ao;
+                phase_calcA(c, cx, cy, &ao, tmp);
+                c.ar.release(mk);
+                if (p.flags & (PM_DO_A | PM_DO_CAS)) { row.A = ao.A; row.Abgr = ao.Abgr; }
+                if (p.flags & PM_DO_AS) { row.As = ao.As; row.As90 = ao.As90; }
+            }
+            // ---- r20, r80, C (main.py:491-492)
+            if (p.flags & PM_DO_CAS) {
+                RadiiOut ro;
+                phase_r20_r80(c, cx, cy, rmax, &ro);
+                if (ro.ok) {
+                    row.r20 = ro.r20; row.r80 = ro.r80;
+                    row.C = 5.0 * log10(ro.r80 / ro.r20);
+                } else {
+                    status = PM_ST_BAD_BRACKET;
+                }
+            }
+            // ---- smoothness (casgm.py:276; the call is commented out at main.py:494)
+            if (p.flags & PM_DO_S) {
+                const double r20 = p.ov.r20_in ? p.ov.r20_in[b] : row.r20;
+                const double skyt = p.ov.smooth_sky_in ? p.ov.smooth_sky_in[b] : c.sky;
+                if (status == PM_ST_OK && (p.ov.r20_in || (p.flags & PM_DO_CAS)))
+                    row.S = phase_smoothness(c, cx, cy, rmax, r20, skyt);
+            }
+        }
+    }
+    row.status = (double)status;
+    if (pm::tid() == 0) p.rows[b] = row;
+    pm::sync();
+}
+
+template <typename T> PM_DEV void analyse_body(const Params& p) {
+    unsigned char* smem = pm::dyn_smem();
+    Ctx<T> c;
+    c.g = make_geo(p.n, p.fs);
+    const SmemMap sm = make_smem_map(c.g, p.smem_bytes);
+    c.sh = (Sh*)(smem + sm.sh);
+    c.seg = (unsigned*)(smem + sm.seg); c.dil = (unsigned*)(smem + sm.dil); c.aper = (unsigned*)(smem + sm.aper);
+    c.rowoff = (unsigned*)(smem + sm.rowoff);
+    c.tw = (double*)(smem + sm.tw); c.i0 = (uint16_t*)(smem + sm.i0); c.ri = (uint16_t*)(smem + sm.ri);
+    c.rstart = (uint16_t*)(smem + sm.rstart);
+    c.ar.init(smem + sm.arena, sm.arena_bytes, p.scratch + (size_t)pm::block() * p.scratch_per_cta, (size_t)p.scratch_per_cta);
+    c.n_g = 0; c.r0 = c.c0 = 0; c.r1 = c.c1 = -1; c.posR = nullptr; c.mw = nullptr; c.bw = 0;
+    build_tables(c);
+    for (;;) {
+        if (pm::tid() == 0) c.sh->ia[0] = (int)pm::atomic_add(p.counter, 1ull);
+        pm::sync();
+        const long long b = (long long)c.sh->ia[0];
+        pm::sync();
+        if (b >= p.B) break;
+        analyse_one(c, p, b);
+    }
+}
+
+// apertures.aperpixmap for a batch of radii (one CTA per mask)
+PM_DEV void aperpixmap_body(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out,
+                            unsigned smem_bytes) {
+    unsigned char* smem = pm::dyn_smem();
+    const Geo g = make_geo(n, 1);
+    unsigned* plane = (unsigned*)smem;
+    double* sq = (double*)(smem + align16((unsigned)(g.n * g.nw * 4)));
+    int* hw = (int*)((unsigned char*)sq + align16((unsigned)((g.half + 1) * ns * 8)));
+    (void)smem_bytes;
+    for (long long b = pm::block(); b < B; b += pm::nblocks()) {
+        build_aperture(g, rad[b], ns, frac, plane, sq, hw);
+        store_plane_u8(g, plane, mask_out + (size_t)b * g.N);
+        pm::sync();
+    }
+}
+PM_HOSTDEV unsigned aperpixmap_smem_bytes(int n, int ns) {
+    const Geo g = make_geo(n, 1);
+    return align16((unsigned)(g.n * g.nw * 4)) + align16((unsigned)((g.half + 1) * ns * 8)) + align16((unsigned)((g.half + 1) * 4));
+}
+
+}  // namespace pmk

@@ -1,0 +1,109 @@
+// pm_platform.cuh — the handful of CUDA execution-model primitives the kernels use,
+// behind one small namespace so that the SAME kernel source can also be compiled by
+// g++ against tests/emul/cuda_emul.h (a fibre-based CTA emulator used only by the
+// CPU test-suite to exercise kernel logic on boxes without a GPU).  The product
+// library is always built by nvcc for sm_100a and contains none of the emulator.
+#pragma once
+#include <stdint.h>
+
+#if defined(PM_EMULATE)
+#include "cuda_emul.h"          // tests/emul — never part of libpawlik_b200.so
+#else
+#include <cuda_runtime.h>
+#include <math.h>
+#define PM_DEV __device__ __forceinline__
+#define PM_DEV_NOINLINE __device__ __noinline__
+#define PM_HOSTDEV __host__ __device__ inline
+#define PM_KERNEL __global__
+namespace pm {
+PM_DEV int tid() { return threadIdx.x; }
+PM_DEV int nthreads() { return blockDim.x; }
+PM_DEV int lane() { return threadIdx.x & 31; }
+PM_DEV int warp() { return threadIdx.x >> 5; }
+PM_DEV int nwarps() { return blockDim.x >> 5; }
+PM_DEV int block() { return blockIdx.x; }
+PM_DEV int nblocks() { return gridDim.x; }
+PM_DEV void sync() { __syncthreads(); }
+PM_DEV int sync_or(int p) { return __syncthreads_or(p); }
+PM_DEV void syncwarp() { __syncwarp(); }
+PM_DEV unsigned ballot(int p) { return __ballot_sync(0xffffffffu, p); }
+PM_DEV unsigned match_any(unsigned v) { return __match_any_sync(0xffffffffu, v); }
+template <typename T> PM_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <typename T> PM_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <typename T> PM_DEV T shfl_up(T v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+template <typename T> PM_DEV T shfl_down(T v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+// warp-wide reductions / scans (the emulator implements these in one rendez-vous)
+PM_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+PM_DEV double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+PM_DEV double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+PM_DEV unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+PM_DEV int warp_sum(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
+PM_DEV unsigned warp_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+PM_DEV unsigned warp_min(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+PM_DEV int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+PM_DEV int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+PM_DEV unsigned warp_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+// inclusive prefix sums across the warp
+PM_DEV unsigned warp_incl_scan(unsigned v) {
+    int l = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+        if (l >= o) v += t;
+    }
+    return v;
+}
+PM_DEV double warp_incl_scan(double v) {
+    int l = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (l >= o) v += t;
+    }
+    return v;
+}
+PM_DEV int popc(unsigned v) { return __popc(v); }
+PM_DEV int clz(unsigned v) { return __clz(v); }
+PM_DEV int ffs(unsigned v) { return __ffs(v); }
+PM_DEV unsigned brev(unsigned v) { return __brev(v); }
+// position (0-based) of the k-th (0-based) set bit of v; 32 if there is none
+PM_DEV int nth_set_bit(unsigned v, int k) {
+    unsigned r = __fns(v, 0, k + 1);
+    return r == 0xffffffffu ? 32 : (int)r;
+}
+template <typename T> PM_DEV T ldg(const T* p) { return __ldg(p); }
+PM_DEV unsigned atomic_add(unsigned* p, unsigned v) { return atomicAdd(p, v); }
+PM_DEV unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
+PM_DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+// IEEE-exact, never contracted into FMA (bit-parity with numpy/scipy where it matters)
+PM_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+PM_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
+PM_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+PM_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+PM_DEV double dsqrt(double a) { return __dsqrt_rn(a); }
+PM_DEV long long d2bits(double a) { return __double_as_longlong(a); }
+PM_DEV double bits2d(long long a) { return __longlong_as_double(a); }
+PM_DEV unsigned f2bits(float a) { return __float_as_uint(a); }
+PM_DEV float bits2f(unsigned a) { return __uint_as_float(a); }
+// hint: pull [p, p+bytes) towards L2 ahead of use (bytes multiple of 16, p 16-byte aligned)
+PM_DEV void prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+PM_DEV unsigned char* dyn_smem() {
+    extern __shared__ __align__(16) unsigned char pm_dyn_smem[];
+    return pm_dyn_smem;
+}
+}  // namespace pm
+#endif

@@ -1,0 +1,198 @@
+// cuda_emul.h — TEST INFRASTRUCTURE ONLY.
+//
+// A tiny CTA emulator: every CUDA thread of a block is a fibre run round-robin on
+// one OS thread; __syncthreads and the warp collectives are rendez-vous points.
+// It lets the CPU test-suite (pytest -m "not gpu") compile the kernel sources of
+// pawlikmorph-lsst_b200/csrc with g++ and compare their logic with the oracle on
+// boxes that have no GPU.  It is NOT a CPU fallback: the product package never
+// loads it, and libpawlik_b200.so is nvcc-only.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+#include <vector>
+
+#define PM_DEV inline
+#define PM_DEV_NOINLINE __attribute__((noinline))
+#define PM_HOSTDEV inline
+#define PM_KERNEL
+
+namespace pm_emul {
+struct Fiber {
+    void* sp = nullptr;
+    char* stack = nullptr;
+    bool done = false;
+};
+struct WarpState {
+    uint64_t slot[2][32];
+    int arrived[2] = {0, 0};
+    unsigned long long gen = 0;  // completed collectives
+};
+struct Block {
+    int nthreads = 0, block_id = 0, nblocks = 0;
+    std::vector<Fiber> fibers;
+    std::vector<WarpState> warps;
+    std::vector<unsigned long long> wgen;  // per-thread count of warp collectives entered
+    unsigned char* smem = nullptr;
+    void* sched_sp = nullptr;
+    int cur = 0;
+    // block barrier
+    int bar_arrived = 0, bar_or = 0, bar_or_result = 0;
+    unsigned long long bar_gen = 0;
+    std::vector<unsigned long long> tgen;
+    unsigned long long progress = 0;
+    const std::function<void()>* body = nullptr;
+};
+extern thread_local Block* g_blk;
+extern "C" void pm_emul_swap(void** save_sp, void* load_sp);
+
+inline void yield_() {
+    Block* b = g_blk;
+    pm_emul_swap(&b->fibers[b->cur].sp, b->sched_sp);
+}
+
+void run_block(int block_id, int nblocks, int nthreads, size_t smem_bytes, const std::function<void()>& body);
+}  // namespace pm_emul
+
+namespace pm {
+using pm_emul::g_blk;
+PM_DEV int tid() { return g_blk->cur; }
+PM_DEV int nthreads() { return g_blk->nthreads; }
+PM_DEV int lane() { return g_blk->cur & 31; }
+PM_DEV int warp() { return g_blk->cur >> 5; }
+PM_DEV int nwarps() { return g_blk->nthreads >> 5; }
+PM_DEV int block() { return g_blk->block_id; }
+PM_DEV int nblocks() { return g_blk->nblocks; }
+
+PM_DEV int sync_or(int p) {
+    pm_emul::Block* b = g_blk;
+    int me = b->cur;
+    unsigned long long my_gen = b->tgen[me]++;
+    b->bar_or |= (p != 0);
+    b->bar_arrived++;
+    b->progress++;
+    if (b->bar_arrived == b->nthreads) {
+        b->bar_or_result = b->bar_or;
+        b->bar_or = 0;
+        b->bar_arrived = 0;
+        b->bar_gen = my_gen + 1;
+    }
+    while (b->bar_gen <= my_gen) pm_emul::yield_();
+    return b->bar_or_result;
+}
+PM_DEV void sync() { (void)sync_or(0); }
+
+// generic warp rendez-vous: publish a 64-bit value, return all 32 once everyone arrived
+PM_DEV void warp_exchange_(uint64_t mine, uint64_t out[32]) {
+    pm_emul::Block* b = g_blk;
+    int me = b->cur, w = me >> 5, l = me & 31;
+    pm_emul::WarpState& ws = b->warps[w];
+    unsigned long long my_gen = b->wgen[me]++;
+    int par = (int)(my_gen & 1);
+    ws.slot[par][l] = mine;
+    ws.arrived[par]++;
+    b->progress++;
+    int lanes = b->nthreads - w * 32 < 32 ? b->nthreads - w * 32 : 32;
+    if (ws.arrived[par] == lanes) {
+        ws.arrived[par] = 0;
+        ws.gen = my_gen + 1;
+    }
+    while (ws.gen <= my_gen) pm_emul::yield_();
+    memcpy(out, ws.slot[par], sizeof(uint64_t) * 32);
+}
+PM_DEV void syncwarp() { uint64_t o[32]; warp_exchange_(0, o); }
+PM_DEV unsigned ballot(int p) {
+    uint64_t o[32]; warp_exchange_(p != 0, o);
+    unsigned r = 0; for (int i = 0; i < 32; i++) r |= (unsigned)(o[i] & 1) << i; return r;
+}
+PM_DEV unsigned match_any(unsigned v) {
+    uint64_t o[32]; warp_exchange_(v, o);
+    unsigned r = 0; for (int i = 0; i < 32; i++) if ((unsigned)o[i] == v) r |= 1u << i; return r;
+}
+template <typename T> PM_DEV uint64_t to_bits_(T v) { uint64_t u = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&u, &v, sizeof(T)); return u; }
+template <typename T> PM_DEV T from_bits_(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
+template <typename T> PM_DEV T shfl(T v, int src) { uint64_t o[32]; warp_exchange_(to_bits_(v), o); return from_bits_<T>(o[src & 31]); }
+template <typename T> PM_DEV T shfl_xor(T v, int m) { uint64_t o[32]; warp_exchange_(to_bits_(v), o); return from_bits_<T>(o[(lane() ^ m) & 31]); }
+template <typename T> PM_DEV T shfl_up(T v, int d) { uint64_t o[32]; warp_exchange_(to_bits_(v), o); int s = lane() - d; return s < 0 ? v : from_bits_<T>(o[s]); }
+template <typename T> PM_DEV T shfl_down(T v, int d) { uint64_t o[32]; warp_exchange_(to_bits_(v), o); int s = lane() + d; return s > 31 ? v : from_bits_<T>(o[s]); }
+
+// warp reductions: one rendez-vous, then the same xor-butterfly order the GPU code uses
+template <typename T, typename F> PM_DEV T warp_tree_(T v, F f) {
+    uint64_t o[32]; warp_exchange_(to_bits_(v), o);
+    T a[32];
+    for (int i = 0; i < 32; i++) a[i] = from_bits_<T>(o[i]);
+    for (int off = 16; off > 0; off >>= 1) {
+        T b[32];
+        for (int i = 0; i < 32; i++) b[i] = f(a[i], a[i ^ off]);
+        for (int i = 0; i < 32; i++) a[i] = b[i];
+    }
+    return a[lane()];
+}
+PM_DEV double warp_sum(double v) { return warp_tree_(v, [](double x, double y) { return x + y; }); }
+PM_DEV double warp_max(double v) { return warp_tree_(v, [](double x, double y) { return fmax(x, y); }); }
+PM_DEV double warp_min(double v) { return warp_tree_(v, [](double x, double y) { return fmin(x, y); }); }
+PM_DEV unsigned warp_sum(unsigned v) { return warp_tree_(v, [](unsigned x, unsigned y) { return x + y; }); }
+PM_DEV int warp_sum(int v) { return warp_tree_(v, [](int x, int y) { return x + y; }); }
+PM_DEV unsigned warp_max(unsigned v) { return warp_tree_(v, [](unsigned x, unsigned y) { return x > y ? x : y; }); }
+PM_DEV unsigned warp_min(unsigned v) { return warp_tree_(v, [](unsigned x, unsigned y) { return x < y ? x : y; }); }
+PM_DEV int warp_max(int v) { return warp_tree_(v, [](int x, int y) { return x > y ? x : y; }); }
+PM_DEV int warp_min(int v) { return warp_tree_(v, [](int x, int y) { return x < y ? x : y; }); }
+PM_DEV unsigned warp_or(unsigned v) { return warp_tree_(v, [](unsigned x, unsigned y) { return x | y; }); }
+template <typename T> PM_DEV T warp_incl_scan_(T v) {
+    uint64_t o[32]; warp_exchange_(to_bits_(v), o);
+    T a[32];
+    for (int i = 0; i < 32; i++) a[i] = from_bits_<T>(o[i]);
+    for (int off = 1; off < 32; off <<= 1) {          // Hillis-Steele, same order as the GPU code
+        T b[32];
+        for (int i = 0; i < 32; i++) b[i] = i >= off ? a[i] + a[i - off] : a[i];
+        for (int i = 0; i < 32; i++) a[i] = b[i];
+    }
+    return a[lane()];
+}
+PM_DEV unsigned warp_incl_scan(unsigned v) { return warp_incl_scan_(v); }
+PM_DEV double warp_incl_scan(double v) { return warp_incl_scan_(v); }
+
+PM_DEV int popc(unsigned v) { return __builtin_popcount(v); }
+PM_DEV int clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+PM_DEV int ffs(unsigned v) { return __builtin_ffs((int)v); }
+PM_DEV unsigned brev(unsigned v) {
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+    v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+}
+PM_DEV int nth_set_bit(unsigned v, int k) {
+    for (int i = 0; i < 32; i++)
+        if ((v >> i) & 1u) { if (k == 0) return i; k--; }
+    return 32;
+}
+template <typename T> PM_DEV T ldg(const T* p) { return *p; }
+PM_DEV unsigned atomic_add(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+PM_DEV unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+PM_DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+// built with -ffp-contract=off: plain IEEE operations
+PM_DEV double dadd(double a, double b) { return a + b; }
+PM_DEV double dsub(double a, double b) { return a - b; }
+PM_DEV double dmul(double a, double b) { return a * b; }
+PM_DEV double ddiv(double a, double b) { return a / b; }
+PM_DEV double dsqrt(double a) { return sqrt(a); }
+PM_DEV long long d2bits(double a) { long long u; memcpy(&u, &a, 8); return u; }
+PM_DEV double bits2d(long long a) { double u; memcpy(&u, &a, 8); return u; }
+PM_DEV unsigned f2bits(float a) { unsigned u; memcpy(&u, &a, 4); return u; }
+PM_DEV float bits2f(unsigned a) { float u; memcpy(&u, &a, 4); return u; }
+PM_DEV void prefetch_l2(const void*, unsigned) {}
+PM_DEV unsigned char* dyn_smem() { return g_blk->smem; }
+}  // namespace pm
+
+// what kernels use from the CUDA headers
+#ifndef __CUDACC__
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+template <typename T> inline T min(T a, T b) { return a < b ? a : b; }
+template <typename T> inline T max(T a, T b) { return a > b ? a : b; }
+#endif

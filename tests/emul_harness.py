@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE: builds tests/emul/_build/libpawlik_emul.so (the kernel sources of the
+product compiled by g++ against the fibre CTA emulator) and calls it through the same C ABI
+with numpy (host) buffers.  Lets `pytest -m "not gpu"` exercise the kernel logic on a box
+without a GPU.  Not a product path: the package never imports this."""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "pawlikmorph-lsst_b200")
+BUILD = os.path.join(REPO, "tests", "emul", "_build")
+SO = os.path.join(BUILD, "libpawlik_emul.so")
+
+_spec = importlib.util.spec_from_file_location("_pm_abi", os.path.join(PKG, "_abi.py"))
+abi = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(abi)
+
+
+def _sources():
+    cs = os.path.join(PKG, "csrc")
+    return [os.path.join(cs, f) for f in os.listdir(cs)] + [os.path.join(REPO, "tests", "emul", f)
+                                                              for f in ("cuda_emul.h", "cuda_emul.cpp")] + \
+        [os.path.join(REPO, "include", "pawlik_b200.h")]
+
+
+def build(force=False):
+    os.makedirs(BUILD, exist_ok=True)
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in _sources()):
+        return SO
+    cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DPM_EMULATE",
+           "-I" + os.path.join(REPO, "tests", "emul"), "-I" + os.path.join(REPO, "include"),
+           "-x", "c++", os.path.join(PKG, "csrc", "pm_capi.cu"), os.path.join(REPO, "tests", "emul", "cuda_emul.cpp"),
+           "-o", SO]
+    subprocess.run(cmd, check=True)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = abi.declare(C.CDLL(build()))
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def analyse(images, sky, sky_err, filter_size=3, flags=abi.PM_DO_ALL, segmap_in=None, apermask_in=None,
+            centroid_in=None, radius_in=None, r20_in=None, threshold_in=None, smooth_sky_in=None,
+            want=("segmap", "sorted", "aper", "cand")):
+    """images [B,n,n] float32/float64 numpy.  Returns dict(rows=[B,16], segmap=..., sorted_idx=..., ...)."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    assert images.dtype in (np.float32, np.float64) and images.ndim == 3
+    B, n, _ = images.shape
+    dtype = abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64
+    f64 = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (B,) + np.shape(a)[1:] if np.ndim(a) else (B,)))
+    sky = f64(sky)
+    sky_err = f64(sky_err)
+    u8 = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a).astype(np.uint8).reshape(B, n, n))
+    keep = dict(seg=u8(segmap_in), ap=u8(apermask_in),
+                cen=None if centroid_in is None else np.ascontiguousarray(np.asarray(centroid_in, dtype=np.float64).reshape(B, 2)),
+                rad=f64(radius_in), r20=f64(r20_in), thr=f64(threshold_in), ssky=f64(smooth_sky_in))
+    ov = abi.Overrides(_p(keep["seg"]), None, _p(keep["ap"]), _p(keep["cen"]), _p(keep["rad"]), _p(keep["r20"]),
+                       _p(keep["thr"]), _p(keep["ssky"]))
+    res = {}
+    cap = 512
+    if "segmap" in want:
+        res["segmap"] = np.full((B, n, n), 255, np.uint8)
+    if "sorted" in want:
+        res["sorted_idx"] = np.full((B, n * n), -7, np.int32)
+        res["n_positive"] = np.full((B,), -7, np.int32)
+    if "aper" in want:
+        res["apermask"] = np.full((B, n, n), 255, np.uint8)
+    if "cand" in want:
+        res["cand_a"] = np.full((B, cap), -7.0, np.float64)
+    out = abi.Outputs(_p(res.get("segmap")), _p(res.get("sorted_idx")), _p(res.get("n_positive")),
+                      _p(res.get("apermask")), _p(res.get("cand_a")), cap)
+    rows = np.full((B, abi.ROW_DOUBLES), np.nan, np.float64)
+    wsb = L.pm_workspace_bytes(B, n, dtype)
+    ws = np.zeros(wsb // 8 + 2, np.float64)
+    rc = L.pm_analyse_batch(images.ctypes.data, dtype, B, n, _p(sky), _p(sky_err), filter_size, flags,
+                            C.byref(ov), C.byref(out), rows.ctypes.data, ws.ctypes.data, wsb, None)
+    abi.check(L, rc, "pm_analyse_batch")
+    res["rows"] = rows
+    return res
+
+
+def row_dict(rows, i):
+    return dict(zip(abi.ROW_FIELDS, rows[i]))
+
+
+def aperpixmap(n, rads, nsubpix=9, frac=0.1):
+    L = lib()
+    rads = np.ascontiguousarray(np.atleast_1d(np.asarray(rads, dtype=np.float64)))
+    out = np.full((len(rads), n, n), 255, np.uint8)
+    rc = L.pm_aperpixmap_batch(n, rads.ctypes.data, len(rads), nsubpix, frac, out.ctypes.data, None)
+    abi.check(L, rc, "pm_aperpixmap_batch")
+    return out
