@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — galaxies/s of the batched `-Aall -cas` (+S, Gini, M20) morphology hot path at 256x256.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (pm_analyse_batch: pixelmap -> rmax/aperture -> sort -> minapix ->
+calcA x3 -> r20/r80/C -> gini/m20 -> S) over the resident synthetic batch of this rank; for N > 1 every
+rank owns a contiguous shard of the galaxies (weak scaling: fixed galaxies per GPU) and the step ends
+with the all-gather of the [B, 16] result rows.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference algorithm on the host cores: the CPU oracle port
+(oracle/pm_oracle.py; the reference itself is pure Python and its third-party leaves are not installed,
+DESIGN.md) driven like `-par multi` (main.py:136-148) by a multiprocessing pool.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "galaxies/sec for -Aall -cas at 256^2"
+UNIT = "galaxies/s"
+FLAGS_ALL = 15
+
+
+def algorithmic_bytes(n, itemsize=4):
+    """image read once + uint8 pixelmap written + one 128-byte result row."""
+    return itemsize * n * n + n * n + 128
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_init():
+    import numpy as np
+
+    import synth
+    from oracle import pm_oracle as O
+    x = synth.make_batch(1, 64, 1).numpy()
+    O.analyse(x[0].astype(np.float64), synth.SKY, synth.SKY_ERR, 3)     # numba / import warm-up
+
+
+def _cpu_one(img):
+    import numpy as np
+
+    import synth
+    from oracle import pm_oracle as O
+    row, _, _ = O.analyse(img.astype(np.float64), synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL)
+    return row["status"]
+
+
+def cpu_pool_rate(images, procs):
+    """galaxies/s of the oracle port over `images` with a pool of `procs` workers (warm)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs, initializer=_cpu_init) as pool:
+        pool.map(_cpu_one, [images[0]] * procs)                           # every worker warm
+        t0 = time.perf_counter()
+        pool.map(_cpu_one, list(images), chunksize=1)
+        dt = time.perf_counter() - t0
+    return len(images) / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import synth
+    procs = os.cpu_count() or 1
+    S = args.cpu_sample or 8 * procs
+    images = synth.make_batch(S, args.n, 20261019 + 3000).numpy()
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(procs, initializer=_cpu_init) as pool:
+        pool.map(_cpu_one, [images[0]] * procs)
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_one, list(images), chunksize=1)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = S * len(times) / total
+    sample = f"{S} synthetic {args.n}x{args.n} cutouts per step (seed 20261019+3000), multiprocessing.Pool({procs})"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic Sersic+noise {args.n}x{args.n} float32 cutouts, -Aall -cas +S +Gini/M20 "
+                                   f"(BASELINE.json configs[2]), bounded sample", "filter_size": 3, "flags": FLAGS_ALL},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        try:
+            for ln in open(self.path):
+                p = [s.strip() for s in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import pawlikmorph_lsst_b200 as pm
+    import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    # ---- resident synthetic batch (per rank)
+    free, _ = torch.cuda.mem_get_info(dev)
+    per = n * n * 4
+    B = args.batch
+    cap = int((free - 6 * 2 ** 30) * 0.9 // per)
+    if B > cap:
+        B = max(1024, cap // 1024 * 1024)
+    t0 = time.perf_counter()
+    x = synth.make_batch(B, n, 20261019 + 1000 * 2 + rank, device=dev, chunk=2048)
+    torch.cuda.synchronize(dev)
+    gen_s = time.perf_counter() - t0
+    sky = torch.full((B,), synth.SKY, dtype=torch.float64, device=dev)
+    err = torch.full((B,), synth.SKY_ERR, dtype=torch.float64, device=dev)
+    rows = torch.empty((B, 16), dtype=torch.float64, device=dev)
+    table = torch.empty((B * world, 16), dtype=torch.float64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        pm.batch.analyse_batch(x, sky, err, 3, FLAGS_ALL, rows_out=rows, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(table, rows)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pm._lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record(stream)
+    fence()
+    launches = pm._lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+    kernel_ms = total_ms / args.steps          # one kernel launch per step (the gather is not a kernel of ours)
+    status = rows[:, 14]
+    n_ok = int((status == 0).sum().item())
+    mean_cands = float(rows[:, 15].mean().item())
+
+    # ---- end to end through the public host API: pinned host images -> rows on the host
+    E = min(args.e2e_batch, B)
+    xh = x[:E].cpu().pin_memory()
+    pm.batch.analyse_host(xh, synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL, device=dev, chunk=args.e2e_chunk)   # warm
+    fence()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rows_h = pm.batch.analyse_host(xh, synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL, device=dev, chunk=args.e2e_chunk)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * E * e2e_steps / e2e_s
+    assert np.array_equal(rows_h, rows[:E].cpu().numpy(), equal_nan=True), "e2e rows differ from the resident run"
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- roofline (HBM) for the one kernel of the step
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    abytes = algorithmic_bytes(n)
+    achieved = B * abytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_galaxy") and tj["dram_bytes_per_galaxy"] * B
+        except Exception:
+            traffic = None
+    # ---- CPU baseline (bounded sample, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        S = args.cpu_sample or 8 * procs
+        sample_imgs = x[:S].cpu().numpy()
+        rate, dt = cpu_pool_rate(sample_imgs, procs)
+        cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+               "sample": f"first {S} cutouts of the same synthetic batch, oracle port, multiprocessing.Pool({procs}), {dt:.1f} s"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{B} synthetic Sersic+noise {n}x{n} float32 cutouts per GPU resident in HBM "
+                                   f"({B * per / 2 ** 30:.1f} GiB > L2, no flush needed), -Aall -cas +S +Gini/M20 "
+                                   f"(BASELINE.json configs[2]); one CTA per galaxy, one launch per step",
+                       "galaxies_per_gpu": B, "n": n, "filter_size": 3, "flags": FLAGS_ALL,
+                       "parallelism": f"galaxy-sharded x{world}" + (" + all-gather of rows" if world > 1 else ""),
+                       "status_ok_fraction": n_ok / B, "mean_candidates": mean_cands, "gen_seconds": gen_s,
+                       "step_ms": step_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_galaxy": abytes,
+                         "kernel": "pm_analyse_kernel<float>", "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * per + 16 * E, "d2h_bytes_per_step": E * 128,
+                    "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PM_BENCH_BATCH", 65536)),
+                    help="galaxies resident per GPU (BASELINE configs[2] holds 262144: pass --batch 262144)")
+    ap.add_argument("--e2e-batch", type=int, default=8192)
+    ap.add_argument("--e2e-chunk", type=int, default=2048)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

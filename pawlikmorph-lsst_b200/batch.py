@@ -1,0 +1,197 @@
+"""Batched entry points: a whole batch of cutouts through the fused per-galaxy kernel.
+
+This is what replaces the reference's per-image driver loop (`main.py:136-170`,
+`_analyseImage` `main.py:218-501`, steps `:421-495`): one call per batch instead of one Python
+call chain per galaxy.  PyTorch is used for device memory, streams and `torch.distributed`
+only; the arithmetic is in libpawlik_b200.so.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import (PM_DO_A, PM_DO_ALL, PM_DO_AS, PM_DO_CAS, PM_DO_S, ROW_DOUBLES, ROW_FIELDS)  # noqa: F401
+from ._lib import lib
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def _per_galaxy(v, B, device, name):
+    if v is None:
+        return None
+    if not torch.is_tensor(v):
+        v = torch.as_tensor(np.asarray(v, dtype=np.float64))
+    v = v.to(device=device, dtype=torch.float64)
+    if v.ndim == 0:
+        v = v.expand(B)
+    v = v.contiguous()
+    if v.shape[0] != B:
+        raise ValueError(f"{name}: expected {B} values, got {tuple(v.shape)}")
+    return v
+
+
+def _mask(v, B, n, device, name):
+    if v is None:
+        return None
+    if not torch.is_tensor(v):
+        v = torch.as_tensor(np.asarray(v))
+    v = (v.to(device) != 0).to(torch.uint8).reshape(B, n, n).contiguous()
+    return v
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class BatchResult:
+    rows: torch.Tensor                      # [B, 16] float64, columns = ROW_FIELDS
+    segmap: Optional[torch.Tensor] = None   # [B, n, n] uint8
+    sorted_idx: Optional[torch.Tensor] = None
+    n_positive: Optional[torch.Tensor] = None
+    apermask: Optional[torch.Tensor] = None
+    cand_a: Optional[torch.Tensor] = None
+
+    def column(self, name):
+        return self.rows[:, ROW_FIELDS.index(name)]
+
+    def row_dict(self, i):
+        r = self.rows[i].tolist()
+        return dict(zip(ROW_FIELDS, r))
+
+
+def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segmap_in=None, apermask_in=None,
+                  centroid_in=None, radius_in=None, r20_in=None, threshold_in=None, smooth_sky_in=None,
+                  want_segmap=False, want_sorted=False, want_apermask=False, cand_cap=0, rows_out=None,
+                  stream=None):
+    """Run the hot path of main.py:421-495 on `images` [B, n, n] (CUDA tensor, float32 or float64,
+    sky still in).  Asynchronous on `stream` (default: the current torch stream).  Returns a
+    BatchResult whose tensors live on the same device."""
+    if not torch.is_tensor(images) or not images.is_cuda:
+        raise TypeError("analyse_batch needs a CUDA tensor (there is no CPU path)")
+    if images.ndim != 3 or images.shape[1] != images.shape[2]:
+        raise ValueError("images must be [B, n, n]")
+    if images.dtype not in (torch.float32, torch.float64):
+        raise TypeError("images must be float32 or float64")
+    images = images.contiguous()
+    dev = images.device
+    B, n = int(images.shape[0]), int(images.shape[1])
+    dtype = _abi.PM_F32 if images.dtype == torch.float32 else _abi.PM_F64
+    L = lib()
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st):
+            sky_t = _per_galaxy(sky, B, dev, "sky")
+            err_t = _per_galaxy(sky_err, B, dev, "sky_err")
+            keep = dict(seg=_mask(segmap_in, B, n, dev, "segmap_in"), ap=_mask(apermask_in, B, n, dev, "apermask_in"),
+                        rad=_per_galaxy(radius_in, B, dev, "radius_in"), r20=_per_galaxy(r20_in, B, dev, "r20_in"),
+                        thr=_per_galaxy(threshold_in, B, dev, "threshold_in"),
+                        ssky=_per_galaxy(smooth_sky_in, B, dev, "smooth_sky_in"), cen=None)
+            if centroid_in is not None:
+                cen = centroid_in if torch.is_tensor(centroid_in) else torch.as_tensor(np.asarray(centroid_in, dtype=np.float64))
+                keep["cen"] = cen.to(device=dev, dtype=torch.float64).reshape(B, 2).contiguous()
+            ov = _abi.Overrides(_ptr(keep["seg"]), None, _ptr(keep["ap"]), _ptr(keep["cen"]), _ptr(keep["rad"]),
+                                _ptr(keep["r20"]), _ptr(keep["thr"]), _ptr(keep["ssky"]))
+            res = BatchResult(rows=rows_out if rows_out is not None else torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev))
+            if res.rows.shape != (B, ROW_DOUBLES) or res.rows.dtype != torch.float64 or not res.rows.is_contiguous():
+                raise ValueError("rows_out must be a contiguous [B, 16] float64 tensor")
+            if want_segmap:
+                res.segmap = torch.empty((B, n, n), dtype=torch.uint8, device=dev)
+            if want_sorted:
+                res.sorted_idx = torch.empty((B, n * n), dtype=torch.int32, device=dev)
+                res.n_positive = torch.empty((B,), dtype=torch.int32, device=dev)
+            if want_apermask:
+                res.apermask = torch.empty((B, n, n), dtype=torch.uint8, device=dev)
+            if cand_cap:
+                res.cand_a = torch.empty((B, int(cand_cap)), dtype=torch.float64, device=dev)
+            out = _abi.Outputs(_ptr(res.segmap), _ptr(res.sorted_idx), _ptr(res.n_positive), _ptr(res.apermask),
+                               _ptr(res.cand_a), int(cand_cap))
+            if B == 0:
+                return res
+            wsb = L.pm_workspace_bytes(B, n, dtype)
+            ws = _workspace(dev, wsb)
+            rc = L.pm_analyse_batch(images.data_ptr(), dtype, B, n, _ptr(sky_t), _ptr(err_t), int(filter_size),
+                                    int(flags), C.byref(ov), C.byref(out), res.rows.data_ptr(), ws.data_ptr(), wsb,
+                                    C.c_void_p(st.cuda_stream))
+            _abi.check(L, rc, "pm_analyse_batch")
+            # keep the temporaries alive until the stream has consumed them
+            for t in list(keep.values()) + [sky_t, err_t, images, ws]:
+                if t is not None:
+                    t.record_stream(st)
+    return res
+
+
+def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="cuda:0", chunk=8192, **kw):
+    """The call a user of the reference's driver makes: HOST arrays in, HOST rows out.
+
+    `images` is a numpy array / CPU tensor [B, n, n]; every chunk is staged through pinned memory,
+    copied to the device, analysed and its rows copied back.  Returns a [B, 16] float64 numpy array
+    (columns = ROW_FIELDS)."""
+    dev = torch.device(device)
+    x = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.to(torch.float64) if x.dtype in (torch.int64, torch.uint64) else x.to(torch.float32)
+    B = x.shape[0]
+    sky = np.broadcast_to(np.asarray(sky, dtype=np.float64), (B,))
+    sky_err = np.broadcast_to(np.asarray(sky_err, dtype=np.float64), (B,))
+    rows = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    for s in range(0, B, chunk):
+        e = min(B, s + chunk)
+        xs = x[s:e]
+        if not xs.is_pinned():
+            xs = xs.pin_memory()
+        with torch.cuda.stream(copy_stream):
+            d = xs.to(dev, non_blocking=True)
+            r = analyse_batch(d, torch.from_numpy(sky[s:e].copy()), torch.from_numpy(sky_err[s:e].copy()),
+                              filter_size, flags, stream=copy_stream, **kw)
+            rows[s:e].copy_(r.rows, non_blocking=True)
+    copy_stream.synchronize()
+    return rows.numpy()
+
+
+# ---- multi-GPU: galaxies are independent, so the batch shards by galaxy (main.py:136-148 did the
+# same with a process pool); the only collective is the gather of the result rows. -----------------
+def shard_bounds(B, world_size, rank):
+    """Contiguous slice [lo, hi) of a batch of B galaxies owned by `rank`."""
+    base, rem = divmod(int(B), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_rows(rows_local, B_total, group=None):
+    """All-gather the per-rank result rows (contiguous shards in rank order) into [B_total, 16].
+    Works with the NCCL backend on CUDA tensors and with gloo on CPU tensors."""
+    import torch.distributed as dist
+    W = dist.get_world_size(group)
+    counts = [shard_bounds(B_total, W, r) for r in range(W)]
+    sizes = [hi - lo for lo, hi in counts]
+    if len(set(sizes)) == 1:
+        out = torch.empty((B_total, rows_local.shape[1]), dtype=rows_local.dtype, device=rows_local.device)
+        dist.all_gather_into_tensor(out, rows_local.contiguous(), group=group)
+        return out
+    mx = max(sizes)
+    pad = torch.zeros((mx, rows_local.shape[1]), dtype=rows_local.dtype, device=rows_local.device)
+    pad[:rows_local.shape[0]] = rows_local
+    parts = [torch.empty_like(pad) for _ in range(W)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def analyse_sharded(images_local, sky_local, sky_err_local, B_total, filter_size=3, flags=PM_DO_ALL, group=None, **kw):
+    """Each rank analyses its own contiguous shard (already resident on its GPU) and all ranks get
+    the full [B_total, 16] table.  Results do not depend on the world size."""
+    res = analyse_batch(images_local, sky_local, sky_err_local, filter_size, flags, **kw)
+    return gather_rows(res.rows, B_total, group=group)
