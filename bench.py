@@ -179,8 +179,9 @@ def run_ours(args):
     # ---- resident synthetic batch (per rank)
     free, _ = torch.cuda.mem_get_info(dev)
     per = n * n * 4
+    per_out = n * n + 128
     B = args.batch
-    cap = int((free - 6 * 2 ** 30) * 0.9 // per)
+    cap = int((free - 6 * 2 ** 30) * 0.9 // (per + per_out))
     if B > cap:
         B = max(1024, cap // 1024 * 1024)
     t0 = time.perf_counter()
@@ -190,11 +191,12 @@ def run_ours(args):
     sky = torch.full((B,), synth.SKY, dtype=torch.float64, device=dev)
     err = torch.full((B,), synth.SKY_ERR, dtype=torch.float64, device=dev)
     rows = torch.empty((B, 16), dtype=torch.float64, device=dev)
+    segmap = torch.empty((B, n, n), dtype=torch.uint8, device=dev)      # the pixelmap is an output of the path
     table = torch.empty((B * world, 16), dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream(dev)
 
     def step():
-        pm.batch.analyse_batch(x, sky, err, 3, FLAGS_ALL, rows_out=rows, stream=stream)
+        pm.batch.analyse_batch(x, sky, err, 3, FLAGS_ALL, rows_out=rows, segmap_out=segmap, stream=stream)
         if world > 1:
             dist.all_gather_into_tensor(table, rows)
 
@@ -206,6 +208,19 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     fence()
+    if args.phases and rank == 0:
+        # tuning aid: per-phase clock64() cycles summed over the CTAs of one extra (untimed) step
+        names = ("pixelmap", "list+window", "rmax+aperture", "sort", "gini/m20/cands", "minapix", "calcA:loop", "r20:brentq",
+                 "smoothness", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "pix:filter", "pix:grow", "pix:store")
+        buf = torch.zeros((592, 16), dtype=torch.int64, device=dev)
+        pm._lib.lib().pm_debug_phase_cycles(buf.data_ptr())
+        step()
+        torch.cuda.synchronize(dev)
+        pm._lib.lib().pm_debug_phase_cycles(None)
+        cyc = buf.sum(dim=0).cpu().numpy()[:16].astype(float)
+        tot = cyc.sum()
+        print("phase cycles per galaxy: " + ", ".join(f"{nm} {c / B:.0f} ({100 * c / tot:.1f}%)" for nm, c in zip(names, cyc))
+              + f"; total {tot / B:.0f}", file=sys.stderr, flush=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -315,6 +330,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=2048)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="print per-phase cycle shares to stderr (tuning aid)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -61,6 +61,7 @@ extern "C" {
 #define PM_STOP_AFTER_RMAX 0x400u     /* ... + calcRmax + aperpixmap */
 #define PM_A_ANGLE90 0x800u           /* calcA on the image with angle = 90 instead of 180 (asymmetry.py:132) */
 #define PM_NO_NOISECORRECT 0x1000u    /* calcA(..., noisecorrect=False): Abgr = 0, A not corrected */
+#define PM_NO_PREFETCH 0x2000u        /* tuning: do not prefetch the next cutout into L2 */
 
 /* pm_row_t.status */
 #define PM_ST_OK 0
@@ -135,6 +136,11 @@ int pm_aperpixmap_batch(int n, const double *rad, int64_t B, int nsubpix, double
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 const char *pm_last_cuda_error(void);
+/* Tuning aid: when set to a zeroed DEVICE buffer of PM_MAX_GRID x 16 uint64, subsequent pm_analyse_batch launches
+ * accumulate per-CTA clock64() cycles per phase (0 pixelmap, 1 list/window, 2 rmax/aperture, 3 sort, 4 gini/m20/
+ * candidates, 5 minapix, 6 calcA, 7 r20/r80, 8 smoothness).  Pass NULL to switch it off (the default). */
+void pm_debug_phase_cycles(void *device_u64_grid_x16);
+#define PM_MAX_GRID 592
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 uint64_t pm_launch_count(void);
 

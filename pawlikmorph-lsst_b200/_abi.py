@@ -16,6 +16,7 @@ PM_STOP_AFTER_PIXELMAP = 0x200
 PM_STOP_AFTER_RMAX = 0x400
 PM_A_ANGLE90 = 0x800
 PM_NO_NOISECORRECT = 0x1000
+PM_NO_PREFETCH = 0x2000
 PM_ST_OK, PM_ST_FAINT_CENTRE, PM_ST_NO_CANDIDATE, PM_ST_BAD_BRACKET, PM_ST_EMPTY_SEGMAP, PM_ST_WORKSPACE = range(6)
 
 ROW_FIELDS = ("apix_col", "apix_row", "rmax", "r20", "r80", "C", "A", "Abgr", "S", "As",
@@ -34,12 +35,14 @@ class Outputs(C.Structure):
                 ("apermask_out", C.c_void_p), ("cand_a_out", C.c_void_p), ("cand_cap", C.c_int32)]
 
 
-EXPORTS = ("pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
+EXPORTS = ("pm_debug_phase_cycles", "pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
            "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch")
 
 
 def declare(lib):
     """Attach prototypes to a loaded library and return it."""
+    lib.pm_debug_phase_cycles.restype = None
+    lib.pm_debug_phase_cycles.argtypes = [C.c_void_p]
     lib.pm_abi_version.restype = C.c_int
     lib.pm_abi_version.argtypes = []
     lib.pm_device_info.restype = C.c_int

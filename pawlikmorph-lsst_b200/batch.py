@@ -75,7 +75,7 @@ class BatchResult:
 def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segmap_in=None, apermask_in=None,
                   centroid_in=None, radius_in=None, r20_in=None, threshold_in=None, smooth_sky_in=None,
                   want_segmap=False, want_sorted=False, want_apermask=False, cand_cap=0, rows_out=None,
-                  stream=None):
+                  segmap_out=None, stream=None):
     """Run the hot path of main.py:421-495 on `images` [B, n, n] (CUDA tensor, float32 or float64,
     sky still in).  Asynchronous on `stream` (default: the current torch stream).  Returns a
     BatchResult whose tensors live on the same device."""
@@ -107,7 +107,11 @@ def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segma
             res = BatchResult(rows=rows_out if rows_out is not None else torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev))
             if res.rows.shape != (B, ROW_DOUBLES) or res.rows.dtype != torch.float64 or not res.rows.is_contiguous():
                 raise ValueError("rows_out must be a contiguous [B, 16] float64 tensor")
-            if want_segmap:
+            if segmap_out is not None:
+                if segmap_out.shape != (B, n, n) or segmap_out.dtype != torch.uint8 or not segmap_out.is_contiguous():
+                    raise ValueError("segmap_out must be a contiguous [B, n, n] uint8 tensor")
+                res.segmap = segmap_out
+            elif want_segmap:
                 res.segmap = torch.empty((B, n, n), dtype=torch.uint8, device=dev)
             if want_sorted:
                 res.sorted_idx = torch.empty((B, n * n), dtype=torch.int32, device=dev)

@@ -5,7 +5,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-SO = os.path.join(HERE, "libpawlik_b200.so")
+# PM_LIB_VARIANT=<threads>x<ctas> selects an experimental build (tuning runs only), e.g. 256x2
+VARIANT = os.environ.get("PM_LIB_VARIANT", "")
+SO = os.path.join(HERE, "libpawlik_b200.so" if not VARIANT else f"libpawlik_b200_{VARIANT}.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh")] + \
     [os.path.join(REPO, "include", "pawlik_b200.h")]
 
@@ -27,6 +29,9 @@ def build(force=False, verbose=False):
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(REPO, "include"),
            os.path.join(HERE, "csrc", "pm_capi.cu"), "-o", SO]
+    if VARIANT:
+        t, k = VARIANT.split("x")
+        cmd[1:1] = [f"-DPM_THREADS={int(t)}", f"-DPM_MIN_CTAS={int(k)}"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

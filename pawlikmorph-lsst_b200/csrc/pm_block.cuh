@@ -8,7 +8,14 @@
 
 namespace pmk {
 
-constexpr int kThreads = 512;
+#ifndef PM_THREADS
+#define PM_THREADS 512
+#endif
+#ifndef PM_MIN_CTAS
+#define PM_MIN_CTAS 1
+#endif
+constexpr int kThreads = PM_THREADS;
+static_assert(kThreads >= 256 && kThreads % 32 == 0, "the radix sort needs >= 256 threads");
 constexpr int kWarps = kThreads / 32;
 constexpr int kRedSlots = 8;
 
@@ -17,7 +24,8 @@ struct Sh {
     double red[kWarps * kRedSlots];  // per-warp partials of block reductions
     double bc[16];                   // broadcast slots
     double rk[132];                  // walk radii of casgm.py:55-73
-    double fk[132];                  // F(rk)
+    double fk[132];                  // F(rk): lower bounds during the walk
+    double fh[132];                  // upper bounds
     unsigned scan_tmp[kWarps + 2];
     unsigned colmask[24];            // OR of all segmap rows (PM_MAX_N / 32 words)
     int ia[8];                       // integer reductions (atomics)
@@ -123,16 +131,17 @@ PM_DEV double block_excl_prefix_d(Sh& sh, double v, double* total) {
     *total = tot;
     return base + (inc - v);
 }
-// in-place exclusive scan of arr[0..count) ; arr[count] = total.  count <= 2 * kThreads.
+// in-place exclusive scan of arr[0..count) ; arr[count] = total.  Any count: every thread owns a
+// contiguous chunk.
 PM_DEV unsigned block_scan_excl_array(Sh& sh, unsigned* arr, int count) {
-    int t = pm::tid();
-    int i0 = 2 * t, i1 = 2 * t + 1;
-    unsigned a = i0 < count ? arr[i0] : 0u, b = i1 < count ? arr[i1] : 0u;
+    const int per = (count + kThreads - 1) / kThreads;
+    const int lo = min(count, pm::tid() * per), hi = min(count, lo + per);
+    unsigned sum = 0;
+    for (int i = lo; i < hi; i++) sum += arr[i];
     unsigned tot;
-    unsigned ex = block_excl_prefix_u(sh, a + b, &tot);
-    if (i0 < count) arr[i0] = ex;
-    if (i1 < count) arr[i1] = ex + a;
-    if (t == 0) arr[count] = tot;
+    unsigned ex = block_excl_prefix_u(sh, sum, &tot);
+    for (int i = lo; i < hi; i++) { const unsigned v = arr[i]; arr[i] = ex; ex += v; }
+    if (pm::tid() == 0) arr[count] = tot;
     pm::sync();
     return tot;
 }
@@ -162,9 +171,20 @@ struct Arena {
         overflow = 1;
         return g_base;  // never dereferenced meaningfully: the caller checks `overflow`
     }
+    PM_DEV bool in_smem(const void* p) const {
+        const unsigned char* q = (const unsigned char*)p;
+        return q >= s_base && q < s_base + s_cap;
+    }
     struct Mark { unsigned s; size_t g; };
     PM_DEV Mark mark() const { Mark m; m.s = s_top; m.g = g_top; return m; }
     PM_DEV void release(Mark m) { s_top = m.s; g_top = m.g; }
+    // after release(mark): re-reserve the first `bytes` of `p`, which was the first allocation made after `mark`
+    PM_DEV void keep(const void* p, size_t bytes) {
+        bytes = (bytes + 15) & ~(size_t)15;
+        const unsigned char* q = (const unsigned char*)p;
+        if (q >= s_base && q < s_base + s_cap) s_top = (unsigned)(q - s_base) + (unsigned)bytes;
+        else g_top = (size_t)(q - g_base) + bytes;
+    }
 };
 
 // ---- stable LSD radix sort of (key, value) pairs, ascending, 8 bits per pass ----------------

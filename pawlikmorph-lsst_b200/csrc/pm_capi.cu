@@ -13,14 +13,14 @@
 
 using namespace pmk;
 
-#define PM_MAX_GRID 592   /* 148 SMs x 4: upper bound on resident CTAs, sizes the workspace */
 #define PM_WS_HEADER 256
 
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local char g_err[256] = "";
+static unsigned long long* g_phase_cycles = nullptr;   // tuning aid, see pm_debug_phase_cycles()
 
 #ifndef PM_EMULATE
-template <typename T> __global__ void __launch_bounds__(kThreads, 1) pm_analyse_kernel(const __grid_constant__ Params p) {
+template <typename T> __global__ void __launch_bounds__(kThreads, PM_MIN_CTAS) pm_analyse_kernel(const __grid_constant__ Params p) {
     analyse_body<T>(p);
 }
 __global__ void __launch_bounds__(kThreads, 1)
@@ -58,8 +58,8 @@ static int env_int(const char* name, int dflt) {
 static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
     const unsigned fixed = smem_fixed_bytes(n, fs);
     const unsigned cap1 = (unsigned)(g_smem_optin ? g_smem_optin : 232448);   // 227 KB
-    const unsigned cap2 = (cap1 + 1024) / 2 - 1024;                            // two CTAs per SM
-    int ctas = (fixed + 64 * 1024 <= cap2) ? 2 : 1;
+    int ctas = PM_MIN_CTAS;                                                    // what the launch bounds were compiled for
+    while (ctas > 1 && fixed + 24 * 1024 > (cap1 + 1024) / (unsigned)ctas - 1024) ctas--;   // large n: fewer, fatter CTAs
     ctas = env_int("PM_CTAS_PER_SM", ctas);
     if (ctas < 1) ctas = 1;
     unsigned per = (cap1 + 1024) / (unsigned)ctas - 1024;
@@ -74,6 +74,7 @@ static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
 extern "C" {
 
 int pm_abi_version(void) { return PM_ABI_VERSION; }
+void pm_debug_phase_cycles(void* device_u64_grid_x16) { g_phase_cycles = (unsigned long long*)device_u64_grid_x16; }
 const char* pm_last_cuda_error(void) { return g_err; }
 uint64_t pm_launch_count(void) { return g_launches.load(); }
 
@@ -123,6 +124,7 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
     p.counter = (unsigned long long*)workspace;
     p.scratch = (unsigned char*)workspace + PM_WS_HEADER;
     p.scratch_per_cta = scratch_bytes_per_cta(n);
+    p.phase_cycles = g_phase_cycles;
     unsigned smem = 0;
     int ctas = 1;
     launch_shape(n, filter_size, &smem, &ctas);

@@ -29,6 +29,7 @@ struct Params {
     unsigned long long scratch_per_cta;
     unsigned long long* counter;  // work counter (zeroed by the host before the launch)
     unsigned smem_bytes;          // dynamic shared memory given to the kernel
+    unsigned long long* phase_cycles;   // optional [grid, 16] per-CTA cycle counters (tuning aid), or null
 };
 
 struct Geo {
@@ -110,6 +111,17 @@ template <> struct KeyT<double> { typedef uint64_t type; };
 PM_DEV float nan_of(float) { return pm::bits2f(0x7fc00000u); }
 PM_DEV double nan_of(double) { return pm::bits2d(0x7ff8000000000000ll); }
 
+struct PhaseClock {
+    unsigned long long* slot;
+    long long last;
+    PM_DEV void start(unsigned long long* s) { slot = s; last = slot ? pm::clock() : 0; }
+    PM_DEV void lap(int phase) {
+        if (!slot) return;
+        const long long now = pm::clock();
+        if (pm::tid() == 0) slot[phase] += (unsigned long long)(now - last);
+        last = now;
+    }
+};
 // Per-cutout context (registers / local; identical in every thread) ---------------------------------
 template <typename T> struct Ctx {
     Geo g;
@@ -124,6 +136,7 @@ template <typename T> struct Ctx {
     int n_g, r0, r1, c0, c1;   // pixel count, bounding box (inclusive)
     unsigned* posR;      // raster list of segmap pixels, (row << 16) | col
     T* mw;               // masked window over the bounding box (NaN outside the segmap)
+    PhaseClock pc;       // tuning aid
     int bw;              // window width
 };
 
@@ -196,52 +209,88 @@ PM_DEV double zoom_taps(double f00, double f01, double f10, double f11, double t
     return s;
 }
 
-// fast path: direct fs x fs sums.  Returns (through sh) min |Z - thr| and max |x| for the band test.
-template <typename T> PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* minabs, double* maxabs) {
+// (fs+1) x (fs+1) patch of staged rows -> the four fs x fs window sums around (a0, b0).  FS > 0: compile-time
+// filter size (fully unrolled); kInterior: no reflection needed.
+template <typename T, int FS, bool kInterior>
+PM_DEV void patch_sums(const T* xb, int rlo, int n, int fs_rt, int a0, int b0, double& faa, double& fab, double& fba, double& fbb) {
+    const int fs = FS ? FS : fs_rt, h = fs / 2;
+    const bool ra = kInterior || a0 + 1 <= n - 1, rb = kInterior || b0 + 1 <= n - 1;   // second tap = first + 1 (else clamped)
+    faa = fab = fba = fbb = 0.0;
+#pragma unroll
+    for (int k = 0; k <= fs; k++) {
+        const int rr = kInterior ? a0 - h + k : refl(a0 - h + k, n);
+        const T* row = xb + (rr - rlo) * n;
+        double sa = 0.0, sb = 0.0;       // sums over the b0 / b1 column windows
+#pragma unroll
+        for (int q = 0; q <= fs; q++) {
+            const double x = (double)row[kInterior ? b0 - h + q : refl(b0 - h + q, n)];
+            if (q < fs) sa += x;
+            if (rb ? (q >= 1) : (q < fs)) sb += x;
+        }
+        if (k < fs) { faa += sa; fab += sb; }
+        if (ra ? (k >= 1) : (k < fs)) { fba += sa; fbb += sb; }
+    }
+}
+
+// fast path: the image rows a band of shrunk rows needs are staged in shared memory with fully coalesced,
+// independent loads (this is the only pass that streams the image from HBM); each thread then forms the
+// (fs+1) x (fs+1) patch sums of one shrunk pixel from the staged rows.  Reports min |Z - thr| and max |x|
+// for the band test.  xb: staging buffer; R: shrunk rows per band.
+template <typename T, int FS>
+PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* minabs, double* maxabs, T* xb, int R) {
     const Geo& g = c.g;
     const int fs = g.fs, h = g.h, n = g.n, m = g.m;
-    const double dfs = (double)fs;
-    double mn = 1e300, mx = 0.0;
+    const double inv = 1.0 / ((double)fs * (double)fs);
+    double mn = 1e300;
+    float mx = 0.0f;
     int faint = 0, bad = 0;
     const int cm = m / 2;
-    for (int task = pm::warp(); task < m * g.mw; task += kWarps) {
-        const int i = task / g.mw, w = task - i * g.mw;
-        const int j = w * 32 + pm::lane();
-        bool above = false;
-        if (j < m) {
-            const int a0 = c.i0[i], b0 = c.i0[j];
-            const int a1 = min(a0 + 1, n - 1), b1 = min(b0 + 1, n - 1);
-            const bool ra = (a1 != a0), rb = (b1 != b0);
-            double faa = 0.0, fab = 0.0, fba = 0.0, fbb = 0.0;
-            for (int k = 0; k <= fs; k++) {
-                const int rr = refl(a0 - h + k, n);
-                const bool inA = k < fs, inB = ra ? (k >= 1) : (k < fs);
-                double sa = 0.0, sb = 0.0;  // row sums over the b0 / b1 windows
-                for (int q = 0; q <= fs; q++) {
-                    const int cc = refl(b0 - h + q, n);
-                    const double x = ld(c, rr, cc);
-                    mx = fmax(mx, fabs(x));
-                    if (!(fabs(x) <= 1.7e308)) bad = 1;
-                    if (q < fs) sa += x;
-                    if (rb ? (q >= 1) : (q < fs)) sb += x;
-                }
-                if (inA) { faa += sa; fab += sb; }
-                if (inB) { fba += sa; fbb += sb; }
-            }
-            faa = (faa / dfs) / dfs; fab = (fab / dfs) / dfs; fba = (fba / dfs) / dfs; fbb = (fbb / dfs) / dfs;
-            const double z = zoom_taps(faa, fab, fba, fbb, c.tw[i], c.tw[j]);
+    for (int i = pm::tid(); i < m * g.mw; i += kThreads) zb[i] = 0;
+    for (int band = 0; band < m; band += R) {
+        const int rows = min(R, m - band);
+        // image rows [rlo, rhi] cover every (reflected) row the band touches
+        const int rlo = max(0, (int)c.i0[band] - h), rhi = min(n - 1, (int)c.i0[band + rows - 1] + h + 1);
+        const int cnt = (rhi - rlo + 1) * n;
+        const T* src = c.img + (size_t)rlo * n;
+        int i = pm::tid();
+        for (; i + 3 * kThreads < cnt; i += 4 * kThreads) {     // four independent loads in flight per thread
+            const T x0 = pm::ldg(src + i), x1 = pm::ldg(src + i + kThreads), x2 = pm::ldg(src + i + 2 * kThreads),
+                    x3 = pm::ldg(src + i + 3 * kThreads);
+            xb[i] = x0; xb[i + kThreads] = x1; xb[i + 2 * kThreads] = x2; xb[i + 3 * kThreads] = x3;
+            const float ax = fmaxf(fmaxf(fabsf((float)x0), fabsf((float)x1)), fmaxf(fabsf((float)x2), fabsf((float)x3)));
+            const float sm = fabsf((float)x0) + fabsf((float)x1) + fabsf((float)x2) + fabsf((float)x3);
+            if (!(sm <= 3.0e38f)) bad = 1;       // inf / nan (or beyond float range): let the exact path decide
+            mx = fmaxf(mx, ax);
+        }
+        for (; i < cnt; i += kThreads) {
+            const T x = pm::ldg(src + i);
+            xb[i] = x;
+            const float ax = fabsf((float)x);
+            if (!(ax <= 3.0e38f)) bad = 1;
+            mx = fmaxf(mx, ax);
+        }
+        pm::sync();
+        for (int item = pm::tid(); item < rows * m; item += kThreads) {
+            const int rb = item / m, j = item - rb * m;
+            const int ii = band + rb;
+            const int a0 = c.i0[ii], b0 = c.i0[j];
+            double faa, fab, fba, fbb;
+            if (a0 - h >= 0 && a0 + h + 1 <= n - 1 && b0 - h >= 0 && b0 + h + 1 <= n - 1)
+                patch_sums<T, FS, true>(xb, rlo, n, fs, a0, b0, faa, fab, fba, fbb);
+            else
+                patch_sums<T, FS, false>(xb, rlo, n, fs, a0, b0, faa, fab, fba, fbb);
+            const double z = zoom_taps(faa * inv, fab * inv, fba * inv, fbb * inv, c.tw[ii], c.tw[j]);
             const double d = z - c.thr;
-            above = z > c.thr;
             if (!(fabs(d) >= 0.0)) bad = 1;
             mn = fmin(mn, fabs(d));
-            if (i == cm && j == cm) faint = (z < c.thr) ? 1 : 0;
+            if (z > c.thr) pm::atomic_or(&zb[ii * g.mw + (j >> 5)], 1u << (j & 31));
+            if (ii == cm && j == cm) faint = (z < c.thr) ? 1 : 0;
         }
-        unsigned bits = pm::ballot(above);
-        if (pm::lane() == 0) zb[i * g.mw + w] = bits;
+        pm::sync();
     }
-    if (bad) mn = 0.0;  // non-finite input: let the exact path decide
+    if (bad) mn = 0.0;
     *minabs = block_min(*c.sh, mn);
-    *maxabs = block_max(*c.sh, mx);
+    *maxabs = block_max(*c.sh, (double)mx * 1.0000002);   // float rounding of |x| never under-estimates the band
     *centre_faint = pm::sync_or(faint);
 }
 
@@ -401,7 +450,18 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
     bool exact = (c.flags & PM_FORCE_EXACT_FILTER) != 0;
     if (!exact) {
         double mn, mx;
-        pixelmap_fast(c, zb, &faint, &mn, &mx);
+        Arena::Mark mk = c.ar.mark();
+        int R = max(1, kThreads / g.m);                            // about one shrunk pixel per thread per band
+        for (;;) {                                                  // staging buffer <= 40 KB
+            const int nrows = (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3;
+            if (R == 1 || (size_t)nrows * g.n * sizeof(T) <= 40960) break;
+            R--;
+        }
+        const int nrows = min(g.n, (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3);
+        T* xb = (T*)c.ar.alloc((size_t)nrows * g.n * sizeof(T));
+        if (g.fs == 3) pixelmap_fast<T, 3>(c, zb, &faint, &mn, &mx, xb, R);
+        else pixelmap_fast<T, 0>(c, zb, &faint, &mn, &mx, xb, R);
+        c.ar.release(mk);
         // |Z_fast - Z_scipy| <= (2 n + fs^2 + 8) * max|x| * 2^-52 (running-sum error growth); x4 margin
         const double band = 4.0 * (2.0 * g.n + (double)(g.fs * g.fs) + 8.0) * mx * 2.220446049250313e-16;
         if (!(mn > band)) exact = true;
@@ -412,9 +472,11 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
         double* F = G + (size_t)g.N;
         pixelmap_exact(c, zb, &faint, G, F);
     }
+    c.pc.lap(13);   // (pixelmap: filter + shrink)
     if (faint) return PM_ST_FAINT_CENTRE;
     region_grow(g, zb, gb);
     upsample_mask(c, gb);
+    c.pc.lap(14);   // (pixelmap: grow + upsample)
     return PM_ST_OK;
 }
 
@@ -710,63 +772,129 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
 // ====================================================================================================
 // disc test for the re-centred aperture of candidate (px, py): apertures.apercentre rolls the mask by
 // pix - (n//2 + 1) on both axes (cyclic), with pix = [col, row]  (asymmetry.py:106,118; apertures.py:231-238)
-PM_DEV bool aper_rolled(const unsigned* aper, const Geo& g, int r, int col, int d0, int d1) {
-    int rr = r - d0, cc = col - d1;
-    if (rr < 0) rr += g.n; else if (rr >= g.n) rr -= g.n;
-    if (cc < 0) cc += g.n; else if (cc >= g.n) cc -= g.n;
-    return bit_at(aper, g.nw, rr, cc);
+template <bool kWrap> PM_DEV void wrap_rc(const Geo& g, int& rr, int& cc) {
+    if (kWrap) {
+        if (rr < 0) rr += g.n; else if (rr >= g.n) rr -= g.n;
+        if (cc < 0) cc += g.n; else if (cc >= g.n) cc -= g.n;
+    }
+}
+PM_DEV float lds_t(unsigned a, float) { return pm::lds_f32(a); }
+PM_DEV double lds_t(unsigned a, double) { return pm::lds_f64(a); }
+
+constexpr int kCandBlock = 4;   // candidates evaluated together per pass over the pixel list
+
+// One work item = (group of kCandBlock candidates, slice of the raster pixel list), evaluated by one warp:
+// every lane loads a map pixel once and pairs it with its mirror image about each candidate of the group.
+// kSmem: the pixel list and the masked window live in shared memory (explicit 32-bit addressed loads).
+template <typename T, bool kWrap, bool kSmem>
+PM_DEV void minapix_item(const Ctx<T>& c, const int (&px)[kCandBlock], const int (&py)[kCandBlock], int first, int stride,
+                         double (&num)[kCandBlock], double (&den)[kCandBlock]) {
+    const Geo& g = c.g;
+    const int n = g.n, bw = c.bw, bh = c.r1 - c.r0 + 1, r0 = c.r0, c0 = c.c0, nw = g.nw;
+    const unsigned ap32 = pm::smem_addr(c.aper);
+    const unsigned mw32 = kSmem ? pm::smem_addr(c.mw) : 0u, pos32 = kSmem ? pm::smem_addr(c.posR) : 0u;
+    int d0[kCandBlock], d1[kCandBlock];
+#pragma unroll
+    for (int j = 0; j < kCandBlock; j++) { d0[j] = px[j] - (g.half + 1); d1[j] = py[j] - (g.half + 1); num[j] = 0.0; den[j] = 0.0; }
+    for (int i = first; i < c.n_g; i += stride) {
+        const unsigned p = kSmem ? pm::lds_u32(pos32 + 4u * (unsigned)i) : c.posR[i];
+        const int r = (int)(p >> 16), col = (int)(p & 0xffff);
+        const unsigned vi = (unsigned)((r - r0) * bw + (col - c0));
+        const T vraw = kSmem ? lds_t(mw32 + (unsigned)sizeof(T) * vi, T()) : c.mw[vi];
+        const double v = (double)vraw - c.sky;
+        const double av = fabs(v);
+        // all loads of the kCandBlock candidates first (independent, in flight together) ...
+        T w[kCandBlock];
+        unsigned b1[kCandBlock], b2[kCandBlock];
+        bool inwin[kCandBlock], inb[kCandBlock];
+#pragma unroll
+        for (int j = 0; j < kCandBlock; j++) {
+            const int tr = 2 * py[j] - r, tc = 2 * px[j] - col;      // mirror image of the pixel about the candidate
+            const unsigned wr = (unsigned)(tr - r0), wc = (unsigned)(tc - c0);
+            inwin[j] = wr < (unsigned)bh && wc < (unsigned)bw;
+            const unsigned wi = inwin[j] ? wr * (unsigned)bw + wc : 0u;
+            w[j] = kSmem ? lds_t(mw32 + (unsigned)sizeof(T) * wi, T()) : c.mw[wi];
+            inb[j] = (unsigned)tr < (unsigned)n && (unsigned)tc < (unsigned)n;
+            int rr = r - d0[j], cc = col - d1[j];
+            wrap_rc<kWrap>(g, rr, cc);
+            b1[j] = pm::lds_u32(ap32 + 4u * (unsigned)(rr * nw + (cc >> 5))) >> (cc & 31);
+            int r2 = inb[j] ? tr - d0[j] : g.half, c2 = inb[j] ? tc - d1[j] : g.half;
+            wrap_rc<kWrap>(g, r2, c2);
+            b2[j] = pm::lds_u32(ap32 + 4u * (unsigned)(r2 * nw + (c2 >> 5))) >> (c2 & 31);
+        }
+        // ... then the (predicated) float64 accumulation
+#pragma unroll
+        for (int j = 0; j < kCandBlock; j++) {
+            const bool t_in_seg = inwin[j] && (w[j] == w[j]);
+            double mt = 0.0;
+            if (t_in_seg) mt = (double)w[j] - c.sky;
+            if (b1[j] & 1u) { num[j] += fabs(v - mt); den[j] += av; }
+            // mirror position inside the image but outside the map: there M = 0 and M180 = v
+            if ((b2[j] & 1u) && inb[j] && !t_in_seg) num[j] += av;
+        }
+    }
 }
 
 template <typename T>
-PM_DEV void phase_minapix(Ctx<T>& c, const unsigned* sp_sorted, int n_cand, double* a_out, double* parts, int slices,
+PM_DEV void phase_minapix(Ctx<T>& c, const unsigned* cand, int n_cand, double* a_out, double* parts, int slices,
                           int* best) {
     const Geo& g = c.g;
     Sh& sh = *c.sh;
-    const int n = c.n_g;
-    const int items = n_cand * slices;
+    const int groups = (n_cand + kCandBlock - 1) / kCandBlock;
+    const int items = groups * slices;
     for (int item = pm::warp(); item < items; item += kWarps) {
-        const int cand = item / slices, sl = item - cand * slices;
-        const unsigned pp = sp_sorted[n - 1 - cand];
-        const int py = (int)(pp >> 16), px = (int)(pp & 0xffff);
-        const int d0 = px - (g.half + 1), d1 = py - (g.half + 1);
-        double num = 0.0, den = 0.0;
-        for (int i = sl * 32 + pm::lane(); i < n; i += 32 * slices) {
-            const unsigned p = c.posR[i];
-            const int r = (int)(p >> 16), col = (int)(p & 0xffff);
-            const double v = (double)c.mw[(r - c.r0) * c.bw + (col - c.c0)] - c.sky;
-            const int tr = 2 * py - r, tc = 2 * px - col;
-            const bool inb = tr >= 0 && tr < g.n && tc >= 0 && tc < g.n;
-            double mt = 0.0;
-            bool t_in_seg = false;
-            if (inb) {
-                const T w = mw_raw(c, tr, tc);
-                if (w == w) { mt = (double)w - c.sky; t_in_seg = true; }
-            }
-            if (aper_rolled(c.aper, g, r, col, d0, d1)) { num += fabs(v - mt); den += fabs(v); }
-            // the mirrored position is outside the map: there M = 0 and M180 = v
-            if (inb && !t_in_seg && aper_rolled(c.aper, g, tr, tc, d0, d1)) num += fabs(v);
+        const int grp = item / slices, sl = item - grp * slices;
+        int px[kCandBlock], py[kCandBlock];
+        bool nowrap = true;
+#pragma unroll
+        for (int j = 0; j < kCandBlock; j++) {
+            const int k = min(grp * kCandBlock + j, n_cand - 1);
+            const unsigned pp = cand[k];
+            py[j] = (int)(pp >> 16); px[j] = (int)(pp & 0xffff);
+            // rows / columns the aperture is probed at: the map's bounding box and its mirror image (clipped)
+            const int d0 = px[j] - (g.half + 1), d1 = py[j] - (g.half + 1);
+            const int rlo = min(c.r0, max(0, 2 * py[j] - c.r1)), rhi = max(c.r1, min(g.n - 1, 2 * py[j] - c.r0));
+            const int clo = min(c.c0, max(0, 2 * px[j] - c.c1)), chi = max(c.c1, min(g.n - 1, 2 * px[j] - c.c0));
+            nowrap = nowrap && (rlo - d0 >= 0) && (rhi - d0 < g.n) && (clo - d1 >= 0) && (chi - d1 < g.n);
         }
-        num = pm::warp_sum(num);
-        den = pm::warp_sum(den);
-        if (pm::lane() == 0) { parts[2 * item] = num; parts[2 * item + 1] = den; }
+        double num[kCandBlock], den[kCandBlock];
+        const bool in_smem = c.ar.in_smem(c.mw) && c.ar.in_smem(c.posR);
+        const int first = sl * 32 + pm::lane(), stride = 32 * slices;
+        if (in_smem) {
+            if (nowrap) minapix_item<T, false, true>(c, px, py, first, stride, num, den);
+            else minapix_item<T, true, true>(c, px, py, first, stride, num, den);
+        } else {
+            if (nowrap) minapix_item<T, false, false>(c, px, py, first, stride, num, den);
+            else minapix_item<T, true, false>(c, px, py, first, stride, num, den);
+        }
+#pragma unroll
+        for (int j = 0; j < kCandBlock; j++) {
+            const double a = pm::warp_sum(num[j]), b = pm::warp_sum(den[j]);
+            if (pm::lane() == 0) { parts[2 * (item * kCandBlock + j)] = a; parts[2 * (item * kCandBlock + j) + 1] = b; }
+        }
     }
     pm::sync();
     double amin = 1.7976931348623157e308 * 2.0;   // +inf
     int nan_idx = 0x7fffffff;
-    for (int cand = pm::tid(); cand < n_cand; cand += kThreads) {
+    for (int k = pm::tid(); k < n_cand; k += kThreads) {
+        const int grp = k / kCandBlock, j = k - grp * kCandBlock;
         double num = 0.0, den = 0.0;
-        for (int s = 0; s < slices; s++) { num += parts[2 * (cand * slices + s)]; den += parts[2 * (cand * slices + s) + 1]; }
+        for (int s = 0; s < slices; s++) {
+            const int item = grp * slices + s;
+            num += parts[2 * (item * kCandBlock + j)];
+            den += parts[2 * (item * kCandBlock + j) + 1];
+        }
         const double a = num / (2.0 * den);
-        a_out[cand] = a;
-        if (a != a) nan_idx = min(nan_idx, cand); else amin = fmin(amin, a);
+        a_out[k] = a;
+        if (a != a) nan_idx = min(nan_idx, k); else amin = fmin(amin, a);
     }
     pm::sync();
     nan_idx = block_min_i(sh, nan_idx);
     if (nan_idx != 0x7fffffff) { *best = nan_idx; return; }   // np.argmin returns the first NaN
     amin = block_min(sh, amin);
     int idx = 0x7fffffff;
-    for (int cand = pm::tid(); cand < n_cand; cand += kThreads)
-        if (a_out[cand] == amin) { idx = cand; break; }
+    for (int k = pm::tid(); k < n_cand; k += kThreads)
+        if (a_out[k] == amin) { idx = k; break; }
     *best = block_min_i(sh, idx);
 }
 
@@ -803,6 +931,7 @@ struct BgrCtx {
     const unsigned* dil;
     const unsigned* rowoff;   // exclusive prefix of dilated-mask pixels per row, [n + 1]
     int nb, nm;
+    int nfree;                // pixels before the first row that holds a mask pixel: there, select(j) == j
 };
 // rank of a mask pixel among mask pixels in raster order
 PM_DEV int mask_rank(const Geo& g, const BgrCtx& b, int r, int col) {
@@ -815,6 +944,7 @@ PM_DEV int mask_rank(const Geo& g, const BgrCtx& b, int r, int col) {
 }
 // flat index of the j-th (0-based) background pixel in raster order
 PM_DEV int bgr_select(const Geo& g, const BgrCtx& b, int j) {
+    if (j < b.nfree) return j;     // the leading all-background rows: the common case
     int lo = 0, hi = g.n - 1;      // largest row r with  r*n - rowoff[r] <= j
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -852,7 +982,7 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     const bool noise = do_img && !(c.flags & PM_NO_NOISECORRECT);
     const bool rot90 = (c.flags & PM_A_ANGLE90) != 0;
     BgrCtx b;
-    b.dil = c.dil; b.rowoff = c.rowoff; b.nb = 0; b.nm = 0;
+    b.dil = c.dil; b.rowoff = c.rowoff; b.nb = 0; b.nm = 0; b.nfree = 0;
     if (noise) {
         dilate9(g, c.seg, c.dil, tmp_plane);
         for (int r = pm::tid(); r < g.n; r += kThreads) {
@@ -863,8 +993,14 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
         pm::sync();
         b.nm = (int)block_scan_excl_array(sh, c.rowoff, g.n);
         b.nb = g.N - b.nm;
+        int fm = 0x7fffffff;
+        for (int r = pm::tid(); r < g.n; r += kThreads)
+            if (c.rowoff[r + 1] != c.rowoff[r]) fm = min(fm, r);
+        fm = block_min_i(sh, fm);
+        b.nfree = (fm == 0x7fffffff) ? g.N : fm * g.n;
     }
     const bool bgr_ok = noise && b.nb > 0 && b.nm > 1;      // asymmetry.py:225-226
+    c.pc.lap(9);    // (calcA: dilation + row scan)
     double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};           // numA denA numB numS180 denS numS90
     for (int task = pm::warp(); task < g.n * g.nw; task += kWarps) {
         const unsigned bits = c.aper[task];
@@ -927,6 +1063,7 @@ struct Fold {
     double* T;
     double* P;
     int A;
+    double abs_sum;   // Σ |T|
 };
 PM_DEV int tri(int a, int b) { return a * (a + 1) / 2 + b; }
 
@@ -952,45 +1089,109 @@ template <typename T_> PM_DEV void build_fold(Ctx<T_>& c, int cx, int cy, Fold& 
         f.T[e] = s;
     }
     pm::sync();
+    double asum = 0.0;
     for (int a = pm::tid(); a <= A; a += kThreads) {
         double run = 0.0;
-        for (int b = 0; b <= a; b++) { run += f.T[tri(a, b)]; f.P[tri(a, b)] = run; }
+        for (int b = 0; b <= a; b++) { const double t = f.T[tri(a, b)]; run += t; asum += fabs(t); f.P[tri(a, b)] = run; }
+    }
+    f.abs_sum = block_sum1(*c.sh, asum);
+}
+// Column a of the folded table for a circle of radius r: entries b < b_lo lie fully inside (prefix sum P),
+// entries b_lo <= b < b_hi are cut by the circle, the rest is outside.  The predicates are photutils'
+// (d < r - pr, d < r + pr with d = sqrt(dx^2 + dy^2) in float64); a float estimate is corrected with them.
+PM_DEV bool inside_d(int a, int b, double lim) { return sqrt((double)(a * a + b * b)) < lim; }
+PM_DEV int first_not_inside(int a, double lim) {     // smallest b >= 0 with !(d(a, b) < lim)
+    if (!(lim > 0.0)) return 0;
+    const double t = lim * lim - (double)a * (double)a;
+    int b = t > 0.0 ? (int)sqrtf((float)t) : 0;
+    while (b > 0 && !inside_d(a, b - 1, lim)) b--;
+    while (inside_d(a, b, lim)) b++;
+    return b;
+}
+PM_DEV void fold_range(int a, double r, int* b_lo_out, int* b_hi_out) {
+    const double pr = 0.5 * sqrt(2.0);
+    const int b_lo = first_not_inside(a, r - pr);
+    const int b_hi = first_not_inside(a, r + pr);
+    *b_lo_out = min(b_lo, a + 1);
+    *b_hi_out = min(max(b_hi, b_lo), a + 1);
+}
+// cheap, conservative bounds of column a's contribution: squared-distance tests with a safety margin
+// (no float64 square roots); every possibly-cut pixel is counted with weight 0 or 1, whichever is worse
+PM_DEV int count_below(int a, double lim2) {          // number of b >= 0 with a^2 + b^2 < lim2
+    const double t = lim2 - (double)a * (double)a;
+    if (!(t > 0.0)) return 0;
+    int b = (int)sqrtf((float)t);
+    while (b > 0 && !((double)(a * a + (b - 1) * (b - 1)) < lim2)) b--;
+    while ((double)(a * a + b * b) < lim2) b++;
+    return b;
+}
+PM_DEV void fold_column_bounds(const Fold& f, int a, double r, double* lo, double* hi) {
+    const double pr = 0.5 * sqrt(2.0);
+    const double rin = r - pr - 1e-9, rout = r + pr + 1e-9;
+    const int b_in = min(rin > 0.0 ? count_below(a, rin * rin) : 0, a + 1);     // certainly inside
+    const int b_out = min(max(count_below(a, rout * rout), b_in), a + 1);       // from here on certainly outside
+    const double s = b_in > 0 ? f.P[tri(a, b_in - 1)] : 0.0;
+    double l = s, h = s;
+    for (int b = b_in; b < b_out; b++) {
+        const double t = f.T[tri(a, b)];
+        if (t < 0.0) l += t; else h += t;
+    }
+    *lo = l; *hi = h;
+}
+// exact F(r) for nr <= kRedSlots radii; results in sh.bc[0..nr).  Pass 1: one (radius, column) item per
+// thread finds the cut range and adds the fully-inside prefix; pass 2: the cut pixels of all columns are
+// dealt out evenly, one exact circle/pixel overlap per thread-step.  off / blo: nr * (A + 1) + 1 entries each.
+PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo) {
+    double acc[kRedSlots];
+#pragma unroll
+    for (int q = 0; q < kRedSlots; q++) acc[q] = 0.0;
+    const int ncol = f.A + 1, items = nr * ncol;
+    for (int item = pm::tid(); item < items; item += kThreads) {
+        const int q = item / ncol, a = item - q * ncol;
+        const double r = radii[q];
+        int b_lo = 0, b_hi = 0;
+        if (!((double)a > r + 1.0)) fold_range(a, r, &b_lo, &b_hi);
+        const double v = b_lo > 0 ? f.P[tri(a, b_lo - 1)] : 0.0;
+#pragma unroll
+        for (int k = 0; k < kRedSlots; k++)
+            if (k == q) acc[k] += v;
+        blo[item] = b_lo;
+        off[item] = (unsigned)(b_hi - b_lo);
+    }
+    pm::sync();
+    const int total = (int)block_scan_excl_array(sh, off, items);
+    for (int e = pm::tid(); e < total; e += kThreads) {
+        int lo = 0, hi = items - 1;          // last item with off[item] <= e
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)off[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const int q = lo / ncol, a = lo - q * ncol, b = blo[lo] + (e - (int)off[lo]);
+        const double v = f.T[tri(a, b)] * overlap_pixel((double)a, (double)b, radii[q]);
+#pragma unroll
+        for (int k = 0; k < kRedSlots; k++)
+            if (k == q) acc[k] += v;
+    }
+    block_sum<kRedSlots>(sh, acc);
+    if (pm::tid() == 0) {
+#pragma unroll
+        for (int q = 0; q < kRedSlots; q++) sh.bc[q] = acc[q];
     }
     pm::sync();
 }
-// exact-overlap aperture sum of M inside radius r: contribution of column a (lane-level work item)
-PM_DEV double fold_column(const Fold& f, int a, double r) {
-    const double pr = 0.5 * sqrt(2.0);
-    const double rin = r - pr, rout = r + pr;
-    // b_lo: first b with d(a, b) >= rin  (entries below are fully inside)
-    int b_lo = 0;
-    if (rin > 0.0) {
-        const double t = rin * rin - (double)a * (double)a;
-        if (t > 0.0) {
-            b_lo = (int)sqrt(t);
-            while (b_lo > 0 && !(sqrt((double)(a * a + (b_lo - 1) * (b_lo - 1))) < rin)) b_lo--;
-            while (sqrt((double)(a * a + b_lo * b_lo)) < rin) b_lo++;
-        }
-    }
-    double s = 0.0;
-    if (b_lo > 0) s = f.P[tri(a, min(b_lo - 1, a))];
-    for (int b = b_lo; b <= a; b++) {
-        const double d = sqrt((double)(a * a + b * b));
-        if (!(d < rout)) break;
-        s += f.T[tri(a, b)] * overlap_pixel((double)a, (double)b, r);
-    }
-    return s;
-}
-// F(r) for `nr` radii at once (nr <= kWarps): warp w evaluates radius w; results in sh.bc[0..nr)
-PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr) {
-    const int w = pm::warp();
-    if (w < nr) {
-        const double r = radii[w];
-        double s = 0.0;
+// bounds lo <= F(r_k) <= hi for the walk radii rk[1..K]: one warp per radius
+PM_DEV void eval_flux_bounds(Sh& sh, const Fold& f, int K) {
+    for (int k = 1 + pm::warp(); k <= K; k += kWarps) {
+        const double r = sh.rk[k];
+        double lo = 0.0, hi = 0.0;
         const int amax = min(f.A, (int)(r + 2.0));
-        for (int a = pm::lane(); a <= amax; a += 32) s += fold_column(f, a, r);
-        s = pm::warp_sum(s);
-        if (pm::lane() == 0) sh.bc[w] = s;
+        for (int a = pm::lane(); a <= amax; a += 32) {
+            double l, h;
+            fold_column_bounds(f, a, r, &l, &h);
+            lo += l; hi += h;
+        }
+        lo = pm::warp_sum(lo); hi = pm::warp_sum(hi);
+        if (pm::lane() == 0) { sh.fk[k] = lo; sh.fh[k] = hi; }
     }
     pm::sync();
 }
@@ -1057,8 +1258,13 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     const int entries = (f.A + 1) * (f.A + 2) / 2;
     f.T = (double*)c.ar.alloc((size_t)entries * 8);
     f.P = (double*)c.ar.alloc((size_t)entries * 8);
+    unsigned* eoff = (unsigned*)c.ar.alloc((size_t)(kRedSlots * (f.A + 1) + 1) * 4);
+    int* eblo = (int*)c.ar.alloc((size_t)(kRedSlots * (f.A + 1) + 1) * 4);
+    int* eblo2 = eblo;
+    unsigned char* vscratch = (unsigned char*)c.ar.alloc(2 * 132 + 16);
     if (c.ar.overflow) { c.ar.release(mk); return; }
     build_fold(c, cx, cy, f);
+    c.pc.lap(10);   // (r20/r80: folded table)
     // total flux inside `radius` (casgm.py:51-52)
     if (pm::tid() == 0) sh.rk[0] = radius;
     // the walk radii (casgm.py:55-73): r_1 = R - δ, r_{k+1} = r_k - δ, δ = (R / 200) * 2
@@ -1069,31 +1275,63 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         while (K < 130 && r > 0.0) { K++; if (pm::tid() == 0) sh.rk[K] = r; r -= delta; }
     }
     pm::sync();
-    eval_flux(sh, f, sh.rk, 1);
+    eval_flux(sh, f, sh.rk, 1, eoff, eblo);
     const double total = sh.bc[0];
     pm::sync();
-    // walk down in batches of kWarps radii until both fractions are bracketed
-    int k20 = -1, k80 = -1;     // first k with F(r_k)/total <= fraction
-    for (int base = 1; base <= K && (k20 < 0 || k80 < 0); base += kWarps) {
-        const int nr = min(kWarps, K - base + 1);
-        eval_flux(sh, f, sh.rk + base, nr);
-        for (int i = 0; i < nr; i++) {
-            const double frac = sh.bc[i] / total;
-            if (k80 < 0 && frac <= 0.8) k80 = base + i;
-            if (k20 < 0 && frac <= 0.2) k20 = base + i;
-        }
-        pm::sync();
+    // Walk down (casgm.py:61-73): first k with F(r_k) / total <= fraction.  Cheap bounds decide most radii;
+    // only the undecided ones near the crossing are evaluated exactly.
+    eval_flux_bounds(sh, f, K);
+    c.pc.lap(11);   // (r20/r80: total + walk bounds)
+    const double slack = 1e-9 * f.abs_sum;          // >> rounding of any partial sum, << one pixel of flux
+    const double fr[2] = {0.2, 0.8};
+    // verdict per radius and fraction: 1 = certainly F/total <= fraction, 0 = certainly not, 2 = undecided
+    unsigned char* verdict = vscratch;              // [2][K + 1]
+    for (int item = pm::tid(); item < 2 * K; item += kThreads) {
+        const int q = item / K, k = 1 + item - q * K;
+        const double lo = sh.fk[k] - slack, hi = sh.fh[k] + slack;
+        int v;
+        if (total > 0.0) v = (hi / total <= fr[q] - 1e-12) ? 1 : ((lo / total > fr[q] + 1e-12) ? 0 : 2);
+        else if (total < 0.0) v = (lo / total <= fr[q] - 1e-12) ? 1 : ((hi / total > fr[q] + 1e-12) ? 0 : 2);
+        else v = 2;
+        verdict[q * (K + 1) + k] = (unsigned char)v;
     }
+    pm::sync();
+    int kfound[2] = {-1, -1};
+    for (int q = 0; q < 2; q++) {
+        int pos = 1;
+        while (pos <= K && kfound[q] < 0) {
+            int list[kRedSlots];
+            int nl = 0, sure = -1;
+            int k = pos;
+            for (; k <= K && nl < kRedSlots; k++) {
+                const int v = verdict[q * (K + 1) + k];
+                if (v == 1) { sure = k; break; }
+                if (v == 2) list[nl++] = k;
+            }
+            if (nl > 0) {
+                if (pm::tid() == 0)
+                    for (int i = 0; i < nl; i++) sh.bc[8 + i] = sh.rk[list[i]];
+                pm::sync();
+                eval_flux(sh, f, sh.bc + 8, nl, eoff, eblo2);
+                for (int i = 0; i < nl && kfound[q] < 0; i++)
+                    if (sh.bc[i] / total <= fr[q]) kfound[q] = list[i];
+                pm::sync();
+            }
+            if (kfound[q] < 0 && sure > 0) kfound[q] = sure;
+            pos = (sure > 0) ? K + 1 : k;
+        }
+    }
+    const int k20 = kfound[0], k80 = kfound[1];
+    c.pc.lap(12);   // (r20/r80: exact walk evaluations)
     if (k20 < 0 || k80 < 0) { c.ar.release(mk); return; }   // the reference walks to r <= 0 and raises
     // brentq on [r_k, r_k + δ] for both fractions, in lock-step
     Brent b[2];
-    const double fr[2] = {0.2, 0.8};
     const int kk[2] = {k20, k80};
     if (pm::tid() == 0) {
         for (int q = 0; q < 2; q++) { sh.fk[2 * q] = sh.rk[kk[q]]; sh.fk[2 * q + 1] = sh.rk[kk[q]] + delta; }
     }
     pm::sync();
-    eval_flux(sh, f, sh.fk, 4);
+    eval_flux(sh, f, sh.fk, 4, eoff, eblo);
     for (int q = 0; q < 2; q++)
         brent_init(b[q], sh.fk[2 * q], sh.fk[2 * q + 1], sh.bc[2 * q] / total - fr[q], sh.bc[2 * q + 1] / total - fr[q]);
     pm::sync();
@@ -1106,7 +1344,7 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         }
         if (nact == 0) break;
         pm::sync();
-        eval_flux(sh, f, sh.fk, nact);
+        eval_flux(sh, f, sh.fk, nact, eoff, eblo);
         for (int q = 0; q < 2; q++)
             if (slot[q] >= 0) b[q].fcur = sh.bc[slot[q]] / total - fr[q];
         pm::sync();
@@ -1120,21 +1358,38 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
 // ====================================================================================================
 // Phase 7 — casgm.smoothness (casgm.py:276-406)
 // ====================================================================================================
-// scipy.ndimage.uniform_filter window of size k at index i covers [i - k/2, i - k/2 + k - 1]
-template <typename T_> PM_DEV double box_mean(const Ctx<T_>& c, int r, int col, int k, int r_lo, int r_len, int c_lo, int c_len) {
-    // mean over the k x k window, "reflect" boundary of the sub-image [r_lo, r_lo + r_len) x [c_lo, c_lo + c_len)
+// k x k box means with scipy.ndimage.uniform_filter geometry (window [i - k/2, i - k/2 + k - 1], "reflect"
+// boundary of the sub-image [rlo, rlo + rlen) x [clo, clo + clen)) for the pixels of rows [ra, rb) x cols [ca, cb).
+// Separable: vertical window sums of a band of rows are staged in `vbuf`, then summed horizontally.
+// fn(r, col, mean) is called once per pixel by the thread that owns it.
+template <typename T_, typename F>
+PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int clen, int ra, int rb, int ca, int cb,
+                      double* vbuf, int vcap, F fn) {
     const int h = k / 2;
-    double s = 0.0;
-    for (int dr = 0; dr < k; dr++) {
-        const int rr = r_lo + refl(r - r_lo - h + dr, r_len);
-        double rs = 0.0;
-        for (int dc = 0; dc < k; dc++) {
-            const int cc = c_lo + refl(col - c_lo - h + dc, c_len);
-            rs += ld(c, rr, cc) - c.sky;
+    const int W = cb - ca, E = W + k - 1;
+    if (W <= 0 || rb <= ra) return;
+    const int R = max(1, min(16, vcap / E));
+    const double inv = 1.0 / ((double)k * (double)k);
+    for (int band = ra; band < rb; band += R) {
+        const int rows = min(R, rb - band);
+        for (int item = pm::tid(); item < rows * E; item += kThreads) {
+            const int q = item / E, e = item - q * E;
+            const int r = band + q;
+            const int cc = clo + refl(ca - clo - h + e, clen);
+            double sum = 0.0;
+            for (int dr = 0; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
+            vbuf[item] = sum;
         }
-        s += rs;
+        pm::sync();
+        for (int item = pm::tid(); item < rows * W; item += kThreads) {
+            const int q = item / W, x = item - q * W;
+            const double* v = vbuf + q * E + x;
+            double sum = 0.0;
+            for (int dc = 0; dc < k; dc++) sum += v[dc];
+            fn(band + q, ca + x, sum * inv);
+        }
+        pm::sync();
     }
-    return s / ((double)k * (double)k);
 }
 
 template <typename T_>
@@ -1147,30 +1402,97 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
     const int ixmin = (int)floor((double)cx - rmax + 0.5), ixmax = (int)ceil((double)cx + rmax + 0.5);
     const int iymin = (int)floor((double)cy - rmax + 0.5), iymax = (int)ceil((double)cy + rmax + 0.5);
     const int x0 = max(ixmin, 0), x1 = min(ixmax, g.n), y0 = max(iymin, 0), y1 = min(iymax, g.n);
-    const int bwid = x1 - x0, bhgt = y1 - y0;
+    Arena::Mark mk = c.ar.mark();
+    const int vcap = max(2 * (x1 - x0 + k), 2048);
+    double* vbuf = (double*)c.ar.alloc((size_t)vcap * 8);
+    const int A = (int)(rmax + 0.5 * sqrt(2.0)) + 1;
+    unsigned* eoff = (unsigned*)c.ar.alloc((size_t)(2 * (A + 1) + 1) * 4);
+    int* eblo = (int*)c.ar.alloc((size_t)(2 * (A + 1) + 1) * 4);
+    if (c.ar.overflow) { c.ar.release(mk); return -99.0; }
+    // Pixels cut by neither circle have weight exactly 1 (inside the annulus) or 0: integer thresholds on the squared
+    // distance reproduce photutils' float64 predicates  d < r_out - pr  and  d < r_in + pr  (d = sqrt(dx^2 + dy^2)).
+    const double pr = 0.5 * sqrt(2.0);
+    int d2_full_out = 0, d2_zero_in = 0;     // first d2 with !(sqrt(d2) < r_out - pr) / !(sqrt(d2) < r_in + pr)
+    {
+        const double lo = rmax - pr, hi = r20 + pr;
+        if (lo > 0.0) { d2_full_out = (int)(lo * lo); while (d2_full_out > 0 && !(sqrt((double)(d2_full_out - 1)) < lo)) d2_full_out--;
+                        while (sqrt((double)d2_full_out) < lo) d2_full_out++; }
+        d2_zero_in = (int)(hi * hi);
+        while (d2_zero_in > 0 && !(sqrt((double)(d2_zero_in - 1)) < hi)) d2_zero_in--;
+        while (sqrt((double)d2_zero_in) < hi) d2_zero_in++;
+    }
     double s[2] = {0.0, 0.0};   // Σ w I ,  Σ w max(I - Is, 0)
-    if (bwid > 0 && bhgt > 0) {
-        for (int i = pm::tid(); i < bwid * bhgt; i += kThreads) {
-            const int r = y0 + i / bwid, col = x0 + i % bwid;
-            const double w = circle_weight(col - cx, r - cy, rmax) - circle_weight(col - cx, r - cy, r20);
+    // ---- (A) interior of the annulus, weight 1: banded separable box means over the bounding box
+    box_means(c, k, 0, g.n, 0, g.n, y0, y1, x0, x1, vbuf, vcap, [&](int r, int col, double Is) {
+        const int dx = col - cx, dy = r - cy, d2 = dx * dx + dy * dy;
+        if (d2 < d2_full_out && d2 >= d2_zero_in) {
+            const double I = ld(c, r, col) - c.sky;
+            const double d = I - Is;
+            s[0] += I;
+            s[1] += d < 0.0 ? 0.0 : d;
+        }
+    });
+    // ---- (B) pixels cut by either circle: enumerated from the folded octant (centre is an integer pixel), one
+    // (entry, mirror image) per thread-step; the box mean is summed directly (k x k loads)
+    {
+        if (pm::tid() == 0) { sh.bc[8] = rmax; sh.bc[9] = r20; }
+        pm::sync();
+        const int ncol = A + 1, items = 2 * ncol;
+        for (int item = pm::tid(); item < items; item += kThreads) {
+            const int q = item / ncol, a = item - q * ncol;
+            const double r = sh.bc[8 + q];
+            int b_lo = 0, b_hi = 0;
+            if (!((double)a > r + 1.0)) fold_range(a, r, &b_lo, &b_hi);
+            eblo[item] = b_lo;
+            eoff[item] = (unsigned)(b_hi - b_lo);
+        }
+        pm::sync();
+        const int total = (int)block_scan_excl_array(sh, eoff, items);
+        for (int e8 = pm::tid(); e8 < total * 8; e8 += kThreads) {
+            const int e = e8 >> 3, sym = e8 & 7;
+            int lo = 0, hi = items - 1;          // last item with eoff[item] <= e
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((int)eoff[mid] <= e) lo = mid; else hi = mid - 1;
+            }
+            const int q = lo / ncol, a = lo - q * ncol, b = eblo[lo] + (e - (int)eoff[lo]);
+            // the 8 mirror images of (a, b); duplicates (a == b, b == 0) are skipped
+            int dx = (sym & 4) ? b : a, dy = (sym & 4) ? a : b;
+            if ((sym & 4) && a == b) continue;
+            if ((sym & 1) && dx == 0) continue;
+            if ((sym & 2) && dy == 0) continue;
+            if (sym & 1) dx = -dx;
+            if (sym & 2) dy = -dy;
+            const int col = cx + dx, r = cy + dy;
+            if (r < y0 || r >= y1 || col < x0 || col >= x1) continue;
+            const int d2 = a * a + b * b;
+            const bool cut_out = !(d2 < d2_full_out) && sqrt((double)d2) < rmax + pr;
+            if (q == 1 && cut_out) continue;                      // also cut by the outer circle: counted there
+            const double w = circle_weight(dx, dy, rmax) - circle_weight(dx, dy, r20);
             if (w == 0.0) continue;
             const double I = ld(c, r, col) - c.sky;
-            const double Is = box_mean(c, r, col, k, 0, g.n, 0, g.n);
-            const double d = I - Is;
+            const int h = k / 2;
+            double bs = 0.0;
+            for (int dr = 0; dr < k; dr++) {
+                const int rr = refl(r - h + dr, g.n);
+                double rs = 0.0;
+                for (int dc = 0; dc < k; dc++) rs += ld(c, rr, refl(col - h + dc, g.n)) - c.sky;
+                bs += rs;
+            }
+            const double d = I - bs / ((double)k * (double)k);
             s[0] += w * I;
             s[1] += w * (d < 0.0 ? 0.0 : d);
         }
     }
     block_sum<2>(sh, s);
-    // ---- background box search (casgm.py:367-398); one candidate position per thread per round
+    // ---- background box search (casgm.py:367-398); one candidate position per warp per round
     // positions are visited in the order (size 32: y = 0, 2, ..; x = 0, 2, ..), then size 16, then 8.
-    int bx = 0, by = 0, bsz = 32, found = 0;
+    int bx = 0, by = 0, bsz = 32;
     {
         int size = 32;
         for (;;) {
             // candidate grid for this size: x in {0, 2, ..} with x < W - size, y likewise; (0, 0) always
             const int nx = max(1, (g.n - size + 1) / 2), ny = max(1, (g.n - size + 1) / 2);
-            // number of x positions with 2*i < n - size  ->  ceil((n - size) / 2), at least 1
             const int total = nx * ny;
             int first = 0x7fffffff;
             for (int base = 0; base < total && first == 0x7fffffff; base += kWarps) {
@@ -1192,24 +1514,23 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
                 }
                 first = block_min_i(sh, ok ? idx : 0x7fffffff);
             }
-            if (first != 0x7fffffff) { by = (first / nx) * 2; bx = (first % nx) * 2; bsz = size; found = 1; break; }
+            if (first != 0x7fffffff) { by = (first / nx) * 2; bx = (first % nx) * 2; bsz = size; break; }
             if (size > 8) size /= 2;
             else {
-                // gave up (casgm.py:397-398): the walk stops with x = 0 and y = first even y >= H - size
+                // gave up (casgm.py:397-398): the walk stops with x = 0 and the first y >= H - size
                 bsz = size; bx = 0;
                 by = 2 * ny;
                 break;
             }
         }
     }
-    (void)found;
     const int rows = max(0, min(bsz, g.n - by)), cols = max(0, min(bsz, g.n - bx));
     double bd = 0.0;
-    for (int i = pm::tid(); i < rows * cols; i += kThreads) {
-        const int r = by + i / cols, col = bx + i % cols;
-        const double d = (ld(c, r, col) - c.sky) - box_mean(c, r, col, k, by, rows, bx, cols);
+    box_means(c, k, by, rows, bx, cols, by, by + rows, bx, bx + cols, vbuf, vcap, [&](int r, int col, double Is) {
+        const double d = (ld(c, r, col) - c.sky) - Is;
         bd += d < 0.0 ? 0.0 : d;
-    }
+    });
+    c.ar.release(mk);
     bd = block_sum1(sh, bd);
     const double bs = bd / (double)(rows * cols);
     const double area = 3.141592653589793 * (rmax * rmax - r20 * r20);
@@ -1237,6 +1558,8 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
     c.ar.s_top = 0; c.ar.g_top = 0; c.ar.overflow = 0;
     pm_row_t row;
     row_defaults(row);
+    PhaseClock& pc = c.pc;
+    pc.start(p.phase_cycles ? p.phase_cycles + (size_t)pm::block() * 16 : nullptr);
     uint8_t* seg_out = p.out.segmap_out ? p.out.segmap_out + (size_t)b * plane_elems : nullptr;
     int32_t* sidx_out = p.out.sorted_idx_out ? p.out.sorted_idx_out + (size_t)b * plane_elems : nullptr;
 
@@ -1253,6 +1576,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         }
     }
     if (seg_out) store_plane_u8(g, c.seg, seg_out);
+    pc.lap(0);   // pixelmap (+ segmap store)
     if (status == PM_ST_OK) phase_bbox(c, &edge);
     if (status == PM_ST_OK && !p.ov.segmap_in) row.object_edge = (double)edge;   // main.py:427 (only on the pixelmap path)
     if (p.ov.segmap_in && (p.flags & PM_STOP_AFTER_PIXELMAP)) row.object_edge = (double)edge;
@@ -1271,7 +1595,12 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         for (int r = pm::tid(); r < g.n; r += kThreads) ng += c.rowoff[r];
         c.n_g = (int)block_sum_u(sh, ng);
         const int n_g = c.n_g;
+        // arena order = shared-memory priority: the masked window (random access in minapix / r20-r80) first
+        c.bw = c.c1 - c.c0 + 1;
+        const int bh = c.r1 - c.r0 + 1;
+        c.mw = (T*)c.ar.alloc((size_t)c.bw * bh * sizeof(T));
         c.posR = (unsigned*)c.ar.alloc((size_t)n_g * 4);
+        Arena::Mark mk_list = c.ar.mark();
         unsigned* spA = (unsigned*)c.ar.alloc((size_t)n_g * 4);     // sorted positions end up here
         Arena::Mark mk_sorted = c.ar.mark();
         K* skA = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
@@ -1279,6 +1608,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         K* skB = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
         unsigned* spB = (unsigned*)c.ar.alloc((size_t)n_g * 4);
         unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+        const unsigned* cand = spA;
         if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }   // workspace contract violated
         SegStats st;
         st.sum = st.m10 = st.m01 = st.vmax = 0.0; st.argmax = 0; st.edge = edge;
@@ -1287,7 +1617,12 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         SortOut so;
         so.gini = so.m20 = -99.0; so.n_cand = 0; so.n_pos = 0;
         if (!done) {
+            for (int i = pm::tid(); i < c.bw * bh; i += kThreads) {
+                const int r = c.r0 + i / c.bw, col = c.c0 + i % c.bw;
+                c.mw[i] = bit_at(c.seg, g.nw, r, col) ? pm::ldg(c.img + (size_t)r * g.n + col) : nan_of(T());
+            }
             phase_list(c, skA, &st);
+            pc.lap(1);   // bbox, counts, window, raster list
             rmax2 = phase_rmax2(c, st, &cen_flat);
             rmax = p.ov.radius_in ? p.ov.radius_in[b] : pm::dsqrt((double)rmax2);
             row.rmax = rmax;
@@ -1302,6 +1637,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
                 c.ar.release(mk);
             }
             if (p.out.apermask_out) store_plane_u8(g, c.aper, p.out.apermask_out + (size_t)b * plane_elems);
+            pc.lap(2);   // rmax + aperture
             if (p.flags & PM_STOP_AFTER_RMAX) done = true;
         }
         if (!done) {
@@ -1314,32 +1650,33 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
                 pm::sync();
             }
             c.ar.release(mk_keys);    // drop skB, spB, hist
+            pc.lap(3);   // sort
             phase_gini_m20_cands(c, skA, spA, st, &so);
             if (p.flags & PM_DO_CAS) { row.gini = so.gini; row.m20 = so.m20; }
             row.n_candidates = (double)so.n_cand;
+            // reverse in place: the canonical DESCENDING order (value desc, flat index desc), asymmetry.py:94-95
+            for (int i = pm::tid(); i < n_g / 2; i += kThreads) {
+                const unsigned a = spA[i], z = spA[n_g - 1 - i];
+                spA[i] = z; spA[n_g - 1 - i] = a;
+            }
+            pm::sync();
             if (sidx_out) {
                 for (int i = pm::tid(); i < g.N; i += kThreads) {
                     int v = -1;
-                    if (i < so.n_pos) { const unsigned q = spA[n_g - 1 - i]; v = (int)(q >> 16) * g.n + (int)(q & 0xffff); }
+                    if (i < so.n_pos) { const unsigned q = spA[i]; v = (int)(q >> 16) * g.n + (int)(q & 0xffff); }
                     sidx_out[i] = v;
                 }
             }
             if (p.out.n_positive_out && pm::tid() == 0) p.out.n_positive_out[b] = so.n_pos;
-            c.ar.release(mk_sorted);  // drop skA (the sorted positions stay)
-            // ---- masked window over the bounding box
-            c.bw = c.c1 - c.c0 + 1;
-            const int bh = c.r1 - c.r0 + 1;
-            c.mw = (T*)c.ar.alloc((size_t)c.bw * bh * sizeof(T));
-            if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+            pm::sync();
+            // keep only the candidates (the first n_cand entries of the descending order)
+            c.ar.release(mk_list);
+            c.ar.keep(spA, (size_t)max(so.n_cand, 1) * 4);
+            pc.lap(4);   // gini, m20, candidates
+            (void)mk_sorted;
         }
         int cx = 0, cy = 0;
         if (!done) {
-            const int bh = c.r1 - c.r0 + 1;
-            for (int i = pm::tid(); i < c.bw * bh; i += kThreads) {
-                const int r = c.r0 + i / c.bw, col = c.c0 + i % c.bw;
-                c.mw[i] = bit_at(c.seg, g.nw, r, col) ? pm::ldg(c.img + (size_t)r * g.n + col) : nan_of(T());
-            }
-            pm::sync();
             // ---- minapix (main.py:467) or supplied centroid
             if (p.ov.centroid_in) {
                 cx = (int)p.ov.centroid_in[2 * b]; cy = (int)p.ov.centroid_in[2 * b + 1];
@@ -1347,19 +1684,20 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
                 status = PM_ST_NO_CANDIDATE; done = true;
             } else {
                 Arena::Mark mk = c.ar.mark();
-                int slices = 1;
-                if (so.n_cand < kWarps) slices = kWarps / so.n_cand;
+                const int groups = (so.n_cand + kCandBlock - 1) / kCandBlock;
+                int slices = (3 * kWarps + groups - 1) / groups;       // aim at >= 3 work items per warp
+                slices = max(1, min(slices, (n_g + 63) / 64));
                 double* a_arr = (double*)c.ar.alloc((size_t)so.n_cand * 8);
-                double* parts = (double*)c.ar.alloc((size_t)so.n_cand * slices * 16);
+                double* parts = (double*)c.ar.alloc((size_t)groups * slices * kCandBlock * 16);
                 int best = 0;
                 if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
                 else {
-                    phase_minapix(c, spA, so.n_cand, a_arr, parts, slices, &best);
+                    phase_minapix(c, cand, so.n_cand, a_arr, parts, slices, &best);
                     if (p.out.cand_a_out) {
                         for (int i = pm::tid(); i < p.out.cand_cap; i += kThreads)
                             p.out.cand_a_out[(size_t)b * p.out.cand_cap + i] = i < so.n_cand ? a_arr[i] : -99.0;
                     }
-                    const unsigned q = spA[n_g - 1 - best];
+                    const unsigned q = cand[best];
                     cy = (int)(q >> 16); cx = (int)(q & 0xffff);
                 }
                 pm::sync();
@@ -1367,6 +1705,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             }
         }
         if (!done) {
+            pc.lap(5);   // minapix
             row.apix_col = (double)cx; row.apix_row = (double)cy;
             // ---- calcA x3 (main.py:470-478)
             if (p.flags & (PM_DO_A | PM_DO_AS | PM_DO_CAS)) {
@@ -1378,6 +1717,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
                 if (p.flags & (PM_DO_A | PM_DO_CAS)) { row.A = ao.A; row.Abgr = ao.Abgr; }
                 if (p.flags & PM_DO_AS) { row.As = ao.As; row.As90 = ao.As90; }
             }
+            pc.lap(6);   // calcA x3
             // ---- r20, r80, C (main.py:491-492)
             if (p.flags & PM_DO_CAS) {
                 RadiiOut ro;
@@ -1389,6 +1729,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
                     status = PM_ST_BAD_BRACKET;
                 }
             }
+            pc.lap(7);   // r20 / r80
             // ---- smoothness (casgm.py:276; the call is commented out at main.py:494)
             if (p.flags & PM_DO_S) {
                 const double r20 = p.ov.r20_in ? p.ov.r20_in[b] : row.r20;
@@ -1398,6 +1739,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             }
         }
     }
+    pc.lap(8);   // smoothness (or whatever ended the cutout early)
     row.status = (double)status;
     if (pm::tid() == 0) p.rows[b] = row;
     pm::sync();
@@ -1416,13 +1758,26 @@ template <typename T> PM_DEV void analyse_body(const Params& p) {
     c.ar.init(smem + sm.arena, sm.arena_bytes, p.scratch + (size_t)pm::block() * p.scratch_per_cta, (size_t)p.scratch_per_cta);
     c.n_g = 0; c.r0 = c.c0 = 0; c.r1 = c.c1 = -1; c.posR = nullptr; c.mw = nullptr; c.bw = 0;
     build_tables(c);
-    for (;;) {
+    // Persistent CTA: galaxy indices come from a global work counter, fetched ONE AHEAD so that the next
+    // cutout can be pulled towards L2 (TMA bulk prefetch) while the current one is being analysed.
+    const size_t img_bytes = (size_t)c.g.N * sizeof(T);
+    if (pm::tid() == 0) c.sh->ia[0] = (int)pm::atomic_add(p.counter, 1ull);
+    pm::sync();
+    long long cur = (long long)c.sh->ia[0];
+    pm::sync();
+    while (cur < p.B) {
         if (pm::tid() == 0) c.sh->ia[0] = (int)pm::atomic_add(p.counter, 1ull);
         pm::sync();
-        const long long b = (long long)c.sh->ia[0];
+        const long long nxt = (long long)c.sh->ia[0];
         pm::sync();
-        if (b >= p.B) break;
-        analyse_one(c, p, b);
+        if (nxt < p.B && !(p.flags & PM_NO_PREFETCH)) {
+            const uintptr_t base = (uintptr_t)p.images + (size_t)nxt * img_bytes;
+            const uintptr_t lo = (base + 15) & ~(uintptr_t)15, hi = (base + img_bytes) & ~(uintptr_t)15;
+            for (uintptr_t a = lo + (uintptr_t)pm::tid() * 4096; a < hi; a += (uintptr_t)kThreads * 4096)
+                pm::prefetch_l2((const void*)a, (unsigned)min((uintptr_t)4096, hi - a));
+        }
+        analyse_one(c, p, cur);
+        cur = nxt;
     }
 }
 

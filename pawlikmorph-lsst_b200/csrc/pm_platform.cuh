@@ -101,6 +101,12 @@ PM_DEV float bits2f(unsigned a) { return __uint_as_float(a); }
 PM_DEV void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+PM_DEV long long clock() { return clock64(); }
+// explicit shared-memory loads through 32-bit addresses (hot loops: cheaper than generic 64-bit addressing)
+PM_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+PM_DEV unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+PM_DEV float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+PM_DEV double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 PM_DEV unsigned char* dyn_smem() {
     extern __shared__ __align__(16) unsigned char pm_dyn_smem[];
     return pm_dyn_smem;

@@ -186,6 +186,11 @@ PM_DEV double bits2d(long long a) { double u; memcpy(&u, &a, 8); return u; }
 PM_DEV unsigned f2bits(float a) { unsigned u; memcpy(&u, &a, 4); return u; }
 PM_DEV float bits2f(unsigned a) { float u; memcpy(&u, &a, 4); return u; }
 PM_DEV void prefetch_l2(const void*, unsigned) {}
+PM_DEV long long clock() { return 0; }
+PM_DEV unsigned smem_addr(const void* p) { return (unsigned)((const unsigned char*)p - g_blk->smem); }
+PM_DEV unsigned lds_u32(unsigned a) { unsigned v; memcpy(&v, g_blk->smem + a, 4); return v; }
+PM_DEV float lds_f32(unsigned a) { float v; memcpy(&v, g_blk->smem + a, 4); return v; }
+PM_DEV double lds_f64(unsigned a) { double v; memcpy(&v, g_blk->smem + a, 8); return v; }
 PM_DEV unsigned char* dyn_smem() { return g_blk->smem; }
 }  // namespace pm
 
