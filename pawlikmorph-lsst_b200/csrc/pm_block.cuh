@@ -28,6 +28,7 @@ struct Sh {
     double fh[132];                  // upper bounds
     unsigned scan_tmp[kWarps + 2];
     unsigned colmask[24];            // OR of all segmap rows (PM_MAX_N / 32 words)
+    unsigned long long mbar[2];      // mbarriers of the two TMA staging buffers (pixelmap)
     int ia[8];                       // integer reductions (atomics)
     int status;
 };

@@ -137,6 +137,7 @@ template <typename T> struct Ctx {
     unsigned* posR;      // raster list of segmap pixels, (row << 16) | col
     T* mw;               // masked window over the bounding box (NaN outside the segmap)
     PhaseClock pc;       // tuning aid
+    unsigned mbar_phase[2];   // parity of the two staging mbarriers (uniform across the CTA)
     int bw;              // window width
 };
 
@@ -232,13 +233,16 @@ PM_DEV void patch_sums(const T* xb, int rlo, int n, int fs_rt, int a0, int b0, d
     }
 }
 
-// fast path: the image rows a band of shrunk rows needs are staged in shared memory with fully coalesced,
-// independent loads (this is the only pass that streams the image from HBM); each thread then forms the
-// (fs+1) x (fs+1) patch sums of one shrunk pixel from the staged rows.  Reports min |Z - thr| and max |x|
-// for the band test.  xb: staging buffer; R: shrunk rows per band.
+// fast path: the image rows a band of shrunk rows needs are staged in shared memory — by a TMA bulk copy
+// (cp.async.bulk, completion on an mbarrier, double-buffered so that the next band lands while the current
+// one is consumed) when the band is 16-byte aligned, by coalesced independent loads otherwise.  This is the
+// only pass that streams the image from HBM.  Each thread then forms the (fs+1) x (fs+1) patch sums of one
+// shrunk pixel from the staged rows.  Reports min |Z - thr| and max |x| for the band test.
+// xb0 / xb1: the two staging buffers; R: shrunk rows per band.
 template <typename T, int FS>
-PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* minabs, double* maxabs, T* xb, int R) {
+PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* minabs, double* maxabs, T* xb0, T* xb1, int R) {
     const Geo& g = c.g;
+    Sh& sh = *c.sh;
     const int fs = g.fs, h = g.h, n = g.n, m = g.m;
     const double inv = 1.0 / ((double)fs * (double)fs);
     double mn = 1e300;
@@ -246,30 +250,58 @@ PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* mi
     int faint = 0, bad = 0;
     const int cm = m / 2;
     for (int i = pm::tid(); i < m * g.mw; i += kThreads) zb[i] = 0;
-    for (int band = 0; band < m; band += R) {
-        const int rows = min(R, m - band);
-        // image rows [rlo, rhi] cover every (reflected) row the band touches
-        const int rlo = max(0, (int)c.i0[band] - h), rhi = min(n - 1, (int)c.i0[band + rows - 1] + h + 1);
-        const int cnt = (rhi - rlo + 1) * n;
-        const T* src = c.img + (size_t)rlo * n;
-        int i = pm::tid();
-        for (; i + 3 * kThreads < cnt; i += 4 * kThreads) {     // four independent loads in flight per thread
-            const T x0 = pm::ldg(src + i), x1 = pm::ldg(src + i + kThreads), x2 = pm::ldg(src + i + 2 * kThreads),
-                    x3 = pm::ldg(src + i + 3 * kThreads);
-            xb[i] = x0; xb[i + kThreads] = x1; xb[i + 2 * kThreads] = x2; xb[i + 3 * kThreads] = x3;
-            const float ax = fmaxf(fmaxf(fabsf((float)x0), fabsf((float)x1)), fmaxf(fabsf((float)x2), fabsf((float)x3)));
-            const float sm = fabsf((float)x0) + fabsf((float)x1) + fabsf((float)x2) + fabsf((float)x3);
-            if (!(sm <= 3.0e38f)) bad = 1;       // inf / nan (or beyond float range): let the exact path decide
-            mx = fmaxf(mx, ax);
+    pm::sync();      // the bit plane is filled with atomics below
+    const int nbands = (m + R - 1) / R;
+    auto band_rows = [&](int k, int* rlo, int* cnt) {
+        const int band = k * R, rows = min(R, m - band);
+        *rlo = max(0, (int)c.i0[band] - h);
+        const int rhi = min(n - 1, (int)c.i0[band + rows - 1] + h + 1);
+        *cnt = (rhi - *rlo + 1) * n;
+    };
+    auto tma_ok = [&](int rlo, int cnt) {
+        return (((uintptr_t)(c.img + (size_t)rlo * n)) & 15) == 0 && (((size_t)cnt * sizeof(T)) & 15) == 0;
+    };
+    auto issue = [&](int k) {       // thread 0: start the bulk copy of band k if it qualifies
+        int rlo, cnt;
+        band_rows(k, &rlo, &cnt);
+        if (tma_ok(rlo, cnt) && pm::tid() == 0)
+            pm::tma_load_1d((k & 1) ? xb1 : xb0, c.img + (size_t)rlo * n, (unsigned)((size_t)cnt * sizeof(T)), &sh.mbar[k & 1]);
+    };
+    issue(0);
+    for (int k = 0; k < nbands; k++) {
+        const int band = k * R, rows = min(R, m - band);
+        int rlo, cnt;
+        band_rows(k, &rlo, &cnt);
+        T* xb = (k & 1) ? xb1 : xb0;
+        if (k + 1 < nbands) issue(k + 1);
+        if (tma_ok(rlo, cnt)) {
+            pm::mbar_wait(&sh.mbar[k & 1], c.mbar_phase[k & 1]);
+            c.mbar_phase[k & 1] ^= 1u;
+            for (int i = pm::tid(); i < cnt; i += kThreads) {          // max |x| of the staged band
+                const float ax = fabsf((float)xb[i]);
+                if (!(ax <= 3.0e38f)) bad = 1;       // inf / nan (or beyond float range): let the exact path decide
+                mx = fmaxf(mx, ax);
+            }
+        } else {
+            const T* src = c.img + (size_t)rlo * n;
+            int i = pm::tid();
+            for (; i + 3 * kThreads < cnt; i += 4 * kThreads) {     // four independent loads in flight per thread
+                const T x0 = pm::ldg(src + i), x1 = pm::ldg(src + i + kThreads), x2 = pm::ldg(src + i + 2 * kThreads),
+                        x3 = pm::ldg(src + i + 3 * kThreads);
+                xb[i] = x0; xb[i + kThreads] = x1; xb[i + 2 * kThreads] = x2; xb[i + 3 * kThreads] = x3;
+                const float sm = fabsf((float)x0) + fabsf((float)x1) + fabsf((float)x2) + fabsf((float)x3);
+                if (!(sm <= 3.0e38f)) bad = 1;
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf((float)x0), fabsf((float)x1)), fmaxf(fabsf((float)x2), fabsf((float)x3))));
+            }
+            for (; i < cnt; i += kThreads) {
+                const T x = pm::ldg(src + i);
+                xb[i] = x;
+                const float ax = fabsf((float)x);
+                if (!(ax <= 3.0e38f)) bad = 1;
+                mx = fmaxf(mx, ax);
+            }
+            pm::sync();
         }
-        for (; i < cnt; i += kThreads) {
-            const T x = pm::ldg(src + i);
-            xb[i] = x;
-            const float ax = fabsf((float)x);
-            if (!(ax <= 3.0e38f)) bad = 1;
-            mx = fmaxf(mx, ax);
-        }
-        pm::sync();
         for (int item = pm::tid(); item < rows * m; item += kThreads) {
             const int rb = item / m, j = item - rb * m;
             const int ii = band + rb;
@@ -286,11 +318,11 @@ PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* mi
             if (z > c.thr) pm::atomic_or(&zb[ii * g.mw + (j >> 5)], 1u << (j & 31));
             if (ii == cm && j == cm) faint = (z < c.thr) ? 1 : 0;
         }
-        pm::sync();
+        pm::sync();      // everybody is done with this buffer before band k + 2 is copied into it
     }
     if (bad) mn = 0.0;
-    *minabs = block_min(*c.sh, mn);
-    *maxabs = block_max(*c.sh, (double)mx * 1.0000002);   // float rounding of |x| never under-estimates the band
+    *minabs = block_min(sh, mn);
+    *maxabs = block_max(sh, (double)mx * 1.0000002);   // float rounding of |x| never under-estimates the band
     *centre_faint = pm::sync_or(faint);
 }
 
@@ -452,15 +484,16 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
         double mn, mx;
         Arena::Mark mk = c.ar.mark();
         int R = max(1, kThreads / g.m);                            // about one shrunk pixel per thread per band
-        for (;;) {                                                  // staging buffer <= 40 KB
-            const int nrows = (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3;
-            if (R == 1 || (size_t)nrows * g.n * sizeof(T) <= 40960) break;
+        for (;;) {                                                  // two staging buffers of <= 24 KB each
+            const int nr = (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3;
+            if (R == 1 || (size_t)nr * g.n * sizeof(T) <= 24576) break;
             R--;
         }
         const int nrows = min(g.n, (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3);
-        T* xb = (T*)c.ar.alloc((size_t)nrows * g.n * sizeof(T));
-        if (g.fs == 3) pixelmap_fast<T, 3>(c, zb, &faint, &mn, &mx, xb, R);
-        else pixelmap_fast<T, 0>(c, zb, &faint, &mn, &mx, xb, R);
+        T* xb0 = (T*)c.ar.alloc((size_t)nrows * g.n * sizeof(T));
+        T* xb1 = (T*)c.ar.alloc((size_t)nrows * g.n * sizeof(T));
+        if (g.fs == 3) pixelmap_fast<T, 3>(c, zb, &faint, &mn, &mx, xb0, xb1, R);
+        else pixelmap_fast<T, 0>(c, zb, &faint, &mn, &mx, xb0, xb1, R);
         c.ar.release(mk);
         // |Z_fast - Z_scipy| <= (2 n + fs^2 + 8) * max|x| * 2^-52 (running-sum error growth); x4 margin
         const double band = 4.0 * (2.0 * g.n + (double)(g.fs * g.fs) + 8.0) * mx * 2.220446049250313e-16;
@@ -828,9 +861,11 @@ PM_DEV void minapix_item(const Ctx<T>& c, const int (&px)[kCandBlock], const int
             const bool t_in_seg = inwin[j] && (w[j] == w[j]);
             double mt = 0.0;
             if (t_in_seg) mt = (double)w[j] - c.sky;
-            if (b1[j] & 1u) { num[j] += fabs(v - mt); den[j] += av; }
+            const bool a1 = (b1[j] & 1u) != 0;
+            pm::dadd_if(a1, num[j], fabs(v - mt));
+            pm::dadd_if(a1, den[j], av);
             // mirror position inside the image but outside the map: there M = 0 and M180 = v
-            if ((b2[j] & 1u) && inb[j] && !t_in_seg) num[j] += av;
+            pm::dadd_if((b2[j] & 1u) && inb[j] && !t_in_seg, num[j], av);
         }
     }
 }
@@ -930,17 +965,14 @@ PM_DEV void dilate9(const Geo& g, const unsigned* seg, unsigned* dil, unsigned* 
 struct BgrCtx {
     const unsigned* dil;
     const unsigned* rowoff;   // exclusive prefix of dilated-mask pixels per row, [n + 1]
+    const unsigned* wordoff;  // ... and per (row, word), [n * nw]
     int nb, nm;
     int nfree;                // pixels before the first row that holds a mask pixel: there, select(j) == j
 };
-// rank of a mask pixel among mask pixels in raster order
+// rank of a mask pixel among mask pixels in raster order (wordoff: exclusive prefix per (row, word))
 PM_DEV int mask_rank(const Geo& g, const BgrCtx& b, int r, int col) {
-    int k = (int)b.rowoff[r];
-    const unsigned* row = b.dil + r * g.nw;
     const int w = col >> 5;
-    for (int i = 0; i < w; i++) k += pm::popc(row[i]);
-    k += pm::popc(row[w] & ((1u << (col & 31)) - 1u));
-    return k;
+    return (int)b.wordoff[r * g.nw + w] + pm::popc(b.dil[r * g.nw + w] & ((1u << (col & 31)) - 1u));
 }
 // flat index of the j-th (0-based) background pixel in raster order
 PM_DEV int bgr_select(const Geo& g, const BgrCtx& b, int j) {
@@ -961,14 +993,12 @@ PM_DEV int bgr_select(const Geo& g, const BgrCtx& b, int j) {
     }
     return lo * g.n;   // unreachable
 }
-// background image B of asymmetry.py:214-244 at (r, col)
-template <typename T> PM_DEV double bgr_value(const Ctx<T>& c, const BgrCtx& b, int r, int col) {
-    const Geo& g = c.g;
-    if (!bit_at(b.dil, g.nw, r, col)) return ld(c, r, col) - c.sky;
-    const int k = mask_rank(g, b, r, col) % b.nb;      // :227-239 truncate or tile
-    const int f = bgr_select(g, b, k);
-    const int fr = f / g.n;
-    return ld(c, fr, f - fr * g.n) - c.sky;
+// background image B of asymmetry.py:214-244: flat index of the image pixel whose value B takes at (r, col)
+PM_DEV int bgr_source(const Geo& g, const BgrCtx& b, int r, int col) {
+    if (!bit_at(b.dil, g.nw, r, col)) return r * g.n + col;
+    int k = mask_rank(g, b, r, col);
+    if (k >= b.nb) k %= b.nb;                          // :227-239 truncate or tile
+    return bgr_select(g, b, k);
 }
 
 struct AsymOut { double A, Abgr, As, As90; };
@@ -982,7 +1012,7 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     const bool noise = do_img && !(c.flags & PM_NO_NOISECORRECT);
     const bool rot90 = (c.flags & PM_A_ANGLE90) != 0;
     BgrCtx b;
-    b.dil = c.dil; b.rowoff = c.rowoff; b.nb = 0; b.nm = 0; b.nfree = 0;
+    b.dil = c.dil; b.rowoff = c.rowoff; b.wordoff = tmp_plane; b.nb = 0; b.nm = 0; b.nfree = 0;
     if (noise) {
         dilate9(g, c.seg, c.dil, tmp_plane);
         for (int r = pm::tid(); r < g.n; r += kThreads) {
@@ -998,6 +1028,11 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
             if (c.rowoff[r + 1] != c.rowoff[r]) fm = min(fm, r);
         fm = block_min_i(sh, fm);
         b.nfree = (fm == 0x7fffffff) ? g.N : fm * g.n;
+        for (int r = pm::tid(); r < g.n; r += kThreads) {        // per-word prefix (the dilation scratch is free again)
+            unsigned run = c.rowoff[r];
+            for (int w = 0; w < g.nw; w++) { tmp_plane[r * g.nw + w] = run; run += (unsigned)pm::popc(c.dil[r * g.nw + w]); }
+        }
+        pm::sync();
     }
     const bool bgr_ok = noise && b.nb > 0 && b.nm > 1;      // asymmetry.py:225-226
     c.pc.lap(9);    // (calcA: dilation + row scan)
@@ -1013,18 +1048,28 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
         const bool in180 = r180 >= 0 && r180 < g.n && c180 >= 0 && c180 < g.n;
         const bool in90 = r90 >= 0 && r90 < g.n && c90 >= 0 && c90 < g.n;
         if (do_img) {
-            const double I = ld(c, r, col) - c.sky;
-            double Ir = 0.0;
-            if (rot90) { if (in90) Ir = ld(c, r90, c90) - c.sky; }
-            else if (in180) Ir = ld(c, r180, c180) - c.sky;
-            s[0] += fabs(I - Ir);
-            s[1] += fabs(I);
+            // source indices first (shared-memory work only), then all image loads back to back
+            const int fI = r * g.n + col;
+            int fR = -1, fB = -1, fBr = -1;
+            if (rot90) { if (in90) fR = r90 * g.n + c90; }
+            else if (in180) fR = r180 * g.n + c180;
             if (bgr_ok) {
                 // the background image is rotated about the SWAPPED centre (asymmetry.py:245)
                 const int rb = 2 * cx - r, cb = 2 * cy - col;
-                const double B = bgr_value(c, b, r, col);
-                double Br = 0.0;
-                if (rb >= 0 && rb < g.n && cb >= 0 && cb < g.n) Br = bgr_value(c, b, rb, cb);
+                fB = bgr_source(g, b, r, col);
+                if (rb >= 0 && rb < g.n && cb >= 0 && cb < g.n) fBr = bgr_source(g, b, rb, cb);
+            }
+            const T xI = pm::ldg(c.img + fI);
+            const T xR = pm::ldg(c.img + (fR >= 0 ? fR : fI));
+            const T xB = pm::ldg(c.img + (fB >= 0 ? fB : fI));
+            const T xBr = pm::ldg(c.img + (fBr >= 0 ? fBr : fI));
+            const double I = (double)xI - c.sky;
+            const double Ir = fR >= 0 ? (double)xR - c.sky : 0.0;
+            s[0] += fabs(I - Ir);
+            s[1] += fabs(I);
+            if (bgr_ok) {
+                const double B = (double)xB - c.sky;
+                const double Br = fBr >= 0 ? (double)xBr - c.sky : 0.0;
                 s[2] += fabs(B - Br);
             }
         }
@@ -1324,29 +1369,82 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     const int k20 = kfound[0], k80 = kfound[1];
     c.pc.lap(12);   // (r20/r80: exact walk evaluations)
     if (k20 < 0 || k80 < 0) { c.ar.release(mk); return; }   // the reference walks to r <= 0 and raises
-    // brentq on [r_k, r_k + δ] for both fractions, in lock-step
+    // brentq on [r_k, r_k + δ] for both fractions, in lock-step.  Inside a bracket only the pixels with
+    // lo - pr <= d < hi + pr can change weight: cache them once (entry + table value), everything closer to
+    // the centre is a constant base sum.  One cached pixel per thread-step and evaluation.
     Brent b[2];
     const int kk[2] = {k20, k80};
-    if (pm::tid() == 0) {
-        for (int q = 0; q < 2; q++) { sh.fk[2 * q] = sh.rk[kk[q]]; sh.fk[2 * q + 1] = sh.rk[kk[q]] + delta; }
+    double blo_r[2], bhi_r[2];
+    for (int q = 0; q < 2; q++) { blo_r[q] = sh.rk[kk[q]]; bhi_r[q] = sh.rk[kk[q]] + delta; }
+    const double pr = 0.5 * sqrt(2.0);
+    const int ncol = f.A + 1;
+    double base[2] = {0.0, 0.0};
+    for (int item = pm::tid(); item < 2 * ncol; item += kThreads) {
+        const int q = item / ncol, a = item - q * ncol;
+        int bl = 0, bh = 0;
+        if (!((double)a > bhi_r[q] + 1.0)) {
+            bl = min(first_not_inside(a, blo_r[q] - pr), a + 1);
+            bh = min(max(first_not_inside(a, bhi_r[q] + pr), bl), a + 1);
+        }
+        if (bl > 0) base[q] += f.P[tri(a, bl - 1)];
+        eblo[item] = bl;
+        eoff[item] = (unsigned)(bh - bl);
     }
     pm::sync();
-    eval_flux(sh, f, sh.fk, 4, eoff, eblo);
-    for (int q = 0; q < 2; q++)
-        brent_init(b[q], sh.fk[2 * q], sh.fk[2 * q + 1], sh.bc[2 * q] / total - fr[q], sh.bc[2 * q + 1] / total - fr[q]);
+    const int ncache = (int)block_scan_excl_array(sh, eoff, 2 * ncol);
+    block_sum<2>(sh, base);
+    unsigned* cent = (unsigned*)c.ar.alloc((size_t)max(ncache, 1) * 4);
+    double* ctv = (double*)c.ar.alloc((size_t)max(ncache, 1) * 8);
+    if (c.ar.overflow) { c.ar.release(mk); return; }
+    for (int e = pm::tid(); e < ncache; e += kThreads) {
+        int lo = 0, hi = 2 * ncol - 1;          // last item with eoff[item] <= e
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)eoff[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const int q = lo / ncol, a = lo - q * ncol, bb = eblo[lo] + (e - (int)eoff[lo]);
+        cent[e] = ((unsigned)q << 30) | ((unsigned)a << 15) | (unsigned)bb;
+        ctv[e] = f.T[tri(a, bb)];
+    }
     pm::sync();
+    // F_q(r_q) for the active fractions -> sh.bc[q]
+    auto eval_cached = [&](const double (&rq)[2], const bool (&act)[2]) {
+        double acc[2] = {0.0, 0.0};
+        for (int e = pm::tid(); e < ncache; e += kThreads) {
+            const unsigned ce = cent[e];
+            const int q = (int)(ce >> 30);
+            if (!act[q]) continue;
+            const double v = ctv[e] * circle_weight((int)((ce >> 15) & 0x7fff), (int)(ce & 0x7fff), rq[q]);
+            if (q == 0) acc[0] += v; else acc[1] += v;
+        }
+        block_sum<2>(sh, acc);
+        if (pm::tid() == 0) { sh.bc[0] = base[0] + acc[0]; sh.bc[1] = base[1] + acc[1]; }
+        pm::sync();
+    };
+    const double fr2[2] = {0.2, 0.8};
+    {
+        const bool both[2] = {true, true};
+        double flo[2], fhi[2];
+        eval_cached(blo_r, both);
+        flo[0] = sh.bc[0]; flo[1] = sh.bc[1];
+        pm::sync();
+        eval_cached(bhi_r, both);
+        fhi[0] = sh.bc[0]; fhi[1] = sh.bc[1];
+        pm::sync();
+        for (int q = 0; q < 2; q++) brent_init(b[q], blo_r[q], bhi_r[q], flo[q] / total - fr2[q], fhi[q] / total - fr2[q]);
+    }
     for (;;) {
-        int nact = 0;
-        int slot[2] = {-1, -1};
+        bool act[2];
+        double rq[2];
         for (int q = 0; q < 2; q++) {
             if (b[q].state == 0) brent_step(b[q]);
-            if (b[q].state == 0) { slot[q] = nact; if (pm::tid() == 0) sh.fk[nact] = b[q].xcur; nact++; }
+            act[q] = b[q].state == 0;
+            rq[q] = b[q].xcur;
         }
-        if (nact == 0) break;
-        pm::sync();
-        eval_flux(sh, f, sh.fk, nact, eoff, eblo);
+        if (!act[0] && !act[1]) break;
+        eval_cached(rq, act);
         for (int q = 0; q < 2; q++)
-            if (slot[q] >= 0) b[q].fcur = sh.bc[slot[q]] / total - fr[q];
+            if (act[q]) b[q].fcur = sh.bc[q] / total - fr2[q];
         pm::sync();
     }
     c.ar.release(mk);
@@ -1377,7 +1475,13 @@ PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int c
             const int r = band + q;
             const int cc = clo + refl(ca - clo - h + e, clen);
             double sum = 0.0;
-            for (int dr = 0; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
+            int dr = 0;
+            for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
+                const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
+                             x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
+                sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
+            }
+            for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
             vbuf[item] = sum;
         }
         pm::sync();
@@ -1476,7 +1580,13 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
             for (int dr = 0; dr < k; dr++) {
                 const int rr = refl(r - h + dr, g.n);
                 double rs = 0.0;
-                for (int dc = 0; dc < k; dc++) rs += ld(c, rr, refl(col - h + dc, g.n)) - c.sky;
+                int dc = 0;
+                for (; dc + 3 < k; dc += 4) {
+                    const double x0 = ld(c, rr, refl(col - h + dc, g.n)), x1 = ld(c, rr, refl(col - h + dc + 1, g.n)),
+                                 x2 = ld(c, rr, refl(col - h + dc + 2, g.n)), x3 = ld(c, rr, refl(col - h + dc + 3, g.n));
+                    rs += x0 - c.sky; rs += x1 - c.sky; rs += x2 - c.sky; rs += x3 - c.sky;
+                }
+                for (; dc < k; dc++) rs += ld(c, rr, refl(col - h + dc, g.n)) - c.sky;
                 bs += rs;
             }
             const double d = I - bs / ((double)k * (double)k);
@@ -1617,9 +1727,11 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         SortOut so;
         so.gini = so.m20 = -99.0; so.n_cand = 0; so.n_pos = 0;
         if (!done) {
-            for (int i = pm::tid(); i < c.bw * bh; i += kThreads) {
-                const int r = c.r0 + i / c.bw, col = c.c0 + i % c.bw;
-                c.mw[i] = bit_at(c.seg, g.nw, r, col) ? pm::ldg(c.img + (size_t)r * g.n + col) : nan_of(T());
+            for (int wr = pm::warp(); wr < bh; wr += kWarps) {        // one window row per warp, loads independent
+                const int r = c.r0 + wr;
+                const T* src = c.img + (size_t)r * g.n + c.c0;
+                for (int x = pm::lane(); x < c.bw; x += 32)
+                    c.mw[wr * c.bw + x] = bit_at(c.seg, g.nw, r, c.c0 + x) ? pm::ldg(src + x) : nan_of(T());
             }
             phase_list(c, skA, &st);
             pc.lap(1);   // bbox, counts, window, raster list
@@ -1757,6 +1869,8 @@ template <typename T> PM_DEV void analyse_body(const Params& p) {
     c.rstart = (uint16_t*)(smem + sm.rstart);
     c.ar.init(smem + sm.arena, sm.arena_bytes, p.scratch + (size_t)pm::block() * p.scratch_per_cta, (size_t)p.scratch_per_cta);
     c.n_g = 0; c.r0 = c.c0 = 0; c.r1 = c.c1 = -1; c.posR = nullptr; c.mw = nullptr; c.bw = 0;
+    c.mbar_phase[0] = c.mbar_phase[1] = 0u;
+    if (pm::tid() == 0) { pm::mbar_init(&c.sh->mbar[0], 1); pm::mbar_init(&c.sh->mbar[1], 1); pm::mbar_fence_init(); }
     build_tables(c);
     // Persistent CTA: galaxy indices come from a global work counter, fetched ONE AHEAD so that the next
     // cutout can be pulled towards L2 (TMA bulk prefetch) while the current one is being analysed.

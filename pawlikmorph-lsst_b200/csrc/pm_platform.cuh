@@ -101,6 +101,31 @@ PM_DEV float bits2f(unsigned a) { return __uint_as_float(a); }
 PM_DEV void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (one elected thread issues; all wait)
+PM_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+PM_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PM_DEV void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+PM_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+}
+// acc += x when pred (a predicated DADD, no select)
+PM_DEV void dadd_if(bool pred, double& acc, double x) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(x), "r"((unsigned)pred));
+}
 PM_DEV long long clock() { return clock64(); }
 // explicit shared-memory loads through 32-bit addresses (hot loops: cheaper than generic 64-bit addressing)
 PM_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

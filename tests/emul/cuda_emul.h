@@ -186,6 +186,16 @@ PM_DEV double bits2d(long long a) { double u; memcpy(&u, &a, 8); return u; }
 PM_DEV unsigned f2bits(float a) { unsigned u; memcpy(&u, &a, 4); return u; }
 PM_DEV float bits2f(unsigned a) { float u; memcpy(&u, &a, 4); return u; }
 PM_DEV void prefetch_l2(const void*, unsigned) {}
+PM_DEV void mbar_init(unsigned long long* bar, unsigned) { *bar = 0; }
+PM_DEV void mbar_fence_init() {}
+PM_DEV void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    memcpy(smem_dst, gsrc, bytes);   // the emulated copy completes at once
+    (*bar)++;
+}
+PM_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {   // phase with this parity completed <=> current parity differs
+    while (((*bar) & 1ull) == (unsigned long long)parity) { g_blk->progress++; pm_emul::yield_(); }
+}
+PM_DEV void dadd_if(bool pred, double& acc, double x) { if (pred) acc += x; }
 PM_DEV long long clock() { return 0; }
 PM_DEV unsigned smem_addr(const void* p) { return (unsigned)((const unsigned char*)p - g_blk->smem); }
 PM_DEV unsigned lds_u32(unsigned a) { unsigned v; memcpy(&v, g_blk->smem + a, 4); return v; }
