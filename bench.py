@@ -324,8 +324,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PM_BENCH_BATCH", 65536)),
-                    help="galaxies resident per GPU (BASELINE configs[2] holds 262144: pass --batch 262144)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PM_BENCH_BATCH", 262144)),
+                    help="galaxies resident per GPU (BASELINE.json configs[2]: 262144; reduced automatically if HBM is short)")
     ap.add_argument("--e2e-batch", type=int, default=8192)
     ap.add_argument("--e2e-chunk", type=int, default=2048)
     ap.add_argument("--cpu-sample", type=int, default=0)

@@ -19,8 +19,10 @@ from ._lib import lib
 _ws_cache = {}
 
 
-def _workspace(device, nbytes):
-    key = (device.type, device.index)
+def _workspace(device, nbytes, stream):
+    # one workspace per (device, stream): launches on different streams may run concurrently and each
+    # needs its own work counter and per-CTA scratch
+    key = (device.type, device.index, int(stream.cuda_stream))
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -125,7 +127,7 @@ def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segma
             if B == 0:
                 return res
             wsb = L.pm_workspace_bytes(B, n, dtype)
-            ws = _workspace(dev, wsb)
+            ws = _workspace(dev, wsb, st)
             rc = L.pm_analyse_batch(images.data_ptr(), dtype, B, n, _ptr(sky_t), _ptr(err_t), int(filter_size),
                                     int(flags), C.byref(ov), C.byref(out), res.rows.data_ptr(), ws.data_ptr(), wsb,
                                     C.c_void_p(st.cuda_stream))
@@ -151,18 +153,21 @@ def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="c
     sky = np.broadcast_to(np.asarray(sky, dtype=np.float64), (B,))
     sky_err = np.broadcast_to(np.asarray(sky_err, dtype=np.float64), (B,))
     rows = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
-    copy_stream = torch.cuda.Stream(dev)
-    for s in range(0, B, chunk):
+    # two streams, alternating chunks: the host->device copy of chunk i+1 overlaps the kernel of chunk i
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for i, s in enumerate(range(0, B, chunk)):
         e = min(B, s + chunk)
         xs = x[s:e]
         if not xs.is_pinned():
             xs = xs.pin_memory()
-        with torch.cuda.stream(copy_stream):
+        st = streams[i & 1]
+        with torch.cuda.stream(st):
             d = xs.to(dev, non_blocking=True)
             r = analyse_batch(d, torch.from_numpy(sky[s:e].copy()), torch.from_numpy(sky_err[s:e].copy()),
-                              filter_size, flags, stream=copy_stream, **kw)
+                              filter_size, flags, stream=st, **kw)
             rows[s:e].copy_(r.rows, non_blocking=True)
-    copy_stream.synchronize()
+    for st in streams:
+        st.synchronize()
     return rows.numpy()
 
 
