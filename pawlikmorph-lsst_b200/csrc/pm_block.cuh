@@ -190,29 +190,54 @@ struct Arena {
     }
 };
 
+// lanes of the warp that hold the same 8-bit digit as this lane (invalid lanes match nobody): the classic
+// ballot multisplit — 8 independent ballots instead of one __match_any_sync (MATCH.ANY costs ~300 cycles)
+PM_DEV unsigned same_digit_mask(unsigned d, bool valid) {
+    unsigned m = pm::ballot(valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const unsigned v = pm::ballot((d >> b) & 1u);
+        m &= ((d >> b) & 1u) ? v : ~v;
+    }
+    return m;
+}
+
 // ---- stable LSD radix sort of (key, value) pairs, ascending, 8 bits per pass ----------------
 // hist: kWarps * 256 counters.  Returns 0 when the sorted data ends in (keyA, valA), 1 for B.
 template <typename K>
-PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* valB, unsigned* hist, int n) {
+PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* valB, unsigned* hist, int n,
+                            unsigned long long* dbg = nullptr) {
+    long long tlast = dbg ? pm::clock() : 0;
+    auto lap = [&](int slot) { if (dbg) { long long now = pm::clock(); if (pm::tid() == 0) dbg[slot] += (unsigned long long)(now - tlast); tlast = now; } };
     const int w = pm::warp(), l = pm::lane(), t = pm::tid();
     int tile = (n + kWarps - 1) / kWarps;
     tile = (tile + 31) & ~31;
-    const int lo = w * tile, hi = min(n, lo + tile);
+    const int lo = min(n, w * tile), hi = min(n, lo + tile);
     K* src = keyA; unsigned* sv = valA; K* dst = keyB; unsigned* dv = valB;
     int where = 0;
     for (int pass = 0; pass < (int)sizeof(K); pass++) {
         const int shift = pass * 8;
         for (int i = t; i < kWarps * 256; i += kThreads) hist[i] = 0;
         pm::sync();
-        for (int base = lo; base < hi; base += 32) {
-            int i = base + l;
-            bool valid = i < hi;
-            unsigned d = valid ? (unsigned)((src[i] >> shift) & 0xff) : 256u + (unsigned)l;
-            unsigned m = pm::match_any(d);
-            if (valid && l == pm::ffs(m) - 1) hist[w * 256 + d] += (unsigned)pm::popc(m);
-            pm::syncwarp();
+        // sweep 1: per-warp digit counts.  Four chunks per step: their loads and ballot chains are independent
+        // (the loop is a chain of dependent ALU ops otherwise); counts go in with shared-memory atomics.
+        for (int base = lo; base < hi; base += 128) {
+            unsigned d[4], m[4];
+            bool valid[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + 32 * u + l;
+                valid[u] = i < hi;
+                d[u] = valid[u] ? (unsigned)((src[valid[u] ? i : lo] >> shift) & 0xff) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) m[u] = same_digit_mask(d[u], valid[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (valid[u] && l == pm::ffs(m[u]) - 1) pm::atomic_add(&hist[w * 256 + d[u]], (unsigned)pm::popc(m[u]));
         }
         pm::sync();
+        lap(13);
         unsigned total = 0;
         if (t < 256) {
             for (int ww = 0; ww < kWarps; ww++) {
@@ -229,23 +254,37 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
             for (int ww = 0; ww < kWarps; ww++) hist[ww * 256 + t] += basep;
         }
         pm::sync();
-        for (int base = lo; base < hi; base += 32) {
-            int i = base + l;
-            bool valid = i < hi;
-            K k = valid ? src[i] : (K)0;
-            unsigned d = valid ? (unsigned)((k >> shift) & 0xff) : 256u + (unsigned)l;
-            unsigned m = pm::match_any(d);
-            unsigned pos = 0;
-            if (valid) pos = hist[w * 256 + d] + (unsigned)pm::popc(m & lt_mask());
-            pm::syncwarp();
-            if (valid) {
-                dst[pos] = k;
-                dv[pos] = sv[i];
-                if (l == pm::ffs(m) - 1) hist[w * 256 + d] += (unsigned)pm::popc(m);
+        lap(14);
+        // sweep 2: stable scatter.  Same four-chunk batching; only the short offset read / update is ordered.
+        for (int base = lo; base < hi; base += 128) {
+            K k[4];
+            unsigned v[4], d[4], m[4];
+            bool valid[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + 32 * u + l;
+                valid[u] = i < hi;
+                k[u] = src[valid[u] ? i : lo];
+                v[u] = sv[valid[u] ? i : lo];
+                d[u] = valid[u] ? (unsigned)((k[u] >> shift) & 0xff) : 0u;
             }
-            pm::syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; u++) m[u] = same_digit_mask(d[u], valid[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                unsigned pos = 0;
+                if (valid[u]) pos = hist[w * 256 + d[u]] + (unsigned)pm::popc(m[u] & lt_mask());
+                pm::syncwarp();
+                if (valid[u]) {
+                    dst[pos] = k[u];
+                    dv[pos] = v[u];
+                    if (l == pm::ffs(m[u]) - 1) hist[w * 256 + d[u]] += (unsigned)pm::popc(m[u]);
+                }
+                pm::syncwarp();
+            }
         }
         pm::sync();
+        lap(15);
         K* tk = src; src = dst; dst = tk;
         unsigned* tv = sv; sv = dv; dv = tv;
         where ^= 1;

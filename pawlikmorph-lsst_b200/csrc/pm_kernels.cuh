@@ -446,19 +446,18 @@ PM_DEV void load_plane_u8(const Geo& g, const uint8_t* src, unsigned* plane) {
     pm::sync();
 }
 PM_DEV void store_plane_u8(const Geo& g, const unsigned* plane, uint8_t* dst) {
-    // 4 pixels per thread-step; word stores when the destination is 4-byte aligned
-    const size_t total = (size_t)g.N;
-    const uintptr_t addr = (uintptr_t)dst;
-    const int head = (int)((4 - (addr & 3)) & 3);
-    for (int i = pm::tid(); i < head && (size_t)i < total; i += kThreads) {
-        int r = i / g.n, col = i - r * g.n;
+    // 4 pixels per thread-step; word stores when the destination is 4-byte aligned (32-bit index math: N < 2^20)
+    const int total = g.N;
+    const int head = min(total, (int)((4 - ((uintptr_t)dst & 3)) & 3));
+    for (int i = pm::tid(); i < head; i += kThreads) {
+        const int r = i / g.n, col = i - r * g.n;
         dst[i] = bit_at(plane, g.nw, r, col) ? 1 : 0;
     }
-    const size_t nwords = total > (size_t)head ? (total - head) / 4 : 0;
+    const int nwords = (total - head) / 4;
     uint32_t* d32 = (uint32_t*)(dst + head);
-    for (size_t k = pm::tid(); k < nwords; k += kThreads) {
-        size_t f = head + 4 * k;
-        int r = (int)(f / g.n), col = (int)(f - (size_t)r * g.n);
+    for (int k = pm::tid(); k < nwords; k += kThreads) {
+        const int f = head + 4 * k;
+        int r = f / g.n, col = f - r * g.n;
         uint32_t v = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -467,8 +466,8 @@ PM_DEV void store_plane_u8(const Geo& g, const unsigned* plane, uint8_t* dst) {
         }
         d32[k] = v;
     }
-    for (size_t f = head + 4 * nwords + pm::tid(); f < total; f += kThreads) {
-        int r = (int)(f / g.n), col = (int)(f - (size_t)r * g.n);
+    for (int f = head + 4 * nwords + pm::tid(); f < total; f += kThreads) {
+        const int r = f / g.n, col = f - r * g.n;
         dst[f] = bit_at(plane, g.nw, r, col) ? 1 : 0;
     }
 }
@@ -505,11 +504,11 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
         double* F = G + (size_t)g.N;
         pixelmap_exact(c, zb, &faint, G, F);
     }
-    c.pc.lap(13);   // (pixelmap: filter + shrink)
+    c.pc.lap(0);
     if (faint) return PM_ST_FAINT_CENTRE;
     region_grow(g, zb, gb);
     upsample_mask(c, gb);
-    c.pc.lap(14);   // (pixelmap: grow + upsample)
+    c.pc.lap(0);
     return PM_ST_OK;
 }
 
@@ -1036,11 +1035,23 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     }
     const bool bgr_ok = noise && b.nb > 0 && b.nm > 1;      // asymmetry.py:225-226
     c.pc.lap(9);    // (calcA: dilation + row scan)
-    double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};           // numA denA numB numS180 denS numS90
-    for (int task = pm::warp(); task < g.n * g.nw; task += kWarps) {
+    // compact list of the non-empty aperture words (deterministic order), two of them per warp-step so that
+    // their dependent chains (bit lookups -> rank/select -> image loads) overlap
+    Arena::Mark mk_t = c.ar.mark();
+    const int nwords = g.n * g.nw;
+    unsigned* flag = (unsigned*)c.ar.alloc((size_t)(nwords + 1) * 4);
+    unsigned short* tlist = (unsigned short*)c.ar.alloc((size_t)nwords * 2);
+    for (int t = pm::tid(); t < nwords; t += kThreads) flag[t] = c.aper[t] != 0u;
+    pm::sync();
+    const int ntask = (int)block_scan_excl_array(sh, flag, nwords);
+    for (int t = pm::tid(); t < nwords; t += kThreads)
+        if (c.aper[t] != 0u) tlist[flag[t]] = (unsigned short)t;
+    pm::sync();
+    double s[3] = {0.0, 0.0, 0.0};           // numA denA numB
+    unsigned u180 = 0, uden = 0, u90 = 0;    // shape asymmetry: integer pixel counts
+    auto contrib = [&](int task) {
         const unsigned bits = c.aper[task];
-        if (bits == 0) continue;
-        if (!((bits >> pm::lane()) & 1u)) continue;
+        if (!((bits >> pm::lane()) & 1u)) return;
         const int r = task / g.nw, col = (task - r * g.nw) * 32 + pm::lane();
         // 180°: (r, c) -> (2cy - r, 2cx - c);  90° (skimage, counter-clockwise): (cy + (c - cx), cx - (r - cy))
         const int r180 = 2 * cy - r, c180 = 2 * cx - col;
@@ -1074,15 +1085,21 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
             }
         }
         if (do_shape) {
-            const int v = bit_at(c.seg, g.nw, r, col) ? 1 : 0;
-            const int v180 = in180 && bit_at(c.seg, g.nw, r180, c180) ? 1 : 0;
-            const int v90 = in90 && bit_at(c.seg, g.nw, r90, c90) ? 1 : 0;
-            s[3] += (double)(v != v180);
-            s[4] += (double)v;
-            s[5] += (double)(v != v90);
+            const unsigned v = bit_at(c.seg, g.nw, r, col) ? 1u : 0u;
+            const unsigned v180 = in180 && bit_at(c.seg, g.nw, r180, c180) ? 1u : 0u;
+            const unsigned v90 = in90 && bit_at(c.seg, g.nw, r90, c90) ? 1u : 0u;
+            u180 += v ^ v180;
+            uden += v;
+            u90 += v ^ v90;
         }
+    };
+    for (int k = pm::warp(); k < ntask; k += 2 * kWarps) {
+        contrib(tlist[k]);
+        if (k + kWarps < ntask) contrib(tlist[k + kWarps]);
     }
-    block_sum<6>(sh, s);
+    block_sum<3>(sh, s);
+    const double n180 = (double)block_sum_u(sh, u180), nden = (double)block_sum_u(sh, uden), n90 = (double)block_sum_u(sh, u90);
+    c.ar.release(mk_t);
     out->A = -99.0; out->Abgr = -99.0; out->As = -99.0; out->As90 = -99.0;
     if (do_img) {
         const double den = 2.0 * s[1];
@@ -1094,8 +1111,8 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
         out->A = A; out->Abgr = Ab;
     }
     if (do_shape) {
-        out->As = s[3] / (2.0 * s[4]);
-        out->As90 = s[5] / (2.0 * s[4]);
+        out->As = n180 / (2.0 * nden);
+        out->As90 = n90 / (2.0 * nden);
     }
 }
 
@@ -1611,13 +1628,22 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
                 if (idx < total) {
                     const int y = (idx / nx) * 2, x = (idx % nx) * 2;
                     double bs = 0.0;
-                    for (int i = pm::lane(); i < size * size; i += 32) {
-                        const int r = y + i / size, col = x + i % size;
-                        if (r < g.n && col < g.n) {
-                            double v = bit_at(c.seg, g.nw, r, col) ? 0.0 : (ld(c, r, col) - c.sky);
+                    // size is 32, 16 or 8: a warp covers 32 / size rows per step; loads are independent
+                    const int sh_ = size == 32 ? 5 : (size == 16 ? 4 : 3);
+                    for (int i0 = 0; i0 < size * size; i0 += 128) {
+                        double vv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = i0 + u * 32 + pm::lane();
+                            const int r = y + (i >> sh_), col = x + (i & (size - 1));
+                            const bool ok_ = i < size * size && r < g.n && col < g.n;
+                            const bool inseg = ok_ && bit_at(c.seg, g.nw, r, col);
+                            const double raw = (ok_ && !inseg) ? ld(c, r, col) : 0.0;
+                            double v = inseg ? 0.0 : raw - c.sky;
                             if (v == 0.0) v = -99.0;
-                            bs += v;
+                            vv[u] = ok_ ? v : 0.0;
                         }
+                        bs += vv[0]; bs += vv[1]; bs += vv[2]; bs += vv[3];
                     }
                     bs = pm::warp_sum(bs);
                     ok = fabs(sky_test) > fabs(bs / (double)(size * size));
@@ -1756,7 +1782,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             // ---- sort ascending by (value, flat index); the reverse is the canonical descending order
             for (int i = pm::tid(); i < n_g; i += kThreads) spA[i] = c.posR[i];
             pm::sync();
-            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g);
+            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, c.pc.slot);
             if (where) {
                 for (int i = pm::tid(); i < n_g; i += kThreads) { spA[i] = spB[i]; skA[i] = skB[i]; }
                 pm::sync();
