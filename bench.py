@@ -211,7 +211,7 @@ def run_ours(args):
     if args.phases and rank == 0:
         # tuning aid: per-phase clock64() cycles summed over the CTAs of one extra (untimed) step
         names = ("pixelmap", "list+window", "rmax+aperture", "sort", "gini/m20/cands", "minapix", "calcA:loop", "r20:brentq",
-                 "smoothness", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "pix:filter", "pix:grow", "pix:store")
+                 "S:bkg", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "S:interior", "S:cut", "S:boxsearch")
         buf = torch.zeros((592, 16), dtype=torch.int64, device=dev)
         pm._lib.lib().pm_debug_phase_cycles(buf.data_ptr())
         step()

@@ -25,12 +25,35 @@ def image_tensor(image):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device())[None]
 
 
-def check_starmask(starMask):
+def star_tensor(starMask, shape):
+    """None / all-ones -> None; otherwise a float64 CUDA tensor of the mask."""
     if starMask is None:
-        return
-    if not np.all(np.asarray(starMask) == 1):
-        raise NotImplementedError("star masks other than all-ones are not supported yet (the catalogue path, "
-                                  "main.py:385-401, is out of scope)")
+        return None
+    m = np.asarray(starMask)
+    if m.shape != tuple(shape):
+        raise ValueError("starMask must have the shape of the image")
+    if np.all(m == 1):
+        return None
+    return torch.from_numpy(np.ascontiguousarray(m.astype(np.float64))).to(device())
+
+
+def rotated_mask(star, angle, cx, cy):
+    """starMask * rotate(starMask, angle, center=(cx, cy), cval=1) (asymmetry.py:186-191, pixmap.py:81-83) for
+    the integer centres and the angles the pipeline uses: skimage's inverse-map rotation is then an index
+    permutation (out-of-range sources take cval = 1).  Device tensor ops (plumbing): exact 0/1 arithmetic."""
+    n = star.shape[0]
+    r = torch.arange(n, device=star.device)[:, None].expand(n, n)
+    c = torch.arange(n, device=star.device)[None, :].expand(n, n)
+    if float(angle) == 180.0:
+        sr, sc = 2 * cy - r, 2 * cx - c
+    elif float(angle) == 90.0:
+        sr, sc = cy + (c - cx), cx - (r - cy)
+    else:
+        raise NotImplementedError("only 180 and 90 degrees")
+    ok = (sr >= 0) & (sr < n) & (sc >= 0) & (sc < n)
+    rot = torch.ones_like(star)
+    rot[ok] = star[sr[ok], sc[ok]]
+    return star * rot
 
 
 def int_centroid(centroid):

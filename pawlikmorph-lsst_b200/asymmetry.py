@@ -1,5 +1,6 @@
 """Drop-in for `pawlikMorphLSST/asymmetry.py` (citations into that file)."""
 import numpy as np
+import torch
 
 from . import _abi, _single
 
@@ -10,7 +11,9 @@ def minapix(image, segmap, apermask, starMask=None):
     """asymmetry.py:50-129 — the pixel [col, row], among the brightest pixels holding 20 % of the
     flux, about which the 180-degree asymmetry inside the re-centred aperture is smallest.
     Ties in the brightness order are canonical (value descending, flat index descending)."""
-    _single.check_starmask(starMask)
+    star = _single.star_tensor(starMask, np.shape(image))
+    if star is not None:                      # asymmetry.py:82-86: imageMask = image * segmap * starMask
+        image = (torch.from_numpy(np.asarray(image, dtype=np.float64)).to(star.device) * star).cpu().numpy()
     row, _ = _single.run(image, flags=0, segmap_in=np.asarray(segmap)[None], apermask_in=np.asarray(apermask)[None])
     st = int(row["status"])
     if st == _abi.PM_ST_NO_CANDIDATE or st == _abi.PM_ST_EMPTY_SEGMAP:
@@ -22,7 +25,6 @@ def calcA(img, segmap, apermask, centroid, angle, starMask=None, noisecorrect=Fa
     """asymmetry.py:132-257 — [A, Abgr] for a rotation by `angle` (180 or 90 degrees) about `centroid`
     = [col, row], inside the (un-recentred) aperture; with `noisecorrect` the background asymmetry of
     asymmetry.py:210-255 is subtracted.  As upstream, shape asymmetry is calcA(segmap, segmap, ...)."""
-    _single.check_starmask(starMask)
     if float(angle) not in (180.0, 90.0):
         raise NotImplementedError("only the angles the pipeline uses (180 and 90 degrees, main.py:470-478) are supported")
     flags = _abi.PM_DO_A
@@ -31,7 +33,17 @@ def calcA(img, segmap, apermask, centroid, angle, starMask=None, noisecorrect=Fa
     if not noisecorrect:
         flags |= _abi.PM_NO_NOISECORRECT
     cen = _single.int_centroid(centroid)
-    row, _ = _single.run(img, flags=flags, segmap_in=np.asarray(segmap)[None], apermask_in=np.asarray(apermask)[None],
+    star = _single.star_tensor(starMask, np.shape(img))
+    seg_used = np.asarray(segmap)
+    if star is not None:
+        # asymmetry.py:186-196: starMask *= rotate(starMask, angle, cval=1); img *= starMask; with noisecorrect the
+        # caller's segmap is multiplied in place too (:219) — reproduced, the kernel then sees masked inputs
+        sm = _single.rotated_mask(star, angle, int(cen[0]), int(cen[1]))
+        img = (torch.from_numpy(np.asarray(img, dtype=np.float64)).to(sm.device) * sm).cpu().numpy()
+        if noisecorrect:
+            segmap *= sm.cpu().numpy()
+            seg_used = segmap
+    row, _ = _single.run(img, flags=flags, segmap_in=np.asarray(seg_used)[None], apermask_in=np.asarray(apermask)[None],
                          centroid_in=cen[None])
     if int(row["status"]) == _abi.PM_ST_EMPTY_SEGMAP:
         raise ValueError("empty segmap")

@@ -213,10 +213,11 @@ PM_DEV double zoom_taps(double f00, double f01, double f10, double f11, double t
 // (fs+1) x (fs+1) patch of staged rows -> the four fs x fs window sums around (a0, b0).  FS > 0: compile-time
 // filter size (fully unrolled); kInterior: no reflection needed.
 template <typename T, int FS, bool kInterior>
-PM_DEV void patch_sums(const T* xb, int rlo, int n, int fs_rt, int a0, int b0, double& faa, double& fab, double& fba, double& fbb) {
+PM_DEV float patch_sums(const T* xb, int rlo, int n, int fs_rt, int a0, int b0, double& faa, double& fab, double& fba, double& fbb) {
     const int fs = FS ? FS : fs_rt, h = fs / 2;
     const bool ra = kInterior || a0 + 1 <= n - 1, rb = kInterior || b0 + 1 <= n - 1;   // second tap = first + 1 (else clamped)
     faa = fab = fba = fbb = 0.0;
+    float amax = 0.0f;
 #pragma unroll
     for (int k = 0; k <= fs; k++) {
         const int rr = kInterior ? a0 - h + k : refl(a0 - h + k, n);
@@ -224,13 +225,16 @@ PM_DEV void patch_sums(const T* xb, int rlo, int n, int fs_rt, int a0, int b0, d
         double sa = 0.0, sb = 0.0;       // sums over the b0 / b1 column windows
 #pragma unroll
         for (int q = 0; q <= fs; q++) {
-            const double x = (double)row[kInterior ? b0 - h + q : refl(b0 - h + q, n)];
+            const T xr = row[kInterior ? b0 - h + q : refl(b0 - h + q, n)];
+            amax = fmaxf(amax, fabsf((float)xr));     // NaN-propagating max is not needed: NaN shows up in Z
+            const double x = (double)xr;
             if (q < fs) sa += x;
             if (rb ? (q >= 1) : (q < fs)) sb += x;
         }
         if (k < fs) { faa += sa; fab += sb; }
         if (ra ? (k >= 1) : (k < fs)) { fba += sa; fbb += sb; }
     }
+    return amax;
 }
 
 // fast path: the image rows a band of shrunk rows needs are staged in shared memory — by a TMA bulk copy
@@ -277,11 +281,6 @@ PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* mi
         if (tma_ok(rlo, cnt)) {
             pm::mbar_wait(&sh.mbar[k & 1], c.mbar_phase[k & 1]);
             c.mbar_phase[k & 1] ^= 1u;
-            for (int i = pm::tid(); i < cnt; i += kThreads) {          // max |x| of the staged band
-                const float ax = fabsf((float)xb[i]);
-                if (!(ax <= 3.0e38f)) bad = 1;       // inf / nan (or beyond float range): let the exact path decide
-                mx = fmaxf(mx, ax);
-            }
         } else {
             const T* src = c.img + (size_t)rlo * n;
             int i = pm::tid();
@@ -307,13 +306,16 @@ PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* mi
             const int ii = band + rb;
             const int a0 = c.i0[ii], b0 = c.i0[j];
             double faa, fab, fba, fbb;
+            float am;
             if (a0 - h >= 0 && a0 + h + 1 <= n - 1 && b0 - h >= 0 && b0 + h + 1 <= n - 1)
-                patch_sums<T, FS, true>(xb, rlo, n, fs, a0, b0, faa, fab, fba, fbb);
+                am = patch_sums<T, FS, true>(xb, rlo, n, fs, a0, b0, faa, fab, fba, fbb);
             else
-                patch_sums<T, FS, false>(xb, rlo, n, fs, a0, b0, faa, fab, fba, fbb);
+                am = patch_sums<T, FS, false>(xb, rlo, n, fs, a0, b0, faa, fab, fba, fbb);
+            if (!(am <= 3.0e38f)) bad = 1;           // inf (or beyond float range): let the exact path decide
+            mx = fmaxf(mx, am);
             const double z = zoom_taps(faa * inv, fab * inv, fba * inv, fbb * inv, c.tw[ii], c.tw[j]);
             const double d = z - c.thr;
-            if (!(fabs(d) >= 0.0)) bad = 1;
+            if (!(fabs(d) >= 0.0)) bad = 1;          // NaN anywhere in the patch
             mn = fmin(mn, fabs(d));
             if (z > c.thr) pm::atomic_or(&zb[ii * g.mw + (j >> 5)], 1u << (j & 31));
             if (ii == cm && j == cm) faint = (z < c.thr) ? 1 : 0;
@@ -1134,8 +1136,7 @@ template <typename T_> PM_DEV void build_fold(Ctx<T_>& c, int cx, int cy, Fold& 
     const int A = f.A;
     const int entries = (A + 1) * (A + 2) / 2;
     for (int e = pm::tid(); e < entries; e += kThreads) {
-        // invert the triangular index
-        int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);     // invert the triangular index
         while (tri(a + 1, 0) <= e) a++;
         while (tri(a, 0) > e) a--;
         const int b = e - tri(a, 0);
@@ -1179,19 +1180,18 @@ PM_DEV void fold_range(int a, double r, int* b_lo_out, int* b_hi_out) {
 }
 // cheap, conservative bounds of column a's contribution: squared-distance tests with a safety margin
 // (no float64 square roots); every possibly-cut pixel is counted with weight 0 or 1, whichever is worse
-PM_DEV int count_below(int a, double lim2) {          // number of b >= 0 with a^2 + b^2 < lim2
-    const double t = lim2 - (double)a * (double)a;
-    if (!(t > 0.0)) return 0;
+PM_DEV int count_below(int a, int lim) {              // number of b >= 0 with a^2 + b^2 <= lim  (integers only)
+    const int t = lim - a * a;
+    if (t < 0) return 0;
     int b = (int)sqrtf((float)t);
-    while (b > 0 && !((double)(a * a + (b - 1) * (b - 1)) < lim2)) b--;
-    while ((double)(a * a + b * b) < lim2) b++;
-    return b;
+    while (b * b > t) b--;
+    while ((b + 1) * (b + 1) <= t) b++;
+    return b + 1;
 }
-PM_DEV void fold_column_bounds(const Fold& f, int a, double r, double* lo, double* hi) {
-    const double pr = 0.5 * sqrt(2.0);
-    const double rin = r - pr - 1e-9, rout = r + pr + 1e-9;
-    const int b_in = min(rin > 0.0 ? count_below(a, rin * rin) : 0, a + 1);     // certainly inside
-    const int b_out = min(max(count_below(a, rout * rout), b_in), a + 1);       // from here on certainly outside
+// lim_in: squared distances <= lim_in are certainly inside; > lim_out certainly outside
+PM_DEV void fold_column_bounds(const Fold& f, int a, int lim_in, int lim_out, double* lo, double* hi) {
+    const int b_in = min(count_below(a, lim_in), a + 1);                         // certainly inside
+    const int b_out = min(max(count_below(a, lim_out), b_in), a + 1);           // from here on certainly outside
     const double s = b_in > 0 ? f.P[tri(a, b_in - 1)] : 0.0;
     double l = s, h = s;
     for (int b = b_in; b < b_out; b++) {
@@ -1241,15 +1241,20 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
     }
     pm::sync();
 }
-// bounds lo <= F(r_k) <= hi for the walk radii rk[1..K]: one warp per radius
+// bounds lo <= F(r_k) <= hi for the walk radii rk[1..K]: one warp per radius.  A pixel at squared distance
+// d2 is certainly inside when d2 <= floor((r - pr - 1e-9)^2) - 1 and certainly outside when d2 > ceil((r + pr + 1e-9)^2).
 PM_DEV void eval_flux_bounds(Sh& sh, const Fold& f, int K) {
+    const double pr = 0.5 * sqrt(2.0);
     for (int k = 1 + pm::warp(); k <= K; k += kWarps) {
         const double r = sh.rk[k];
+        const double rin = r - pr - 1e-9, rout = r + pr + 1e-9;
+        const int lim_in = rin > 0.0 ? (int)floor(rin * rin) - 1 : -1;
+        const int lim_out = (int)ceil(rout * rout);
         double lo = 0.0, hi = 0.0;
         const int amax = min(f.A, (int)(r + 2.0));
         for (int a = pm::lane(); a <= amax; a += 32) {
             double l, h;
-            fold_column_bounds(f, a, r, &l, &h);
+            fold_column_bounds(f, a, lim_in, lim_out, &l, &h);
             lo += l; hi += h;
         }
         lo = pm::warp_sum(lo); hi = pm::warp_sum(hi);
@@ -1477,37 +1482,44 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
 // boundary of the sub-image [rlo, rlo + rlen) x [clo, clo + clen)) for the pixels of rows [ra, rb) x cols [ca, cb).
 // Separable: vertical window sums of a band of rows are staged in `vbuf`, then summed horizontally.
 // fn(r, col, mean) is called once per pixel by the thread that owns it.
-template <typename T_, typename F>
+template <typename T_, typename W_, typename F>
 PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int clen, int ra, int rb, int ca, int cb,
-                      double* vbuf, int vcap, F fn) {
+                      double* vbuf, int vcap, W_ want, F fn) {
     const int h = k / 2;
     const int W = cb - ca, E = W + k - 1;
     if (W <= 0 || rb <= ra) return;
-    const int R = max(1, min(16, vcap / E));
+    const int R = max(1, min(2 * kWarps, vcap / E));
     const double inv = 1.0 / ((double)k * (double)k);
+    const bool cols_inside = (ca - h >= clo) && (cb - 1 - h + k - 1 < clo + clen);     // no column reflection needed
     for (int band = ra; band < rb; band += R) {
         const int rows = min(R, rb - band);
-        for (int item = pm::tid(); item < rows * E; item += kThreads) {
-            const int q = item / E, e = item - q * E;
+        // stage 1: vertical window sums, one row of the band per warp, lanes along the columns (coalesced)
+        for (int q = pm::warp(); q < rows; q += kWarps) {
             const int r = band + q;
-            const int cc = clo + refl(ca - clo - h + e, clen);
-            double sum = 0.0;
-            int dr = 0;
-            for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
-                const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
-                             x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
-                sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
+            for (int e = pm::lane(); e < E; e += 32) {
+                const int cc = cols_inside ? ca - h + e : clo + refl(ca - clo - h + e, clen);
+                double sum = 0.0;
+                int dr = 0;
+                for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
+                    const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
+                                 x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
+                    sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
+                }
+                for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
+                vbuf[q * E + e] = sum;
             }
-            for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
-            vbuf[item] = sum;
         }
         pm::sync();
-        for (int item = pm::tid(); item < rows * W; item += kThreads) {
-            const int q = item / W, x = item - q * W;
-            const double* v = vbuf + q * E + x;
-            double sum = 0.0;
-            for (int dc = 0; dc < k; dc++) sum += v[dc];
-            fn(band + q, ca + x, sum * inv);
+        // stage 2: horizontal sums for the pixels the caller wants
+        for (int q = pm::warp(); q < rows; q += kWarps) {
+            const int r = band + q;
+            for (int x = pm::lane(); x < W; x += 32) {
+                if (!want(r, ca + x)) continue;
+                const double* v = vbuf + q * E + x;
+                double sum = 0.0;
+                for (int dc = 0; dc < k; dc++) sum += v[dc];
+                fn(r, ca + x, sum * inv);
+            }
         }
         pm::sync();
     }
@@ -1544,15 +1556,18 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
     }
     double s[2] = {0.0, 0.0};   // Σ w I ,  Σ w max(I - Is, 0)
     // ---- (A) interior of the annulus, weight 1: banded separable box means over the bounding box
-    box_means(c, k, 0, g.n, 0, g.n, y0, y1, x0, x1, vbuf, vcap, [&](int r, int col, double Is) {
-        const int dx = col - cx, dy = r - cy, d2 = dx * dx + dy * dy;
-        if (d2 < d2_full_out && d2 >= d2_zero_in) {
-            const double I = ld(c, r, col) - c.sky;
-            const double d = I - Is;
-            s[0] += I;
-            s[1] += d < 0.0 ? 0.0 : d;
-        }
-    });
+    box_means(c, k, 0, g.n, 0, g.n, y0, y1, x0, x1, vbuf, vcap,
+              [&](int r, int col) {
+                  const int dx = col - cx, dy = r - cy, d2 = dx * dx + dy * dy;
+                  return d2 < d2_full_out && d2 >= d2_zero_in;
+              },
+              [&](int r, int col, double Is) {
+                  const double I = ld(c, r, col) - c.sky;
+                  const double d = I - Is;
+                  s[0] += I;
+                  s[1] += d < 0.0 ? 0.0 : d;
+              });
+    c.pc.lap(13);   // (smoothness: interior pass)
     // ---- (B) pixels cut by either circle: enumerated from the folded octant (centre is an integer pixel), one
     // (entry, mirror image) per thread-step; the box mean is summed directly (k x k loads)
     {
@@ -1612,6 +1627,7 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
         }
     }
     block_sum<2>(sh, s);
+    c.pc.lap(14);   // (smoothness: cut pixels)
     // ---- background box search (casgm.py:367-398); one candidate position per warp per round
     // positions are visited in the order (size 32: y = 0, 2, ..; x = 0, 2, ..), then size 16, then 8.
     int bx = 0, by = 0, bsz = 32;
@@ -1660,12 +1676,15 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
             }
         }
     }
+    c.pc.lap(15);   // (smoothness: background box search)
     const int rows = max(0, min(bsz, g.n - by)), cols = max(0, min(bsz, g.n - bx));
     double bd = 0.0;
-    box_means(c, k, by, rows, bx, cols, by, by + rows, bx, bx + cols, vbuf, vcap, [&](int r, int col, double Is) {
-        const double d = (ld(c, r, col) - c.sky) - Is;
-        bd += d < 0.0 ? 0.0 : d;
-    });
+    box_means(c, k, by, rows, bx, cols, by, by + rows, bx, bx + cols, vbuf, vcap,
+              [&](int, int) { return true; },
+              [&](int r, int col, double Is) {
+                  const double d = (ld(c, r, col) - c.sky) - Is;
+                  bd += d < 0.0 ? 0.0 : d;
+              });
     c.ar.release(mk);
     bd = block_sum1(sh, bd);
     const double bs = bd / (double)(rows * cols);
@@ -1782,7 +1801,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             // ---- sort ascending by (value, flat index); the reverse is the canonical descending order
             for (int i = pm::tid(); i < n_g; i += kThreads) spA[i] = c.posR[i];
             pm::sync();
-            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, c.pc.slot);
+            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g);
             if (where) {
                 for (int i = pm::tid(); i < n_g; i += kThreads) { spA[i] = spB[i]; skA[i] = skB[i]; }
                 pm::sync();

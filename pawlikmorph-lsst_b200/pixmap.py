@@ -1,6 +1,7 @@
 """Drop-in for `pawlikMorphLSST/pixmap.py`: same names, arguments and error behaviour; the work is
 done by the CUDA library.  Citations are into /root/reference/pawlikMorphLSST/pixmap.py."""
 import numpy as np
+import torch
 
 from . import _abi, _single
 
@@ -30,7 +31,9 @@ def pixelmap(image, threshold, filterSize, starMask=None):
     `threshold` (pixmap.py:175-179)."""
     if filterSize % 2 == 0:
         raise _FilterSizeError("ERROR! Filter can not be of even size.")
-    _single.check_starmask(starMask)
+    star = _single.star_tensor(starMask, np.shape(image))
+    if star is not None:                      # pixmap.py:156-158: imageTmp = image * starMask, then the same path
+        image = (torch.from_numpy(np.asarray(image, dtype=np.float64)).to(star.device) * star).cpu().numpy()
     row, res = _single.run(image, filter_size=int(filterSize), flags=_abi.PM_STOP_AFTER_PIXELMAP,
                            threshold_in=[float(threshold)], want_segmap=True)
     if int(row["status"]) == _abi.PM_ST_FAINT_CENTRE:
@@ -54,6 +57,12 @@ def checkPixelmapEdges(segmap):
 
 
 def calcMaskedFraction(oldMask, starMask, cenpix):
-    """pixmap.py:58-88 — only reached on the star-catalogue path (`-cc`, main.py:472-473), which is out
-    of scope (and broken upstream, main.py:395)."""
-    raise NotImplementedError("calcMaskedFraction belongs to the star-catalogue path, which is out of scope")
+    """pixmap.py:58-88 — fraction of the object's pixelmap covered by the (180-degree symmetrised) star mask:
+    1 - sum(oldMask * starMask * rotate(starMask, 180, center=cenpix, cval=1)) / sum(oldMask).
+    A masked pixel count: evaluated with device tensor ops (there is no kernel worth writing for it)."""
+    dev = _single.device()
+    star = torch.from_numpy(np.ascontiguousarray(np.asarray(starMask, dtype=np.float64))).to(dev)
+    old = torch.from_numpy(np.ascontiguousarray(np.asarray(oldMask, dtype=np.float64))).to(dev)
+    cen = _single.int_centroid(cenpix)
+    sm = _single.rotated_mask(star, 180.0, int(cen[0]), int(cen[1]))
+    return float(1.0 - (old * sm).sum() / old.sum())

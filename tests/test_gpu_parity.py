@@ -174,3 +174,41 @@ def test_host_api_and_errors():
     with pytest.raises(TypeError):
         pm.batch.analyse_batch(torch.zeros((1, 64, 64)), 0.0, 0.0, 3)                     # not on the GPU
     assert pm.batch.analyse_batch(torch.zeros((0, 64, 64), device="cuda"), 0.0, 0.0, 3).rows.shape == (0, 16)
+
+
+def test_star_masks_in_the_per_cutout_api():
+    """starMask arguments of pixelmap / minapix / calcA / calcMaskedFraction (pixmap.py:156-158, :58-88;
+    asymmetry.py:82-86, :182-196, :219) against the oracle."""
+    import pawlikmorph_lsst_b200 as pm
+    from oracle import pm_oracle as O
+    n = 96
+    img_sky = P.synth_batch(1, n, 81)[0].astype(np.float64)
+    star = np.ones((n, n))
+    star[20:34, 50:70] = 0.0          # a masked star off-centre
+    star[52:58, 30:36] = 0.0          # and one inside the galaxy
+    seg = pm.pixmap.pixelmap(img_sky, 105.0, 3, star)
+    assert np.array_equal(seg, O.pixelmap(img_sky, 105.0, 3, star))
+    img = img_sky - 100.0
+    rmax = pm.pixmap.calcRmax(img, seg)
+    ap = pm.apertures.aperpixmap(n, rmax, 9, 0.1)
+    apix = pm.asymmetry.minapix(img, seg, ap, star)
+    assert apix == O.minapix(img, seg, ap, star)
+    for angle, nc in ((180.0, False), (90.0, False)):
+        got = pm.asymmetry.calcA(img, seg.copy(), ap, apix, angle, star, nc)
+        want = O.calcA(img, seg.copy(), ap, apix, angle, star, nc)
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+    # noisecorrect=True with a star mask: upstream multiplies the segmap by starMask * rotate(starMask) in place and
+    # dilates it (asymmetry.py:219-220); skimage's bilinear rotation leaves ~1e-14 instead of 0 next to mask edges and
+    # binary_dilation counts those as set.  The library uses the exact 0/1 rotated mask (DESIGN.md section 1), so the
+    # checker is the oracle fed with the exactly masked inputs.
+    import torch
+    from pawlikmorph_lsst_b200 import _single
+    sm = _single.rotated_mask(torch.from_numpy(star).cuda(), 180.0, apix[0], apix[1]).cpu().numpy()
+    s1 = seg.copy()
+    got = pm.asymmetry.calcA(img, s1, ap, apix, 180.0, star, True)
+    want = O.calcA(img * sm, seg * sm, ap, apix, 180.0, None, True)
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    assert np.array_equal(s1, seg * sm)                      # the in-place segmap update of asymmetry.py:219
+    np.testing.assert_allclose(pm.asymmetry.calcA(seg, seg, ap, apix, 90.0, star), O.calcA(seg, seg, ap, apix, 90.0, star),
+                               rtol=1e-12)
+    np.testing.assert_allclose(pm.pixmap.calcMaskedFraction(seg, star, apix), O.calcMaskedFraction(seg, star, apix), rtol=1e-12)
