@@ -27,7 +27,7 @@ if REPO not in sys.path:
 
 METRIC = "galaxies/sec for -Aall -cas at 256^2"
 UNIT = "galaxies/s"
-FLAGS_ALL = 15
+FLAGS_ALL = 15 | int(os.environ.get("PM_BENCH_EXTRA_FLAGS", "0"), 0)    # tuning only, e.g. 0x2000 = no L2 prefetch
 
 
 def algorithmic_bytes(n, itemsize=4):

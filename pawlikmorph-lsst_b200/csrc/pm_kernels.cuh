@@ -1482,10 +1482,27 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
 // boundary of the sub-image [rlo, rlo + rlen) x [clo, clo + clen)) for the pixels of rows [ra, rb) x cols [ca, cb).
 // Separable: vertical window sums of a band of rows are staged in `vbuf`, then summed horizontally.
 // fn(r, col, mean) is called once per pixel by the thread that owns it.
+// Σ_{i<K} (p[i * stride] - sky), loads issued together (compile-time K)
+template <int K, typename T_> PM_DEV double strided_sum(const T_* p, int stride, double sky) {
+    T_ x[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) x[i] = pm::ldg(p + (size_t)i * stride);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) s += (double)x[i] - sky;
+    return s;
+}
+template <int K> PM_DEV double run_sum(const double* v) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) s += v[i];
+    return s;
+}
+
 template <typename T_, typename W_, typename F>
 PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int clen, int ra, int rb, int ca, int cb,
                       double* vbuf, int vcap, W_ want, F fn) {
-    const int h = k / 2;
+    const int h = k / 2, n = c.g.n;
     const int W = cb - ca, E = W + k - 1;
     if (W <= 0 || rb <= ra) return;
     const int R = max(1, min(2 * kWarps, vcap / E));
@@ -1496,16 +1513,31 @@ PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int c
         // stage 1: vertical window sums, one row of the band per warp, lanes along the columns (coalesced)
         for (int q = pm::warp(); q < rows; q += kWarps) {
             const int r = band + q;
+            const bool rows_inside = (r - h >= rlo) && (r - h + k - 1 < rlo + rlen);      // no row reflection needed
             for (int e = pm::lane(); e < E; e += 32) {
                 const int cc = cols_inside ? ca - h + e : clo + refl(ca - clo - h + e, clen);
                 double sum = 0.0;
-                int dr = 0;
-                for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
-                    const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
-                                 x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
-                    sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
+                if (rows_inside && k <= 8) {
+                    const T_* p = c.img + (size_t)(r - h) * n + cc;
+                    switch (k) {
+                        case 1: sum = strided_sum<1>(p, n, c.sky); break;
+                        case 2: sum = strided_sum<2>(p, n, c.sky); break;
+                        case 3: sum = strided_sum<3>(p, n, c.sky); break;
+                        case 4: sum = strided_sum<4>(p, n, c.sky); break;
+                        case 5: sum = strided_sum<5>(p, n, c.sky); break;
+                        case 6: sum = strided_sum<6>(p, n, c.sky); break;
+                        case 7: sum = strided_sum<7>(p, n, c.sky); break;
+                        default: sum = strided_sum<8>(p, n, c.sky); break;
+                    }
+                } else {
+                    int dr = 0;
+                    for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
+                        const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
+                                     x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
+                        sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
+                    }
+                    for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
                 }
-                for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
                 vbuf[q * E + e] = sum;
             }
         }
@@ -1516,8 +1548,18 @@ PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int c
             for (int x = pm::lane(); x < W; x += 32) {
                 if (!want(r, ca + x)) continue;
                 const double* v = vbuf + q * E + x;
-                double sum = 0.0;
-                for (int dc = 0; dc < k; dc++) sum += v[dc];
+                double sum;
+                switch (k) {
+                    case 1: sum = run_sum<1>(v); break;
+                    case 2: sum = run_sum<2>(v); break;
+                    case 3: sum = run_sum<3>(v); break;
+                    case 4: sum = run_sum<4>(v); break;
+                    case 5: sum = run_sum<5>(v); break;
+                    case 6: sum = run_sum<6>(v); break;
+                    case 7: sum = run_sum<7>(v); break;
+                    case 8: sum = run_sum<8>(v); break;
+                    default: sum = 0.0; for (int dc = 0; dc < k; dc++) sum += v[dc]; break;
+                }
                 fn(r, ca + x, sum * inv);
             }
         }
@@ -1584,15 +1626,32 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
         }
         pm::sync();
         const int total = (int)block_scan_excl_array(sh, eoff, items);
-        for (int e8 = pm::tid(); e8 < total * 8; e8 += kThreads) {
-            const int e = e8 >> 3, sym = e8 & 7;
+        // B1: one exact weight per cut entry (shared by its mirror images)
+        double* wcut = (double*)c.ar.alloc((size_t)max(total, 1) * 8);
+        unsigned* ecut = (unsigned*)c.ar.alloc((size_t)max(total, 1) * 4);
+        if (c.ar.overflow) { c.ar.release(mk); return -99.0; }
+        for (int e = pm::tid(); e < total; e += kThreads) {
             int lo = 0, hi = items - 1;          // last item with eoff[item] <= e
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
                 if ((int)eoff[mid] <= e) lo = mid; else hi = mid - 1;
             }
             const int q = lo / ncol, a = lo - q * ncol, b = eblo[lo] + (e - (int)eoff[lo]);
-            // the 8 mirror images of (a, b); duplicates (a == b, b == 0) are skipped
+            const int d2 = a * a + b * b;
+            const bool cut_out = !(d2 < d2_full_out) && sqrt((double)d2) < rmax + pr;
+            double w = 0.0;
+            if (!(q == 1 && cut_out))                                 // cut by both circles: counted with the outer one
+                w = circle_weight(a, b, rmax) - circle_weight(a, b, r20);
+            wcut[e] = w;
+            ecut[e] = ((unsigned)a << 16) | (unsigned)b;
+        }
+        pm::sync();
+        // B2: the (up to 8) mirror images of every entry, one per thread-step
+        for (int e8 = pm::tid(); e8 < total * 8; e8 += kThreads) {
+            const int e = e8 >> 3, sym = e8 & 7;
+            const double w = wcut[e];
+            if (w == 0.0) continue;
+            const int a = (int)(ecut[e] >> 16), b = (int)(ecut[e] & 0xffff);
             int dx = (sym & 4) ? b : a, dy = (sym & 4) ? a : b;
             if ((sym & 4) && a == b) continue;
             if ((sym & 1) && dx == 0) continue;
@@ -1601,25 +1660,32 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
             if (sym & 2) dy = -dy;
             const int col = cx + dx, r = cy + dy;
             if (r < y0 || r >= y1 || col < x0 || col >= x1) continue;
-            const int d2 = a * a + b * b;
-            const bool cut_out = !(d2 < d2_full_out) && sqrt((double)d2) < rmax + pr;
-            if (q == 1 && cut_out) continue;                      // also cut by the outer circle: counted there
-            const double w = circle_weight(dx, dy, rmax) - circle_weight(dx, dy, r20);
-            if (w == 0.0) continue;
             const double I = ld(c, r, col) - c.sky;
             const int h = k / 2;
             double bs = 0.0;
-            for (int dr = 0; dr < k; dr++) {
-                const int rr = refl(r - h + dr, g.n);
-                double rs = 0.0;
-                int dc = 0;
-                for (; dc + 3 < k; dc += 4) {
-                    const double x0 = ld(c, rr, refl(col - h + dc, g.n)), x1 = ld(c, rr, refl(col - h + dc + 1, g.n)),
-                                 x2 = ld(c, rr, refl(col - h + dc + 2, g.n)), x3 = ld(c, rr, refl(col - h + dc + 3, g.n));
-                    rs += x0 - c.sky; rs += x1 - c.sky; rs += x2 - c.sky; rs += x3 - c.sky;
+            if (k <= 8 && r - h >= 0 && r - h + k - 1 < g.n && col - h >= 0 && col - h + k - 1 < g.n) {
+                for (int dr = 0; dr < k; dr++) {
+                    const T_* p = c.img + (size_t)(r - h + dr) * g.n + (col - h);
+                    double rs;
+                    switch (k) {
+                        case 1: rs = strided_sum<1>(p, 1, c.sky); break;
+                        case 2: rs = strided_sum<2>(p, 1, c.sky); break;
+                        case 3: rs = strided_sum<3>(p, 1, c.sky); break;
+                        case 4: rs = strided_sum<4>(p, 1, c.sky); break;
+                        case 5: rs = strided_sum<5>(p, 1, c.sky); break;
+                        case 6: rs = strided_sum<6>(p, 1, c.sky); break;
+                        case 7: rs = strided_sum<7>(p, 1, c.sky); break;
+                        default: rs = strided_sum<8>(p, 1, c.sky); break;
+                    }
+                    bs += rs;
                 }
-                for (; dc < k; dc++) rs += ld(c, rr, refl(col - h + dc, g.n)) - c.sky;
-                bs += rs;
+            } else {
+                for (int dr = 0; dr < k; dr++) {
+                    const int rr = refl(r - h + dr, g.n);
+                    double rs = 0.0;
+                    for (int dc = 0; dc < k; dc++) rs += ld(c, rr, refl(col - h + dc, g.n)) - c.sky;
+                    bs += rs;
+                }
             }
             const double d = I - bs / ((double)k * (double)k);
             s[0] += w * I;
@@ -1750,10 +1816,11 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         for (int r = pm::tid(); r < g.n; r += kThreads) ng += c.rowoff[r];
         c.n_g = (int)block_sum_u(sh, ng);
         const int n_g = c.n_g;
-        // arena order = shared-memory priority: the masked window (random access in minapix / r20-r80) first
+        // arena plan: [raster list][sorted positions -> candidates][sort temporaries], then — once the sort
+        // temporaries are released — the masked window (so that both the sort and minapix run out of shared memory)
         c.bw = c.c1 - c.c0 + 1;
         const int bh = c.r1 - c.r0 + 1;
-        c.mw = (T*)c.ar.alloc((size_t)c.bw * bh * sizeof(T));
+        c.mw = nullptr;
         c.posR = (unsigned*)c.ar.alloc((size_t)n_g * 4);
         Arena::Mark mk_list = c.ar.mark();
         unsigned* spA = (unsigned*)c.ar.alloc((size_t)n_g * 4);     // sorted positions end up here
@@ -1772,12 +1839,6 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         SortOut so;
         so.gini = so.m20 = -99.0; so.n_cand = 0; so.n_pos = 0;
         if (!done) {
-            for (int wr = pm::warp(); wr < bh; wr += kWarps) {        // one window row per warp, loads independent
-                const int r = c.r0 + wr;
-                const T* src = c.img + (size_t)r * g.n + c.c0;
-                for (int x = pm::lane(); x < c.bw; x += 32)
-                    c.mw[wr * c.bw + x] = bit_at(c.seg, g.nw, r, c.c0 + x) ? pm::ldg(src + x) : nan_of(T());
-            }
             phase_list(c, skA, &st);
             pc.lap(1);   // bbox, counts, window, raster list
             rmax2 = phase_rmax2(c, st, &cen_flat);
@@ -1829,6 +1890,18 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             // keep only the candidates (the first n_cand entries of the descending order)
             c.ar.release(mk_list);
             c.ar.keep(spA, (size_t)max(so.n_cand, 1) * 4);
+            // ---- masked window over the bounding box (NaN outside the map)
+            c.mw = (T*)c.ar.alloc((size_t)c.bw * bh * sizeof(T));
+            if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+            else {
+                for (int wr = pm::warp(); wr < bh; wr += kWarps) {        // one window row per warp, loads independent
+                    const int r = c.r0 + wr;
+                    const T* src = c.img + (size_t)r * g.n + c.c0;
+                    for (int x = pm::lane(); x < c.bw; x += 32)
+                        c.mw[wr * c.bw + x] = bit_at(c.seg, g.nw, r, c.c0 + x) ? pm::ldg(src + x) : nan_of(T());
+                }
+                pm::sync();
+            }
             pc.lap(4);   // gini, m20, candidates
             (void)mk_sorted;
         }
@@ -1917,8 +1990,9 @@ template <typename T> PM_DEV void analyse_body(const Params& p) {
     c.mbar_phase[0] = c.mbar_phase[1] = 0u;
     if (pm::tid() == 0) { pm::mbar_init(&c.sh->mbar[0], 1); pm::mbar_init(&c.sh->mbar[1], 1); pm::mbar_fence_init(); }
     build_tables(c);
-    // Persistent CTA: galaxy indices come from a global work counter, fetched ONE AHEAD so that the next
-    // cutout can be pulled towards L2 (TMA bulk prefetch) while the current one is being analysed.
+    // Persistent CTA: galaxy indices come from a global work counter, fetched ONE AHEAD so that the next cutout
+    // can optionally be pulled towards L2 (TMA bulk prefetch, PM_L2_PREFETCH) while the current one is analysed.
+    // Off by default: with the TMA-staged pixelmap it no longer pays (measured -1 %: it competes for L2 capacity).
     const size_t img_bytes = (size_t)c.g.N * sizeof(T);
     if (pm::tid() == 0) c.sh->ia[0] = (int)pm::atomic_add(p.counter, 1ull);
     pm::sync();
@@ -1929,7 +2003,7 @@ template <typename T> PM_DEV void analyse_body(const Params& p) {
         pm::sync();
         const long long nxt = (long long)c.sh->ia[0];
         pm::sync();
-        if (nxt < p.B && !(p.flags & PM_NO_PREFETCH)) {
+        if (nxt < p.B && (p.flags & PM_L2_PREFETCH)) {
             const uintptr_t base = (uintptr_t)p.images + (size_t)nxt * img_bytes;
             const uintptr_t lo = (base + 15) & ~(uintptr_t)15, hi = (base + img_bytes) & ~(uintptr_t)15;
             for (uintptr_t a = lo + (uintptr_t)pm::tid() * 4096; a < hi; a += (uintptr_t)kThreads * 4096)
