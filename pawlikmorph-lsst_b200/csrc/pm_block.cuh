@@ -31,7 +31,7 @@ struct Sh {
     unsigned scan_tmp[kWarps + 2];
     unsigned colmask[24];            // OR of all segmap rows (PM_MAX_N / 32 words)
     unsigned long long mbar[2];      // mbarriers of the two TMA staging buffers (pixelmap)
-    int ia[8];                       // integer reductions (atomics)
+    int ia[8 + 2 * kRedSlots];       // work index; integer thresholds of the radii being evaluated
     int status;
 };
 

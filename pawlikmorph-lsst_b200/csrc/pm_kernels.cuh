@@ -1162,21 +1162,25 @@ template <typename T_> PM_DEV void build_fold(Ctx<T_>& c, int cx, int cy, Fold& 
 // Column a of the folded table for a circle of radius r: entries b < b_lo lie fully inside (prefix sum P),
 // entries b_lo <= b < b_hi are cut by the circle, the rest is outside.  The predicates are photutils'
 // (d < r - pr, d < r + pr with d = sqrt(dx^2 + dy^2) in float64); a float estimate is corrected with them.
-PM_DEV bool inside_d(int a, int b, double lim) { return sqrt((double)(a * a + b * b)) < lim; }
-PM_DEV int first_not_inside(int a, double lim) {     // smallest b >= 0 with !(d(a, b) < lim)
+// smallest integer d2 >= 0 with !(sqrt((double)d2) < lim): photutils' float64 predicate as an integer threshold
+PM_DEV int d2_threshold(double lim) {
     if (!(lim > 0.0)) return 0;
-    const double t = lim * lim - (double)a * (double)a;
-    int b = t > 0.0 ? (int)sqrtf((float)t) : 0;
-    while (b > 0 && !inside_d(a, b - 1, lim)) b--;
-    while (inside_d(a, b, lim)) b++;
-    return b;
+    if (!(lim < 46000.0)) return 0x7fffffff;
+    int d = (int)(lim * lim);
+    while (d > 0 && !(sqrt((double)(d - 1)) < lim)) d--;
+    while (sqrt((double)d) < lim) d++;
+    return d;
+}
+PM_DEV int count_below(int a, int lim);
+// cut range of column a for integer thresholds (d2 < d_in: fully inside; d2 >= d_out: outside)
+PM_DEV void fold_range_i(int a, int d_in, int d_out, int* b_lo_out, int* b_hi_out) {
+    const int b_lo = count_below(a, d_in - 1), b_hi = count_below(a, d_out - 1);
+    *b_lo_out = min(b_lo, a + 1);
+    *b_hi_out = min(max(b_hi, b_lo), a + 1);
 }
 PM_DEV void fold_range(int a, double r, int* b_lo_out, int* b_hi_out) {
     const double pr = 0.5 * sqrt(2.0);
-    const int b_lo = first_not_inside(a, r - pr);
-    const int b_hi = first_not_inside(a, r + pr);
-    *b_lo_out = min(b_lo, a + 1);
-    *b_hi_out = min(max(b_hi, b_lo), a + 1);
+    fold_range_i(a, d2_threshold(r - pr), d2_threshold(r + pr), b_lo_out, b_hi_out);
 }
 // cheap, conservative bounds of column a's contribution: squared-distance tests with a safety margin
 // (no float64 square roots); every possibly-cut pixel is counted with weight 0 or 1, whichever is worse
@@ -1208,11 +1212,17 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
 #pragma unroll
     for (int q = 0; q < kRedSlots; q++) acc[q] = 0.0;
     const int ncol = f.A + 1, items = nr * ncol;
+    if (pm::tid() < nr) {                      // integer distance thresholds of each radius, once
+        const double pr = 0.5 * sqrt(2.0);
+        sh.ia[8 + 2 * pm::tid()] = d2_threshold(radii[pm::tid()] - pr);
+        sh.ia[9 + 2 * pm::tid()] = d2_threshold(radii[pm::tid()] + pr);
+    }
+    pm::sync();
     for (int item = pm::tid(); item < items; item += kThreads) {
         const int q = item / ncol, a = item - q * ncol;
         const double r = radii[q];
         int b_lo = 0, b_hi = 0;
-        if (!((double)a > r + 1.0)) fold_range(a, r, &b_lo, &b_hi);
+        if (!((double)a > r + 1.0)) fold_range_i(a, sh.ia[8 + 2 * q], sh.ia[9 + 2 * q], &b_lo, &b_hi);
         const double v = b_lo > 0 ? f.P[tri(a, b_lo - 1)] : 0.0;
 #pragma unroll
         for (int k = 0; k < kRedSlots; k++)
@@ -1400,14 +1410,12 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     for (int q = 0; q < 2; q++) { blo_r[q] = sh.rk[kk[q]]; bhi_r[q] = sh.rk[kk[q]] + delta; }
     const double pr = 0.5 * sqrt(2.0);
     const int ncol = f.A + 1;
+    const int dlim[4] = {d2_threshold(blo_r[0] - pr), d2_threshold(bhi_r[0] + pr), d2_threshold(blo_r[1] - pr), d2_threshold(bhi_r[1] + pr)};
     double base[2] = {0.0, 0.0};
     for (int item = pm::tid(); item < 2 * ncol; item += kThreads) {
         const int q = item / ncol, a = item - q * ncol;
         int bl = 0, bh = 0;
-        if (!((double)a > bhi_r[q] + 1.0)) {
-            bl = min(first_not_inside(a, blo_r[q] - pr), a + 1);
-            bh = min(max(first_not_inside(a, bhi_r[q] + pr), bl), a + 1);
-        }
+        if (!((double)a > bhi_r[q] + 1.0)) fold_range_i(a, dlim[2 * q], dlim[2 * q + 1], &bl, &bh);
         if (bl > 0) base[q] += f.P[tri(a, bl - 1)];
         eblo[item] = bl;
         eoff[item] = (unsigned)(bh - bl);
@@ -1587,15 +1595,8 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
     // Pixels cut by neither circle have weight exactly 1 (inside the annulus) or 0: integer thresholds on the squared
     // distance reproduce photutils' float64 predicates  d < r_out - pr  and  d < r_in + pr  (d = sqrt(dx^2 + dy^2)).
     const double pr = 0.5 * sqrt(2.0);
-    int d2_full_out = 0, d2_zero_in = 0;     // first d2 with !(sqrt(d2) < r_out - pr) / !(sqrt(d2) < r_in + pr)
-    {
-        const double lo = rmax - pr, hi = r20 + pr;
-        if (lo > 0.0) { d2_full_out = (int)(lo * lo); while (d2_full_out > 0 && !(sqrt((double)(d2_full_out - 1)) < lo)) d2_full_out--;
-                        while (sqrt((double)d2_full_out) < lo) d2_full_out++; }
-        d2_zero_in = (int)(hi * hi);
-        while (d2_zero_in > 0 && !(sqrt((double)(d2_zero_in - 1)) < hi)) d2_zero_in--;
-        while (sqrt((double)d2_zero_in) < hi) d2_zero_in++;
-    }
+    const int d2_full_out = d2_threshold(rmax - pr), d2_zero_out = d2_threshold(rmax + pr);   // first d2 not fully inside / first outside
+    const int d2_full_in = d2_threshold(r20 - pr), d2_zero_in = d2_threshold(r20 + pr);
     double s[2] = {0.0, 0.0};   // Σ w I ,  Σ w max(I - Is, 0)
     // ---- (A) interior of the annulus, weight 1: banded separable box means over the bounding box
     box_means(c, k, 0, g.n, 0, g.n, y0, y1, x0, x1, vbuf, vcap,
@@ -1620,7 +1621,7 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
             const int q = item / ncol, a = item - q * ncol;
             const double r = sh.bc[8 + q];
             int b_lo = 0, b_hi = 0;
-            if (!((double)a > r + 1.0)) fold_range(a, r, &b_lo, &b_hi);
+            if (!((double)a > r + 1.0)) fold_range_i(a, q == 0 ? d2_full_out : d2_full_in, q == 0 ? d2_zero_out : d2_zero_in, &b_lo, &b_hi);
             eblo[item] = b_lo;
             eoff[item] = (unsigned)(b_hi - b_lo);
         }
@@ -1638,7 +1639,7 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
             }
             const int q = lo / ncol, a = lo - q * ncol, b = eblo[lo] + (e - (int)eoff[lo]);
             const int d2 = a * a + b * b;
-            const bool cut_out = !(d2 < d2_full_out) && sqrt((double)d2) < rmax + pr;
+            const bool cut_out = !(d2 < d2_full_out) && d2 < d2_zero_out;
             double w = 0.0;
             if (!(q == 1 && cut_out))                                 // cut by both circles: counted with the outer one
                 w = circle_weight(a, b, rmax) - circle_weight(a, b, r20);
