@@ -61,6 +61,7 @@ extern "C" {
 #define PM_STOP_AFTER_RMAX 0x400u     /* ... + calcRmax + aperpixmap */
 #define PM_A_ANGLE90 0x800u           /* calcA on the image with angle = 90 instead of 180 (asymmetry.py:132) */
 #define PM_NO_NOISECORRECT 0x1000u    /* calcA(..., noisecorrect=False): Abgr = 0, A not corrected */
+#define PM_NO_PRUNE 0x4000u           /* tuning/test: evaluate every minapix candidate completely (no exact pruning) */
 #define PM_L2_PREFETCH 0x2000u        /* tuning: TMA-prefetch the next cutout into L2 while the current one runs (off) */
 
 /* pm_row_t.status */

@@ -17,6 +17,7 @@ PM_STOP_AFTER_RMAX = 0x400
 PM_A_ANGLE90 = 0x800
 PM_NO_NOISECORRECT = 0x1000
 PM_L2_PREFETCH = 0x2000
+PM_NO_PRUNE = 0x4000
 PM_ST_OK, PM_ST_FAINT_CENTRE, PM_ST_NO_CANDIDATE, PM_ST_BAD_BRACKET, PM_ST_EMPTY_SEGMAP, PM_ST_WORKSPACE = range(6)
 
 ROW_FIELDS = ("apix_col", "apix_row", "rmax", "r20", "r80", "C", "A", "Abgr", "S", "As",

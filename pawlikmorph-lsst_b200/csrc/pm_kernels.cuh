@@ -519,6 +519,7 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
 // ====================================================================================================
 struct SegStats {
     double sum, m10, m01;   // Σ v, Σ row·v, Σ col·v  over segmap pixels (v = img - sky)
+    double abs_sum;         // Σ |v|
     double vmax;            // max v over segmap pixels
     int argmax;             // flat index of the first pixel attaining it
     int edge;
@@ -536,7 +537,7 @@ PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
     }
     pm::sync();
     block_scan_excl_array(sh, c.rowoff, g.n);
-    double s = 0.0, m10 = 0.0, m01 = 0.0, vmax = -1.7976931348623157e308;
+    double s = 0.0, sa = 0.0, m10 = 0.0, m01 = 0.0, vmax = -1.7976931348623157e308;
     int amax = 0x7fffffff;
     for (int r = pm::warp(); r < g.n; r += kWarps) {
         unsigned off = c.rowoff[r];
@@ -551,16 +552,16 @@ PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
                 c.posR[o] = ((unsigned)r << 16) | (unsigned)col;
                 keys[o] = key_of(x, c.sky);
                 const double v = (double)x - c.sky;
-                s += v; m10 += (double)r * v; m01 += (double)col * v;
+                s += v; sa += fabs(v); m10 += (double)r * v; m01 += (double)col * v;
                 const int flat = r * g.n + col;
                 if (v > vmax || (v == vmax && flat < amax)) { vmax = v; amax = flat; }
             }
             off += (unsigned)pm::popc(bits);
         }
     }
-    double red[3] = {s, m10, m01};
-    block_sum<3>(sh, red);
-    st->sum = red[0]; st->m10 = red[1]; st->m01 = red[2];
+    double red[4] = {s, m10, m01, sa};
+    block_sum<4>(sh, red);
+    st->sum = red[0]; st->m10 = red[1]; st->m01 = red[2]; st->abs_sum = red[3];
     const double bm = block_max(sh, vmax);
     st->vmax = bm;
     st->argmax = block_min_i(sh, (vmax == bm) ? amax : 0x7fffffff);
@@ -821,7 +822,7 @@ constexpr int kCandBlock = 4;   // candidates evaluated together per pass over t
 // every lane loads a map pixel once and pairs it with its mirror image about each candidate of the group.
 // kSmem: the pixel list and the masked window live in shared memory (explicit 32-bit addressed loads).
 template <typename T, bool kWrap, bool kSmem>
-PM_DEV void minapix_item(const Ctx<T>& c, const int (&px)[kCandBlock], const int (&py)[kCandBlock], int first, int stride,
+PM_DEV void minapix_item(const Ctx<T>& c, const int (&px)[kCandBlock], const int (&py)[kCandBlock], int first, int end, int stride,
                          double (&num)[kCandBlock], double (&den)[kCandBlock]) {
     const Geo& g = c.g;
     const int n = g.n, bw = c.bw, bh = c.r1 - c.r0 + 1, r0 = c.r0, c0 = c.c0, nw = g.nw;
@@ -830,7 +831,7 @@ PM_DEV void minapix_item(const Ctx<T>& c, const int (&px)[kCandBlock], const int
     int d0[kCandBlock], d1[kCandBlock];
 #pragma unroll
     for (int j = 0; j < kCandBlock; j++) { d0[j] = px[j] - (g.half + 1); d1[j] = py[j] - (g.half + 1); num[j] = 0.0; den[j] = 0.0; }
-    for (int i = first; i < c.n_g; i += stride) {
+    for (int i = first; i < end; i += stride) {
         const unsigned p = kSmem ? pm::lds_u32(pos32 + 4u * (unsigned)i) : c.posR[i];
         const int r = (int)(p >> 16), col = (int)(p & 0xffff);
         const unsigned vi = (unsigned)((r - r0) * bw + (col - c0));
@@ -871,43 +872,52 @@ PM_DEV void minapix_item(const Ctx<T>& c, const int (&px)[kCandBlock], const int
     }
 }
 
+// One warp: candidates cidx[0..3] (indices into `cand`) against the list elements first, first + stride, ... < end;
+// warp-reduced sums to out[2 j], out[2 j + 1] (lane 0).
+template <typename T>
+PM_DEV void minapix_group(const Ctx<T>& c, const unsigned* cand, const int (&cidx)[kCandBlock], int first, int end, int stride,
+                          double* out) {
+    const Geo& g = c.g;
+    int px[kCandBlock], py[kCandBlock];
+    bool nowrap = true;
+#pragma unroll
+    for (int j = 0; j < kCandBlock; j++) {
+        const unsigned pp = cand[cidx[j]];
+        py[j] = (int)(pp >> 16); px[j] = (int)(pp & 0xffff);
+        // rows / columns the aperture is probed at: the map's bounding box and its mirror image (clipped)
+        const int d0 = px[j] - (g.half + 1), d1 = py[j] - (g.half + 1);
+        const int rlo = min(c.r0, max(0, 2 * py[j] - c.r1)), rhi = max(c.r1, min(g.n - 1, 2 * py[j] - c.r0));
+        const int clo = min(c.c0, max(0, 2 * px[j] - c.c1)), chi = max(c.c1, min(g.n - 1, 2 * px[j] - c.c0));
+        nowrap = nowrap && (rlo - d0 >= 0) && (rhi - d0 < g.n) && (clo - d1 >= 0) && (chi - d1 < g.n);
+    }
+    double num[kCandBlock], den[kCandBlock];
+    const bool in_smem = c.ar.in_smem(c.mw) && c.ar.in_smem(c.posR);
+    if (in_smem) {
+        if (nowrap) minapix_item<T, false, true>(c, px, py, first, end, stride, num, den);
+        else minapix_item<T, true, true>(c, px, py, first, end, stride, num, den);
+    } else {
+        if (nowrap) minapix_item<T, false, false>(c, px, py, first, end, stride, num, den);
+        else minapix_item<T, true, false>(c, px, py, first, end, stride, num, den);
+    }
+#pragma unroll
+    for (int j = 0; j < kCandBlock; j++) {
+        const double a = pm::warp_sum(num[j]), b = pm::warp_sum(den[j]);
+        if (pm::lane() == 0) { out[2 * j] = a; out[2 * j + 1] = b; }
+    }
+}
+
 template <typename T>
 PM_DEV void phase_minapix(Ctx<T>& c, const unsigned* cand, int n_cand, double* a_out, double* parts, int slices,
                           int* best) {
-    const Geo& g = c.g;
     Sh& sh = *c.sh;
     const int groups = (n_cand + kCandBlock - 1) / kCandBlock;
     const int items = groups * slices;
     for (int item = pm::warp(); item < items; item += kWarps) {
         const int grp = item / slices, sl = item - grp * slices;
-        int px[kCandBlock], py[kCandBlock];
-        bool nowrap = true;
+        int cidx[kCandBlock];
 #pragma unroll
-        for (int j = 0; j < kCandBlock; j++) {
-            const int k = min(grp * kCandBlock + j, n_cand - 1);
-            const unsigned pp = cand[k];
-            py[j] = (int)(pp >> 16); px[j] = (int)(pp & 0xffff);
-            // rows / columns the aperture is probed at: the map's bounding box and its mirror image (clipped)
-            const int d0 = px[j] - (g.half + 1), d1 = py[j] - (g.half + 1);
-            const int rlo = min(c.r0, max(0, 2 * py[j] - c.r1)), rhi = max(c.r1, min(g.n - 1, 2 * py[j] - c.r0));
-            const int clo = min(c.c0, max(0, 2 * px[j] - c.c1)), chi = max(c.c1, min(g.n - 1, 2 * px[j] - c.c0));
-            nowrap = nowrap && (rlo - d0 >= 0) && (rhi - d0 < g.n) && (clo - d1 >= 0) && (chi - d1 < g.n);
-        }
-        double num[kCandBlock], den[kCandBlock];
-        const bool in_smem = c.ar.in_smem(c.mw) && c.ar.in_smem(c.posR);
-        const int first = sl * 32 + pm::lane(), stride = 32 * slices;
-        if (in_smem) {
-            if (nowrap) minapix_item<T, false, true>(c, px, py, first, stride, num, den);
-            else minapix_item<T, true, true>(c, px, py, first, stride, num, den);
-        } else {
-            if (nowrap) minapix_item<T, false, false>(c, px, py, first, stride, num, den);
-            else minapix_item<T, true, false>(c, px, py, first, stride, num, den);
-        }
-#pragma unroll
-        for (int j = 0; j < kCandBlock; j++) {
-            const double a = pm::warp_sum(num[j]), b = pm::warp_sum(den[j]);
-            if (pm::lane() == 0) { parts[2 * (item * kCandBlock + j)] = a; parts[2 * (item * kCandBlock + j) + 1] = b; }
-        }
+        for (int j = 0; j < kCandBlock; j++) cidx[j] = min(grp * kCandBlock + j, n_cand - 1);
+        minapix_group(c, cand, cidx, sl * 32 + pm::lane(), c.n_g, 32 * slices, parts + 2 * item * kCandBlock);
     }
     pm::sync();
     double amin = 1.7976931348623157e308 * 2.0;   // +inf
@@ -931,6 +941,96 @@ PM_DEV void phase_minapix(Ctx<T>& c, const unsigned* cand, int n_cand, double* a
     int idx = 0x7fffffff;
     for (int k = pm::tid(); k < n_cand; k += kThreads)
         if (a_out[k] == amin) { idx = k; break; }
+    *best = block_min_i(sh, idx);
+}
+
+// minapix with exact pruning (used when the per-candidate asymmetries are not requested as an output).
+// Every term of the numerator Σ|M - M180| is non-negative and the denominator is at most D = Σ_map |M|, so a
+// candidate whose PARTIAL numerator already exceeds 2 D a* — a* being the asymmetry of some fully evaluated
+// candidate — cannot be the minimum and is dropped.  The first kCandBlock candidates (the brightest pixels) are
+// evaluated completely first; the others advance through kStages chunks of the pixel list (middle rows, where
+// the flux is, first) and are re-grouped after every chunk.  The value of a surviving candidate does not depend
+// on which others were dropped (fixed chunk order, one warp per group and chunk).
+constexpr int kStages = 8;
+template <typename T>
+PM_DEV void phase_minapix_pruned(Ctx<T>& c, const unsigned* cand, int n_cand, double dmax, double* acc /*[2 n_cand]*/,
+                                 int* alive /*[n_cand]*/, int* alive2 /*[n_cand]*/, unsigned* flag /*[n_cand + 1]*/,
+                                 double* parts /*[kWarps*8 + 8*groups]*/,
+                                 int* best) {
+    Sh& sh = *c.sh;
+    const int n = c.n_g;
+    // ---- the first group, completely: all warps, interleaved slices
+    {
+        int cidx[kCandBlock];
+#pragma unroll
+        for (int j = 0; j < kCandBlock; j++) cidx[j] = min(j, n_cand - 1);
+        minapix_group(c, cand, cidx, pm::warp() * 32 + pm::lane(), n, 32 * kWarps, parts + 8 * pm::warp());
+        pm::sync();
+        for (int k = pm::tid(); k < 2 * n_cand; k += kThreads) acc[k] = 0.0;
+        pm::sync();
+        if (pm::tid() < min(kCandBlock, n_cand)) {
+            double num = 0.0, den = 0.0;
+            for (int w = 0; w < kWarps; w++) { num += parts[8 * w + 2 * pm::tid()]; den += parts[8 * w + 2 * pm::tid() + 1]; }
+            acc[2 * pm::tid()] = num; acc[2 * pm::tid() + 1] = den;
+        }
+        pm::sync();
+    }
+    double astar = 1.7976931348623157e308 * 2.0;
+    bool any_nan = false;
+    for (int k = 0; k < min(kCandBlock, n_cand); k++) {
+        const double a = acc[2 * k] / (2.0 * acc[2 * k + 1]);
+        if (a != a) any_nan = true; else astar = fmin(astar, a);
+    }
+    // ---- the rest, chunk by chunk
+    int n_alive = max(0, n_cand - kCandBlock);
+    for (int k = pm::tid(); k < n_alive; k += kThreads) alive[k] = kCandBlock + k;
+    pm::sync();
+    const int order[kStages] = {3, 4, 2, 5, 1, 6, 0, 7};
+    const double cut = any_nan ? 1.7976931348623157e308 * 2.0 : 2.0 * dmax * (1.0 + 1e-9) * astar * (1.0 + 1e-9);
+    for (int st = 0; st < kStages && n_alive > 0; st++) {
+        const int ch = order[st];
+        const int lo = (int)(((long long)n * ch) / kStages), hi = (int)(((long long)n * (ch + 1)) / kStages);
+        const int groups = (n_alive + kCandBlock - 1) / kCandBlock;
+        for (int grp = pm::warp(); grp < groups; grp += kWarps) {
+            int cidx[kCandBlock];
+#pragma unroll
+            for (int j = 0; j < kCandBlock; j++) cidx[j] = alive[min(grp * kCandBlock + j, n_alive - 1)];
+            minapix_group(c, cand, cidx, lo + pm::lane(), hi, 32, parts + 8 * kWarps + 8 * grp);
+        }
+        pm::sync();
+        // accumulate, decide, compact the survivors (order preserved)
+        for (int k = pm::tid(); k < n_alive; k += kThreads) {
+            const int ci = alive[k];
+            const double num = acc[2 * ci] + parts[8 * kWarps + 8 * (k / kCandBlock) + 2 * (k % kCandBlock)];
+            const double den = acc[2 * ci + 1] + parts[8 * kWarps + 8 * (k / kCandBlock) + 2 * (k % kCandBlock) + 1];
+            acc[2 * ci] = num; acc[2 * ci + 1] = den;
+            flag[k] = (st == kStages - 1 || !(num > cut)) ? 1u : 0u;     // NaN partial sums are never dropped
+        }
+        pm::sync();
+        if (st == kStages - 1) break;
+        const int keep = (int)block_scan_excl_array(sh, flag, n_alive);
+        for (int k = pm::tid(); k < n_alive; k += kThreads)
+            if (flag[k + 1] != flag[k]) alive2[flag[k]] = alive[k];
+        pm::sync();
+        { int* t = alive; alive = alive2; alive2 = t; }
+        n_alive = keep;
+    }
+    // ---- first minimum over the completely evaluated candidates (dropped ones are strictly larger than a*)
+    double amin = 1.7976931348623157e308 * 2.0;
+    int nan_idx = 0x7fffffff;
+    for (int k = pm::tid(); k < n_alive + min(kCandBlock, n_cand); k += kThreads) {
+        const int ci = k < min(kCandBlock, n_cand) ? k : alive[k - min(kCandBlock, n_cand)];
+        const double a = acc[2 * ci] / (2.0 * acc[2 * ci + 1]);
+        if (a != a) nan_idx = min(nan_idx, ci); else amin = fmin(amin, a);
+    }
+    nan_idx = block_min_i(sh, nan_idx);
+    if (nan_idx != 0x7fffffff) { *best = nan_idx; return; }
+    amin = block_min(sh, amin);
+    int idx = 0x7fffffff;
+    for (int k = pm::tid(); k < n_alive + min(kCandBlock, n_cand); k += kThreads) {
+        const int ci = k < min(kCandBlock, n_cand) ? k : alive[k - min(kCandBlock, n_cand)];
+        if (acc[2 * ci] / (2.0 * acc[2 * ci + 1]) == amin) idx = min(idx, ci);
+    }
     *best = block_min_i(sh, idx);
 }
 
@@ -1834,7 +1934,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         const unsigned* cand = spA;
         if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }   // workspace contract violated
         SegStats st;
-        st.sum = st.m10 = st.m01 = st.vmax = 0.0; st.argmax = 0; st.edge = edge;
+        st.sum = st.m10 = st.m01 = st.vmax = st.abs_sum = 0.0; st.argmax = 0; st.edge = edge;
         int cen_flat = 0, rmax2 = 0;
         double rmax = 0.0;
         SortOut so;
@@ -1916,18 +2016,31 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             } else {
                 Arena::Mark mk = c.ar.mark();
                 const int groups = (so.n_cand + kCandBlock - 1) / kCandBlock;
-                int slices = (3 * kWarps + groups - 1) / groups;       // aim at >= 3 work items per warp
-                slices = max(1, min(slices, (n_g + 63) / 64));
-                double* a_arr = (double*)c.ar.alloc((size_t)so.n_cand * 8);
-                double* parts = (double*)c.ar.alloc((size_t)groups * slices * kCandBlock * 16);
                 int best = 0;
-                if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
-                else {
-                    phase_minapix(c, cand, so.n_cand, a_arr, parts, slices, &best);
-                    if (p.out.cand_a_out) {
-                        for (int i = pm::tid(); i < p.out.cand_cap; i += kThreads)
-                            p.out.cand_a_out[(size_t)b * p.out.cand_cap + i] = i < so.n_cand ? a_arr[i] : -99.0;
+                const bool prune = p.out.cand_a_out == nullptr && so.n_cand > 2 * kCandBlock && !(p.flags & PM_NO_PRUNE);
+                if (prune) {
+                    double* acc = (double*)c.ar.alloc((size_t)so.n_cand * 16);
+                    int* alive = (int*)c.ar.alloc((size_t)so.n_cand * 4);
+                    int* alive2 = (int*)c.ar.alloc((size_t)so.n_cand * 4);
+                    unsigned* flag = (unsigned*)c.ar.alloc((size_t)(so.n_cand + 1) * 4);
+                    double* parts = (double*)c.ar.alloc((size_t)(kWarps + groups) * 64);
+                    if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+                    else phase_minapix_pruned(c, cand, so.n_cand, st.abs_sum, acc, alive, alive2, flag, parts, &best);
+                } else {
+                    int slices = (3 * kWarps + groups - 1) / groups;       // aim at >= 3 work items per warp
+                    slices = max(1, min(slices, (n_g + 63) / 64));
+                    double* a_arr = (double*)c.ar.alloc((size_t)so.n_cand * 8);
+                    double* parts = (double*)c.ar.alloc((size_t)groups * slices * kCandBlock * 16);
+                    if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+                    else {
+                        phase_minapix(c, cand, so.n_cand, a_arr, parts, slices, &best);
+                        if (p.out.cand_a_out) {
+                            for (int i = pm::tid(); i < p.out.cand_cap; i += kThreads)
+                                p.out.cand_a_out[(size_t)b * p.out.cand_cap + i] = i < so.n_cand ? a_arr[i] : -99.0;
+                        }
                     }
+                }
+                if (!done) {
                     const unsigned q = cand[best];
                     cy = (int)(q >> 16); cx = (int)(q & 0xffff);
                 }

@@ -58,3 +58,21 @@ def test_flag_subsets_and_faint_centre():
     # faint centre -> status 1, all sentinels, empty map (pixmap.py:178-179, main.py:420-424)
     res = run(x, 100.0, 1e6, 3, 15)
     assert np.all(res["rows"][:, 14] == 1) and np.all(res["rows"][:, :13] == -99) and not res["segmap"].any()
+
+
+@pytest.mark.parametrize("name,i", [("sdss_s", i) for i in range(1, 69, 9)] + [("sdss_l", i) for i in range(2, 69, 11)]
+                         + [("synth", i) for i in (0, 11, 19, 26, 27, 29, 31)])
+def test_golden_with_pruned_minapix(name, i):
+    """Without the per-candidate output minapix drops candidates whose partial numerator already exceeds the best
+    complete asymmetry (exact pruning): the chosen centre, and with it every statistic, must not change."""
+    from tests.runners import emul_runner_pruned
+    P.check_golden_case(emul_runner_pruned, name, i)
+
+
+def test_pruned_and_unpruned_minapix_agree():
+    from tests.emul_harness import abi
+    from tests.runners import emul_runner_pruned
+    x = P.synth_batch(6, 128, 91)
+    a = emul_runner_pruned(x, 100.0, 5.0, 3, 15)
+    b = emul_runner_pruned(x, 100.0, 5.0, 3, 15 | abi.PM_NO_PRUNE)
+    assert np.array_equal(a["rows"], b["rows"], equal_nan=True)

@@ -212,3 +212,21 @@ def test_star_masks_in_the_per_cutout_api():
     np.testing.assert_allclose(pm.asymmetry.calcA(seg, seg, ap, apix, 90.0, star), O.calcA(seg, seg, ap, apix, 90.0, star),
                                rtol=1e-12)
     np.testing.assert_allclose(pm.pixmap.calcMaskedFraction(seg, star, apix), O.calcMaskedFraction(seg, star, apix), rtol=1e-12)
+
+
+def test_pruned_minapix():
+    """The production configuration (no per-candidate output -> exact pruning in minapix) on every golden case and
+    against the unpruned evaluation at bench size."""
+    import torch
+
+    import pawlikmorph_lsst_b200 as pm
+    import synth
+    from tests.runners import gpu_runner_pruned
+    for name in ("sdss_s", "sdss_l", "synth"):
+        g = P.golden(name)
+        for i in range(g.n):
+            P.check_golden_case(gpu_runner_pruned, name, i)
+    x = synth.make_batch(4096, 256, 778, device="cuda")
+    a = pm.batch.analyse_batch(x, 100.0, 5.0, 3, 15).rows
+    b = pm.batch.analyse_batch(x, 100.0, 5.0, 3, 15 | pm._abi.PM_NO_PRUNE).rows
+    assert torch.equal(a, b)
