@@ -23,12 +23,14 @@ constexpr int kRedSlots = 8;
 
 // Block-shared scalars.  Lives at offset 0 of the dynamic shared memory.
 struct Sh {
-    double red[kWarps * kRedSlots];  // per-warp partials of block reductions
+    double red[2][kWarps * kRedSlots];  // per-warp partials of block reductions, two alternating halves: a reduction
+                                        // needs ONE barrier (the previous half is still being read while this one fills)
     double bc[16];                   // broadcast slots
     double rk[132];                  // walk radii of casgm.py:55-73
     double fk[132];                  // F(rk): lower bounds during the walk
     double fh[132];                  // upper bounds
-    unsigned scan_tmp[kWarps + 2];
+    unsigned scan_tmp[2][kWarps + 2];
+    unsigned char par[kThreads];     // per-thread parity of the reduction scratch (each thread touches only its own)
     unsigned colmask[24];            // OR of all segmap rows (PM_MAX_N / 32 words)
     unsigned long long mbar[2];      // mbarriers of the two TMA staging buffers (pixelmap)
     int ia[8 + 2 * kRedSlots];       // work index; integer thresholds of the radii being evaluated
@@ -38,22 +40,30 @@ struct Sh {
 PM_DEV unsigned lt_mask() { return (1u << pm::lane()) - 1u; }
 
 // ---- reductions ------------------------------------------------------------------------
+// All block reductions: per-warp partials go to one of two alternating scratch halves, ONE barrier, then every
+// thread combines the partials in a fixed order.  The half written by reduction k is read until the barrier of
+// reduction k + 1 at the latest, and written again only by reduction k + 2: no trailing barrier is needed.
+PM_DEV unsigned red_half(Sh& sh) {
+    const unsigned h = sh.par[pm::tid()];
+    sh.par[pm::tid()] = (unsigned char)(h ^ 1u);
+    return h;
+}
 template <int K> PM_DEV void block_sum(Sh& sh, double (&v)[K]) {
     static_assert(K <= kRedSlots, "too many reduction slots");
+    double* red = sh.red[red_half(sh)];
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = pm::warp_sum(v[k]);
     if (pm::lane() == 0) {
 #pragma unroll
-        for (int k = 0; k < K; k++) sh.red[pm::warp() * K + k] = v[k];
+        for (int k = 0; k < K; k++) red[pm::warp() * K + k] = v[k];
     }
     pm::sync();
 #pragma unroll
     for (int k = 0; k < K; k++) {
         double s = 0.0;
-        for (int w = 0; w < kWarps; w++) s += sh.red[w * K + k];
+        for (int w = 0; w < kWarps; w++) s += red[w * K + k];
         v[k] = s;
     }
-    pm::sync();
 }
 PM_DEV double block_sum1(Sh& sh, double v) {
     double a[1] = {v};
@@ -61,76 +71,76 @@ PM_DEV double block_sum1(Sh& sh, double v) {
     return a[0];
 }
 PM_DEV double block_max(Sh& sh, double v) {
+    double* red = sh.red[red_half(sh)];
     v = pm::warp_max(v);
-    if (pm::lane() == 0) sh.red[pm::warp()] = v;
+    if (pm::lane() == 0) red[pm::warp()] = v;
     pm::sync();
-    double s = sh.red[0];
-    for (int w = 1; w < kWarps; w++) s = fmax(s, sh.red[w]);
-    pm::sync();
+    double s = red[0];
+    for (int w = 1; w < kWarps; w++) s = fmax(s, red[w]);
     return s;
 }
 PM_DEV double block_min(Sh& sh, double v) {
+    double* red = sh.red[red_half(sh)];
     v = pm::warp_min(v);
-    if (pm::lane() == 0) sh.red[pm::warp()] = v;
+    if (pm::lane() == 0) red[pm::warp()] = v;
     pm::sync();
-    double s = sh.red[0];
-    for (int w = 1; w < kWarps; w++) s = fmin(s, sh.red[w]);
-    pm::sync();
+    double s = red[0];
+    for (int w = 1; w < kWarps; w++) s = fmin(s, red[w]);
     return s;
 }
 PM_DEV int block_min_i(Sh& sh, int v) {
+    unsigned* tmp = sh.scan_tmp[red_half(sh)];
     v = pm::warp_min(v);
-    if (pm::lane() == 0) sh.scan_tmp[pm::warp()] = (unsigned)v;
+    if (pm::lane() == 0) tmp[pm::warp()] = (unsigned)v;
     pm::sync();
-    int s = (int)sh.scan_tmp[0];
-    for (int w = 1; w < kWarps; w++) s = min(s, (int)sh.scan_tmp[w]);
-    pm::sync();
+    int s = (int)tmp[0];
+    for (int w = 1; w < kWarps; w++) s = min(s, (int)tmp[w]);
     return s;
 }
 PM_DEV int block_max_i(Sh& sh, int v) {
+    unsigned* tmp = sh.scan_tmp[red_half(sh)];
     v = pm::warp_max(v);
-    if (pm::lane() == 0) sh.scan_tmp[pm::warp()] = (unsigned)v;
+    if (pm::lane() == 0) tmp[pm::warp()] = (unsigned)v;
     pm::sync();
-    int s = (int)sh.scan_tmp[0];
-    for (int w = 1; w < kWarps; w++) s = max(s, (int)sh.scan_tmp[w]);
-    pm::sync();
+    int s = (int)tmp[0];
+    for (int w = 1; w < kWarps; w++) s = max(s, (int)tmp[w]);
     return s;
 }
 PM_DEV unsigned block_sum_u(Sh& sh, unsigned v) {
+    unsigned* tmp = sh.scan_tmp[red_half(sh)];
     v = pm::warp_sum(v);
-    if (pm::lane() == 0) sh.scan_tmp[pm::warp()] = v;
+    if (pm::lane() == 0) tmp[pm::warp()] = v;
     pm::sync();
     unsigned s = 0;
-    for (int w = 0; w < kWarps; w++) s += sh.scan_tmp[w];
-    pm::sync();
+    for (int w = 0; w < kWarps; w++) s += tmp[w];
     return s;
 }
 // exclusive prefix of one value per thread (thread order); *total gets the block total
 PM_DEV unsigned block_excl_prefix_u(Sh& sh, unsigned v, unsigned* total) {
+    unsigned* tmp = sh.scan_tmp[red_half(sh)];
     unsigned inc = pm::warp_incl_scan(v);
-    if (pm::lane() == 31) sh.scan_tmp[pm::warp()] = inc;
+    if (pm::lane() == 31) tmp[pm::warp()] = inc;
     pm::sync();
     unsigned base = 0, tot = 0;
     for (int w = 0; w < kWarps; w++) {
-        unsigned t = sh.scan_tmp[w];
+        unsigned t = tmp[w];
         if (w < pm::warp()) base += t;
         tot += t;
     }
-    pm::sync();
     *total = tot;
     return base + inc - v;
 }
 PM_DEV double block_excl_prefix_d(Sh& sh, double v, double* total) {
+    double* red = sh.red[red_half(sh)];
     double inc = pm::warp_incl_scan(v);
-    if (pm::lane() == 31) sh.red[pm::warp()] = inc;
+    if (pm::lane() == 31) red[pm::warp()] = inc;
     pm::sync();
     double base = 0.0, tot = 0.0;
     for (int w = 0; w < kWarps; w++) {
-        double t = sh.red[w];
+        double t = red[w];
         if (w < pm::warp()) base += t;
         tot += t;
     }
-    pm::sync();
     *total = tot;
     return base + (inc - v);
 }

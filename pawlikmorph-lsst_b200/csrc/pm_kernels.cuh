@@ -1305,11 +1305,10 @@ PM_DEV void fold_column_bounds(const Fold& f, int a, int lim_in, int lim_out, do
     }
     *lo = l; *hi = h;
 }
-// exact F(r) for nr <= kRedSlots radii; results in sh.bc[0..nr).  Pass 1: one (radius, column) item per
+// exact F(r) for nr <= kRedSlots radii; results in acc[0..nr) of every thread.  Pass 1: one (radius, column) item per
 // thread finds the cut range and adds the fully-inside prefix; pass 2: the cut pixels of all columns are
 // dealt out evenly, one exact circle/pixel overlap per thread-step.  off / blo: nr * (A + 1) + 1 entries each.
-PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo) {
-    double acc[kRedSlots];
+PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo, double (&acc)[kRedSlots]) {
 #pragma unroll
     for (int q = 0; q < kRedSlots; q++) acc[q] = 0.0;
     const int ncol = f.A + 1, items = nr * ncol;
@@ -1345,12 +1344,7 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
         for (int k = 0; k < kRedSlots; k++)
             if (k == q) acc[k] += v;
     }
-    block_sum<kRedSlots>(sh, acc);
-    if (pm::tid() == 0) {
-#pragma unroll
-        for (int q = 0; q < kRedSlots; q++) sh.bc[q] = acc[q];
-    }
-    pm::sync();
+    block_sum<kRedSlots>(sh, acc);      // every thread now holds F(radii[q]) in acc[q]
 }
 // bounds lo <= F(r_k) <= hi for the walk radii rk[1..K]: one warp per radius.  A pixel at squared distance
 // d2 is certainly inside when d2 <= floor((r - pr - 1e-9)^2) - 1 and certainly outside when d2 > ceil((r + pr + 1e-9)^2).
@@ -1453,9 +1447,9 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         while (K < 130 && r > 0.0) { K++; if (pm::tid() == 0) sh.rk[K] = r; r -= delta; }
     }
     pm::sync();
-    eval_flux(sh, f, sh.rk, 1, eoff, eblo);
-    const double total = sh.bc[0];
-    pm::sync();
+    double fv[kRedSlots];
+    eval_flux(sh, f, sh.rk, 1, eoff, eblo, fv);
+    const double total = fv[0];
     // Walk down (casgm.py:61-73): first k with F(r_k) / total <= fraction.  Cheap bounds decide most radii;
     // only the undecided ones near the crossing are evaluated exactly.
     eval_flux_bounds(sh, f, K);
@@ -1490,10 +1484,10 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
                 if (pm::tid() == 0)
                     for (int i = 0; i < nl; i++) sh.bc[8 + i] = sh.rk[list[i]];
                 pm::sync();
-                eval_flux(sh, f, sh.bc + 8, nl, eoff, eblo2);
+                eval_flux(sh, f, sh.bc + 8, nl, eoff, eblo2, fv);
                 for (int i = 0; i < nl && kfound[q] < 0; i++)
-                    if (sh.bc[i] / total <= fr[q]) kfound[q] = list[i];
-                pm::sync();
+                    if (fv[i] / total <= fr[q]) kfound[q] = list[i];
+                pm::sync();      // sh.bc[8..] is rewritten by the next batch
             }
             if (kfound[q] < 0 && sure > 0) kfound[q] = sure;
             pos = (sure > 0) ? K + 1 : k;
@@ -1538,7 +1532,8 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         ctv[e] = f.T[tri(a, bb)];
     }
     pm::sync();
-    // F_q(r_q) for the active fractions -> sh.bc[q]
+    // F_q(r_q) for the active fractions -> fq[q] (in every thread)
+    double fq[2] = {0.0, 0.0};
     auto eval_cached = [&](const double (&rq)[2], const bool (&act)[2]) {
         double acc[2] = {0.0, 0.0};
         for (int e = pm::tid(); e < ncache; e += kThreads) {
@@ -1549,19 +1544,16 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
             if (q == 0) acc[0] += v; else acc[1] += v;
         }
         block_sum<2>(sh, acc);
-        if (pm::tid() == 0) { sh.bc[0] = base[0] + acc[0]; sh.bc[1] = base[1] + acc[1]; }
-        pm::sync();
+        fq[0] = base[0] + acc[0]; fq[1] = base[1] + acc[1];
     };
     const double fr2[2] = {0.2, 0.8};
     {
         const bool both[2] = {true, true};
         double flo[2], fhi[2];
         eval_cached(blo_r, both);
-        flo[0] = sh.bc[0]; flo[1] = sh.bc[1];
-        pm::sync();
+        flo[0] = fq[0]; flo[1] = fq[1];
         eval_cached(bhi_r, both);
-        fhi[0] = sh.bc[0]; fhi[1] = sh.bc[1];
-        pm::sync();
+        fhi[0] = fq[0]; fhi[1] = fq[1];
         for (int q = 0; q < 2; q++) brent_init(b[q], blo_r[q], bhi_r[q], flo[q] / total - fr2[q], fhi[q] / total - fr2[q]);
     }
     for (;;) {
@@ -1575,8 +1567,7 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         if (!act[0] && !act[1]) break;
         eval_cached(rq, act);
         for (int q = 0; q < 2; q++)
-            if (act[q]) b[q].fcur = sh.bc[q] / total - fr2[q];
-        pm::sync();
+            if (act[q]) b[q].fcur = fq[q] / total - fr2[q];
     }
     c.ar.release(mk);
     if (b[0].state != 1 || b[1].state != 1) return;
@@ -2104,6 +2095,7 @@ template <typename T> PM_DEV void analyse_body(const Params& p) {
     c.ar.init(smem + sm.arena, sm.arena_bytes, p.scratch + (size_t)pm::block() * p.scratch_per_cta, (size_t)p.scratch_per_cta);
     c.n_g = 0; c.r0 = c.c0 = 0; c.r1 = c.c1 = -1; c.posR = nullptr; c.plist = nullptr; c.mw = nullptr; c.bw = 0;
     c.mbar_phase[0] = c.mbar_phase[1] = 0u;
+    c.sh->par[pm::tid()] = 0;
     if (pm::tid() == 0) { pm::mbar_init(&c.sh->mbar[0], 1); pm::mbar_init(&c.sh->mbar[1], 1); pm::mbar_fence_init(); }
     build_tables(c);
     // Persistent CTA: galaxy indices come from a global work counter, fetched ONE AHEAD so that the next cutout
