@@ -263,8 +263,11 @@ PM_DEV void pixelmap_fast(Ctx<T>& c, unsigned* zb, int* centre_faint, double* mi
         const int rhi = min(n - 1, (int)c.i0[band + rows - 1] + h + 1);
         *cnt = (rhi - *rlo + 1) * n;
     };
+    // TMA needs 16-byte aligned source / size and BOTH staging buffers in shared memory (large n with a large
+    // filter can push them to the global scratch: then the cooperative-load path is used)
+    const bool staging_in_smem = xb0 != xb1 && c.ar.in_smem(xb0) && c.ar.in_smem(xb1);
     auto tma_ok = [&](int rlo, int cnt) {
-        return (((uintptr_t)(c.img + (size_t)rlo * n)) & 15) == 0 && (((size_t)cnt * sizeof(T)) & 15) == 0;
+        return staging_in_smem && (((uintptr_t)(c.img + (size_t)rlo * n)) & 15) == 0 && (((size_t)cnt * sizeof(T)) & 15) == 0;
     };
     auto issue = [&](int k) {       // thread 0: start the bulk copy of band k if it qualifies
         int rlo, cnt;
@@ -449,7 +452,21 @@ PM_DEV void load_plane_u8(const Geo& g, const uint8_t* src, unsigned* plane) {
     pm::sync();
 }
 PM_DEV void store_plane_u8(const Geo& g, const unsigned* plane, uint8_t* dst) {
-    // 4 pixels per thread-step; word stores when the destination is 4-byte aligned (32-bit index math: N < 2^20)
+    if ((g.n & 3) == 0 && ((uintptr_t)dst & 3) == 0) {
+        // aligned rows: one (row, 32-pixel word) per thread-step; 4 bits -> 4 bytes with one multiply
+        // ((b & 0xF) * 0x00204081) & 0x01010101 puts bit k into byte k
+        for (int task = pm::tid(); task < g.n * g.nw; task += kThreads) {
+            const int r = task / g.nw, w = task - r * g.nw;
+            const unsigned bits = plane[task];
+            uint32_t* d32 = (uint32_t*)(dst + (size_t)r * g.n + w * 32);
+            const int nq = min(8, (g.n - w * 32) >> 2);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (q < nq) d32[q] = (((bits >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        }
+        return;
+    }
+    // general case: 4 pixels per thread-step; word stores when the destination is 4-byte aligned (N < 2^20)
     const int total = g.N;
     const int head = min(total, (int)((4 - ((uintptr_t)dst & 3)) & 3));
     for (int i = pm::tid(); i < head; i += kThreads) {
@@ -492,8 +509,10 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
             R--;
         }
         const int nrows = min(g.n, (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3);
-        T* xb0 = (T*)c.ar.alloc((size_t)nrows * g.n * sizeof(T));
-        T* xb1 = (T*)c.ar.alloc((size_t)nrows * g.n * sizeof(T));
+        const size_t xbytes = (size_t)nrows * g.n * sizeof(T);
+        T* xb0 = (T*)c.ar.alloc(xbytes);
+        T* xb1 = xb0;                                               // one buffer only when two do not fit shared memory
+        if (2 * xbytes + 16 <= (size_t)(c.ar.s_cap - mk.s)) xb1 = (T*)c.ar.alloc(xbytes);
         if (g.fs == 3) pixelmap_fast<T, 3>(c, zb, &faint, &mn, &mx, xb0, xb1, R);
         else pixelmap_fast<T, 0>(c, zb, &faint, &mn, &mx, xb0, xb1, R);
         c.ar.release(mk);

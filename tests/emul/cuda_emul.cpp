@@ -54,6 +54,7 @@ void run_block(int block_id, int nblocks, int nthreads, size_t smem_bytes, const
     blk.wgen.assign(nthreads, 0);
     blk.tgen.assign(nthreads, 0);
     blk.smem = (unsigned char*)aligned_alloc(128, (smem_bytes + 127) / 128 * 128 + 128);
+    blk.smem_bytes = smem_bytes;
     memset(blk.smem, 0xCD, smem_bytes);  // smem is uninitialised on the GPU too
     Block* saved = g_blk;
     g_blk = &blk;

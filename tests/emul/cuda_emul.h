@@ -38,6 +38,7 @@ struct Block {
     std::vector<WarpState> warps;
     std::vector<unsigned long long> wgen;  // per-thread count of warp collectives entered
     unsigned char* smem = nullptr;
+    size_t smem_bytes = 0;
     void* sched_sp = nullptr;
     int cur = 0;
     // block barrier
@@ -189,6 +190,12 @@ PM_DEV void prefetch_l2(const void*, unsigned) {}
 PM_DEV void mbar_init(unsigned long long* bar, unsigned) { *bar = 0; }
 PM_DEV void mbar_fence_init() {}
 PM_DEV void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    // the hardware requires a SHARED destination and 16-byte alignment: catch violations on the CPU
+    const unsigned char* d = (const unsigned char*)smem_dst;
+    if (d < g_blk->smem || d + bytes > g_blk->smem + g_blk->smem_bytes || ((uintptr_t)gsrc & 15) || (bytes & 15) || ((uintptr_t)d & 15)) {
+        fprintf(stderr, "pm_emul: illegal TMA bulk copy (dst not in shared memory or misaligned)\n");
+        abort();
+    }
     memcpy(smem_dst, gsrc, bytes);   // the emulated copy completes at once
     (*bar)++;
 }
@@ -197,7 +204,11 @@ PM_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {   // phase wit
 }
 PM_DEV void dadd_if(bool pred, double& acc, double x) { if (pred) acc += x; }
 PM_DEV long long clock() { return 0; }
-PM_DEV unsigned smem_addr(const void* p) { return (unsigned)((const unsigned char*)p - g_blk->smem); }
+PM_DEV unsigned smem_addr(const void* p) {
+    const unsigned char* q = (const unsigned char*)p;
+    if (q < g_blk->smem || q >= g_blk->smem + g_blk->smem_bytes) { fprintf(stderr, "pm_emul: smem_addr of a non-shared pointer\n"); abort(); }
+    return (unsigned)(q - g_blk->smem);
+}
 PM_DEV unsigned lds_u32(unsigned a) { unsigned v; memcpy(&v, g_blk->smem + a, 4); return v; }
 PM_DEV float lds_f32(unsigned a) { float v; memcpy(&v, g_blk->smem + a, 4); return v; }
 PM_DEV double lds_f64(unsigned a) { double v; memcpy(&v, g_blk->smem + a, 8); return v; }

@@ -76,3 +76,24 @@ def test_pruned_and_unpruned_minapix_agree():
     a = emul_runner_pruned(x, 100.0, 5.0, 3, 15)
     b = emul_runner_pruned(x, 100.0, 5.0, 3, 15 | abi.PM_NO_PRUNE)
     assert np.array_equal(a["rows"], b["rows"], equal_nan=True)
+
+
+@pytest.mark.parametrize("n,fs", [(8, 1), (9, 3), (12, 3), (15, 5), (16, 15), (17, 1), (33, 11), (40, 13)])
+def test_tiny_cutouts_and_every_filter_size(n, fs):
+    """Smallest sizes the ABI accepts and the whole range of filter sizes (imganalysis.py:45-47)."""
+    rng = np.random.default_rng(7 + n)
+    yy, xx = np.mgrid[0:n, 0:n]
+    x = np.stack([(100 + rng.normal(0, 5, (n, n)) + 400 * np.exp(-((xx - n // 2) ** 2 + (yy - n // 2) ** 2) / (2 * (n / 8) ** 2)))
+                  for _ in range(2)]).astype(np.float32)
+    P.check_against_oracle(run, x, 100.0, 5.0, fs)
+
+
+def test_large_cutout_with_large_filter_spills_staging():
+    """n = 640 with filterSize 15: the pixelmap staging rows no longer fit shared memory twice, so the TMA
+    double buffer must give way to the cooperative-load path (the emulator aborts on a TMA copy whose
+    destination is not shared memory)."""
+    rng = np.random.default_rng(123)
+    n = 640
+    yy, xx = np.mgrid[0:n, 0:n]
+    img = (100 + rng.normal(0, 5, (n, n)) + 900 * np.exp(-(((xx - 321) / 7.0) ** 2 + ((yy - 318) / 5.0) ** 2) / 2)).astype(np.float32)
+    P.check_against_oracle(run, img[None], 100.0, 5.0, 15)

@@ -230,3 +230,21 @@ def test_pruned_minapix():
     a = pm.batch.analyse_batch(x, 100.0, 5.0, 3, 15).rows
     b = pm.batch.analyse_batch(x, 100.0, 5.0, 3, 15 | pm._abi.PM_NO_PRUNE).rows
     assert torch.equal(a, b)
+
+
+def test_maximum_size_and_supplied_segmaps():
+    """n = PM_MAX_N (640) with filter sizes 1 and 15, and the -segmap path (main.py:428-439): a supplied map
+    must give exactly the rows of the computed one."""
+    import pawlikmorph_lsst_b200 as pm
+    rng = np.random.default_rng(123)
+    n = 640
+    yy, xx = np.mgrid[0:n, 0:n]
+    img = (100 + rng.normal(0, 5, (n, n)) + 900 * np.exp(-(((xx - 321) / 7.0) ** 2 + ((yy - 318) / 5.0) ** 2) / 2)).astype(np.float32)
+    for fs in (1, 15):
+        P.check_against_oracle(run, img[None], 100.0, 5.0, fs)
+    x = P.synth_batch(4, 256, 97)
+    a = run(x, 100.0, 5.0, 3, 15)
+    b = run(x, 100.0, 5.0, 3, 15, segmap_in=a["segmap"])
+    rows_a, rows_b = a["rows"].copy(), b["rows"].copy()
+    rows_a[:, 13] = 0      # object_edge is only set on the pixelmap path (main.py:427)
+    assert np.array_equal(rows_a, rows_b)
