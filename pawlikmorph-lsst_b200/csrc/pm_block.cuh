@@ -307,9 +307,13 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
 // CircularAperture(...).do_photometry(method="exact") at casgm.py:51-52, :66-67, :116-117, :333-336).
 PM_DEV double fsqrt0(double v) { return v > 0.0 ? sqrt(v) : 0.0; }
 PM_DEV double area_arc(double x1, double y1, double x2, double y2, double r) {
-    double a = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
-    double theta = 2.0 * asin(0.5 * a / r);
-    return 0.5 * r * r * (theta - sin(theta));
+    // photutils: a = chord, theta = 2 asin(a / 2r), area = r^2 (theta - sin theta) / 2.  sin(theta) is taken as
+    // 2 h sqrt(1 - h^2), h = a / 2r (independent of the asin: shorter dependency chain; same value to ~1 ulp)
+    const double a = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+    const double h = 0.5 * a / r;
+    const double theta = 2.0 * asin(h);
+    const double sin_theta = 2.0 * h * sqrt(fmax(1.0 - h * h, 0.0));
+    return 0.5 * r * r * (theta - sin_theta);
 }
 PM_DEV double area_tri(double x1, double y1, double x2, double y2, double x3, double y3) {
     return 0.5 * fabs(x1 * (y2 - y3) + x2 * (y3 - y1) + x3 * (y1 - y2));
@@ -319,19 +323,20 @@ PM_DEV_NOINLINE double overlap_core(double xmin, double ymin, double xmax, doubl
     const double r2 = r * r;
     if (xmin * xmin + ymin * ymin > r2) return 0.0;
     if (xmax * xmax + ymax * ymax < r2) return (xmax - xmin) * (ymax - ymin);
-    const double d1 = fsqrt0(xmax * xmax + ymin * ymin);
-    const double d2 = fsqrt0(xmin * xmin + ymax * ymax);
-    if (d1 < r && d2 < r) {
+    // corner tests on squared distances (photutils compares the square roots: same decisions up to rounding at
+    // the exact boundary, where the area formulas agree anyway)
+    const bool in1 = xmax * xmax + ymin * ymin < r2, in2 = xmin * xmin + ymax * ymax < r2;
+    if (in1 && in2) {
         double x1 = fsqrt0(r2 - ymax * ymax), y1 = ymax;
         double x2 = xmax, y2 = fsqrt0(r2 - xmax * xmax);
         return (xmax - xmin) * (ymax - ymin) - area_tri(x1, y1, x2, y2, xmax, ymax) + area_arc(x1, y1, x2, y2, r);
     }
-    if (d1 < r) {
+    if (in1) {
         double x1 = xmin, y1 = fsqrt0(r2 - xmin * xmin);
         double x2 = xmax, y2 = fsqrt0(r2 - xmax * xmax);
         return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, x1, ymin, xmax, ymin) + area_tri(x1, y1, x2, ymin, x2, y2);
     }
-    if (d2 < r) {
+    if (in2) {
         double x1 = fsqrt0(r2 - ymin * ymin), y1 = ymin;
         double x2 = fsqrt0(r2 - ymax * ymax), y2 = ymax;
         return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, xmin, y1, xmin, ymax) + area_tri(x1, y1, xmin, y2, x2, y2);

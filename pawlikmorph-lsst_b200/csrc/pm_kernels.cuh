@@ -138,13 +138,19 @@ template <typename T> struct Ctx {
     const unsigned* plist;   // the list minapix iterates over: posR, or the brightness-sorted list (pruned path)
     T* mw;               // masked window over the bounding box (NaN outside the segmap)
     PhaseClock pc;       // tuning aid
+    const T* crop;       // copy of the central part of the image in shared memory (late phases), or null
+    int crop_r0, crop_c0, crop_h, crop_w;
     unsigned mbar_phase[2];   // parity of the two staging mbarriers (uniform across the CTA)
     int bw;              // window width
 };
 
-template <typename T> PM_DEV double ld(const Ctx<T>& c, int r, int col) {
-    return (double)pm::ldg(c.img + (size_t)r * c.g.n + col);
+// image value at (r, col): from the shared-memory crop when it covers the pixel, else from global memory
+template <typename T> PM_DEV T ld_raw(const Ctx<T>& c, int r, int col) {
+    const unsigned rr = (unsigned)(r - c.crop_r0), cc = (unsigned)(col - c.crop_c0);
+    if (rr < (unsigned)c.crop_h && cc < (unsigned)c.crop_w) return c.crop[rr * (unsigned)c.crop_w + cc];
+    return pm::ldg(c.img + (size_t)r * c.g.n + col);
 }
+template <typename T> PM_DEV double ld(const Ctx<T>& c, int r, int col) { return (double)ld_raw(c, r, col); }
 PM_DEV bool bit_at(const unsigned* plane, int nw, int r, int c) {
     return (plane[r * nw + (c >> 5)] >> (c & 31)) & 1u;
 }
@@ -1185,16 +1191,17 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
             // source indices first (shared-memory work only), then all image loads back to back
             const int fI = r * g.n + col;
             int fR = -1, fB = -1, fBr = -1;
-            if (rot90) { if (in90) fR = r90 * g.n + c90; }
-            else if (in180) fR = r180 * g.n + c180;
+            int rR = r, cR = col;
+            if (rot90) { if (in90) { fR = 1; rR = r90; cR = c90; } }
+            else if (in180) { fR = 1; rR = r180; cR = c180; }
             if (bgr_ok) {
                 // the background image is rotated about the SWAPPED centre (asymmetry.py:245)
                 const int rb = 2 * cx - r, cb = 2 * cy - col;
                 fB = bgr_source(g, b, r, col);
                 if (rb >= 0 && rb < g.n && cb >= 0 && cb < g.n) fBr = bgr_source(g, b, rb, cb);
             }
-            const T xI = pm::ldg(c.img + fI);
-            const T xR = pm::ldg(c.img + (fR >= 0 ? fR : fI));
+            const T xI = ld_raw(c, r, col);
+            const T xR = ld_raw(c, rR, cR);
             const T xB = pm::ldg(c.img + (fB >= 0 ? fB : fI));
             const T xBr = pm::ldg(c.img + (fBr >= 0 ? fBr : fI));
             const double I = (double)xI - c.sky;
@@ -1890,6 +1897,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
     c.thr = p.ov.threshold_in ? p.ov.threshold_in[b] : c.sky + (p.sky_err ? p.sky_err[b] : 0.0);
     c.flags = p.flags;
     c.ar.s_top = 0; c.ar.g_top = 0; c.ar.overflow = 0;
+    c.crop = nullptr; c.crop_r0 = c.crop_c0 = 0; c.crop_h = c.crop_w = 0;
     pm_row_t row;
     row_defaults(row);
     PhaseClock& pc = c.pc;
@@ -2064,18 +2072,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         if (!done) {
             pc.lap(5);   // minapix
             row.apix_col = (double)cx; row.apix_row = (double)cy;
-            // ---- calcA x3 (main.py:470-478)
-            if (p.flags & (PM_DO_A | PM_DO_AS | PM_DO_CAS)) {
-                Arena::Mark mk = c.ar.mark();
-                unsigned* tmp = (unsigned*)c.ar.alloc((size_t)g.n * g.nw * 4);
-                AsymOut ao;
-                phase_calcA(c, cx, cy, &ao, tmp);
-                c.ar.release(mk);
-                if (p.flags & (PM_DO_A | PM_DO_CAS)) { row.A = ao.A; row.Abgr = ao.Abgr; }
-                if (p.flags & PM_DO_AS) { row.As = ao.As; row.As90 = ao.As90; }
-            }
-            pc.lap(6);   // calcA x3
-            // ---- r20, r80, C (main.py:491-492)
+            // ---- r20, r80, C (main.py:491-492) — before calcA: it is the last user of the masked window
             if (p.flags & PM_DO_CAS) {
                 RadiiOut ro;
                 phase_r20_r80(c, cx, cy, rmax, &ro);
@@ -2087,6 +2084,47 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
                 }
             }
             pc.lap(7);   // r20 / r80
+            // ---- the arena is free now: stage the central part of the image (what calcA and smoothness touch:
+            // the aperture about the image centre, its mirror image about apix, the annulus about apix) in shared memory
+            c.ar.s_top = 0; c.ar.g_top = 0;
+            c.posR = nullptr; c.mw = nullptr;
+            if (p.flags & (PM_DO_A | PM_DO_CAS | PM_DO_S)) {
+                // bounding box of {image centre, apix, mirror of the centre about apix} grown by rmax + margin
+                const int reach = (int)fmin(rmax, 4096.0) + 12;
+                int lo_r = max(0, min(min(g.half, cy), 2 * cy - g.half) - reach), hi_r = min(g.n - 1, max(max(g.half, cy), 2 * cy - g.half) + reach);
+                int lo_c = max(0, min(min(g.half, cx), 2 * cx - g.half) - reach), hi_c = min(g.n - 1, max(max(g.half, cx), 2 * cx - g.half) + reach);
+                // leave room for the scratch of calcA / smoothness (bit plane, task list, band buffers)
+                const long long room = (long long)c.ar.s_cap - (long long)(g.n * g.nw * 12 + 24 * 1024);
+                while ((long long)(hi_r - lo_r + 1) * (hi_c - lo_c + 1) * (long long)sizeof(T) > room && hi_r - lo_r > 16 && hi_c - lo_c > 16) {
+                    lo_r++; hi_r--; lo_c++; hi_c--;
+                }
+                const int ch = hi_r - lo_r + 1, cw = hi_c - lo_c + 1;
+                if (ch > 0 && cw > 0 && (long long)ch * cw * (long long)sizeof(T) <= room) {
+                    T* cb = (T*)c.ar.alloc((size_t)ch * cw * sizeof(T));
+                    for (int wr = pm::warp(); wr < ch; wr += kWarps) {
+                        const T* src = c.img + (size_t)(lo_r + wr) * g.n + lo_c;
+                        int x = pm::lane();
+                        for (; x + 96 < cw; x += 128) {       // four independent loads in flight
+                            const T a0 = pm::ldg(src + x), a1 = pm::ldg(src + x + 32), a2 = pm::ldg(src + x + 64), a3 = pm::ldg(src + x + 96);
+                            cb[wr * cw + x] = a0; cb[wr * cw + x + 32] = a1; cb[wr * cw + x + 64] = a2; cb[wr * cw + x + 96] = a3;
+                        }
+                        for (; x < cw; x += 32) cb[wr * cw + x] = pm::ldg(src + x);
+                    }
+                    pm::sync();
+                    c.crop = cb; c.crop_r0 = lo_r; c.crop_c0 = lo_c; c.crop_h = ch; c.crop_w = cw;
+                }
+            }
+            // ---- calcA x3 (main.py:470-478)
+            if (p.flags & (PM_DO_A | PM_DO_AS | PM_DO_CAS)) {
+                Arena::Mark mk = c.ar.mark();
+                unsigned* tmp = (unsigned*)c.ar.alloc((size_t)g.n * g.nw * 4);
+                AsymOut ao;
+                phase_calcA(c, cx, cy, &ao, tmp);
+                c.ar.release(mk);
+                if (p.flags & (PM_DO_A | PM_DO_CAS)) { row.A = ao.A; row.Abgr = ao.Abgr; }
+                if (p.flags & PM_DO_AS) { row.As = ao.As; row.As90 = ao.As90; }
+            }
+            pc.lap(6);   // calcA x3
             // ---- smoothness (casgm.py:276; the call is commented out at main.py:494)
             if (p.flags & PM_DO_S) {
                 const double r20 = p.ov.r20_in ? p.ov.r20_in[b] : row.r20;
