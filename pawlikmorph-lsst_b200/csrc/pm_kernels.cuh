@@ -1991,7 +1991,6 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             c.ar.release(mk_keys);    // drop skB, spB, hist
             pc.lap(3);   // sort
             phase_gini_m20_cands(c, skA, spA, st, &so);
-            if (p.flags & PM_DO_CAS) { row.gini = so.gini; row.m20 = so.m20; }
             row.n_candidates = (double)so.n_cand;
             // reverse in place: the canonical DESCENDING order (value desc, flat index desc), asymmetry.py:94-95
             for (int i = pm::tid(); i < n_g / 2; i += kThreads) {
@@ -2072,6 +2071,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         if (!done) {
             pc.lap(5);   // minapix
             row.apix_col = (double)cx; row.apix_row = (double)cy;
+            if (p.flags & PM_DO_CAS) { row.gini = so.gini; row.m20 = so.m20; }   // (not reached without a candidate)
             // ---- r20, r80, C (main.py:491-492) — before calcA: it is the last user of the masked window
             if (p.flags & PM_DO_CAS) {
                 RadiiOut ro;
