@@ -1306,10 +1306,6 @@ PM_DEV void fold_range_i(int a, int d_in, int d_out, int* b_lo_out, int* b_hi_ou
     *b_lo_out = min(b_lo, a + 1);
     *b_hi_out = min(max(b_hi, b_lo), a + 1);
 }
-PM_DEV void fold_range(int a, double r, int* b_lo_out, int* b_hi_out) {
-    const double pr = 0.5 * sqrt(2.0);
-    fold_range_i(a, d2_threshold(r - pr), d2_threshold(r + pr), b_lo_out, b_hi_out);
-}
 // cheap, conservative bounds of column a's contribution: squared-distance tests with a safety margin
 // (no float64 square roots); every possibly-cut pixel is counted with weight 0 or 1, whichever is worse
 PM_DEV int count_below(int a, int lim) {              // number of b >= 0 with a^2 + b^2 <= lim  (integers only)
