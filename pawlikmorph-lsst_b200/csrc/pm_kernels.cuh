@@ -671,7 +671,7 @@ PM_DEV double sub_coord_sq(int d, int k, int ns, int half) {
 }
 // count of sub-sample pairs (k, l) with sqrt(x_k^2 + y_l^2) <= rad, via the squared threshold `a_star`
 PM_DEV int sub_count(const double* sq, int d, int e, int ns, double a_star) {
-    int cnt = 0;
+    int cnt = 0;      // (a two-pointer sweep over the sorted coordinates measured slower: divergent, dependent loads)
     for (int k = 0; k < ns; k++) {
         const double a = sq[d * ns + k];
         for (int l = 0; l < ns; l++) cnt += (pm::dadd(a, sq[e * ns + l]) <= a_star) ? 1 : 0;
@@ -1169,19 +1169,19 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     Arena::Mark mk_t = c.ar.mark();
     const int nwords = g.n * g.nw;
     unsigned* flag = (unsigned*)c.ar.alloc((size_t)(nwords + 1) * 4);
-    unsigned short* tlist = (unsigned short*)c.ar.alloc((size_t)nwords * 2);
+    unsigned* tlist = (unsigned*)c.ar.alloc((size_t)nwords * 4);      // (row << 16) | word
     for (int t = pm::tid(); t < nwords; t += kThreads) flag[t] = c.aper[t] != 0u;
     pm::sync();
     const int ntask = (int)block_scan_excl_array(sh, flag, nwords);
     for (int t = pm::tid(); t < nwords; t += kThreads)
-        if (c.aper[t] != 0u) tlist[flag[t]] = (unsigned short)t;
+        if (c.aper[t] != 0u) { const int r = t / g.nw; tlist[flag[t]] = ((unsigned)r << 16) | (unsigned)(t - r * g.nw); }
     pm::sync();
     double s[3] = {0.0, 0.0, 0.0};           // numA denA numB
     unsigned u180 = 0, uden = 0, u90 = 0;    // shape asymmetry: integer pixel counts
-    auto contrib = [&](int task) {
-        const unsigned bits = c.aper[task];
+    auto contrib = [&](unsigned task) {
+        const int r = (int)(task >> 16), col = (int)(task & 0xffffu) * 32 + pm::lane();
+        const unsigned bits = c.aper[r * g.nw + (int)(task & 0xffffu)];
         if (!((bits >> pm::lane()) & 1u)) return;
-        const int r = task / g.nw, col = (task - r * g.nw) * 32 + pm::lane();
         // 180°: (r, c) -> (2cy - r, 2cx - c);  90° (skimage, counter-clockwise): (cy + (c - cx), cx - (r - cy))
         const int r180 = 2 * cy - r, c180 = 2 * cx - col;
         const int r90 = cy + (col - cx), c90 = cx - (r - cy);
@@ -1495,14 +1495,37 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     for (int q = 0; q < 2; q++) {
         int pos = 1;
         while (pos <= K && kfound[q] < 0) {
-            int list[kRedSlots];
-            int nl = 0, sure = -1;
-            int k = pos;
-            for (; k <= K && nl < kRedSlots; k++) {
-                const int v = verdict[q * (K + 1) + k];
-                if (v == 1) { sure = k; break; }
-                if (v == 2) list[nl++] = k;
+            // warp 0 scans the verdicts 32 at a time (ballots): undecided radii are collected until the first
+            // certain one (or kRedSlots of them); the outcome is broadcast through shared memory
+            if (pm::warp() == 0) {
+                int nl_ = 0, sure_ = -1, k_ = pos;
+                while (k_ <= K && nl_ < kRedSlots && sure_ < 0) {
+                    const int kk_ = k_ + pm::lane();
+                    const int v = kk_ <= K ? (int)verdict[q * (K + 1) + kk_] : 0;
+                    const unsigned m1 = pm::ballot(v == 1);
+                    unsigned m2 = pm::ballot(v == 2);
+                    const int f1 = m1 ? pm::ffs(m1) - 1 : 32;             // first certain radius of this group
+                    if (f1 < 32) m2 &= (1u << f1) - 1u;
+                    int consumed = 32;                                     // radii of this group dealt with
+                    while (m2 && nl_ < kRedSlots) {
+                        const int bpos = pm::ffs(m2) - 1;
+                        if (pm::lane() == 0) sh.ia[8 + nl_] = k_ + bpos;
+                        nl_++;
+                        m2 &= m2 - 1u;
+                        if (nl_ == kRedSlots) consumed = bpos + 1;
+                    }
+                    if (nl_ == kRedSlots && consumed <= f1) { k_ += consumed; break; }
+                    if (f1 < 32) { sure_ = k_ + f1; break; }
+                    k_ += 32;
+                }
+                if (pm::lane() == 0) { sh.ia[4] = nl_; sh.ia[5] = sure_; sh.ia[6] = min(k_, K + 1); }
             }
+            pm::sync();
+            int list[kRedSlots];
+            const int nl = sh.ia[4], sure = sh.ia[5];
+            const int k = sh.ia[6];
+            for (int i = 0; i < kRedSlots; i++) list[i] = i < nl ? sh.ia[8 + i] : 0;
+            pm::sync();
             if (nl > 0) {
                 if (pm::tid() == 0)
                     for (int i = 0; i < nl; i++) sh.bc[8 + i] = sh.rk[list[i]];
