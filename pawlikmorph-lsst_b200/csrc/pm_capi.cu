@@ -27,20 +27,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 pm_aperpixmap_kernel(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out, unsigned smem_bytes) {
     aperpixmap_body(n, rad, B, ns, frac, mask_out, smem_bytes);
 }
-static int g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
-static size_t g_smem_optin = 0;
-static int device_props() {
-    if (g_sm_count) return PM_OK;
+static thread_local int g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0, g_dev = -1;
+static thread_local size_t g_smem_optin = 0;
+static int device_props() {      // properties of the CURRENT device of the calling thread (re-queried when it changes)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaGetDevice: %s", cudaGetErrorString(e)); return PM_ENODEV; }
+    if (dev == g_dev && g_sm_count) return PM_OK;
     int sm = 0, maj = 0, mnr = 0, optin = 0;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&mnr, cudaDevAttrComputeCapabilityMinor, dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (sm <= 0) { snprintf(g_err, sizeof g_err, "no CUDA device"); return PM_ENODEV; }
-    g_cc_major = maj; g_cc_minor = mnr; g_smem_optin = (size_t)optin; g_sm_count = sm;
+    if (maj < 9) { snprintf(g_err, sizeof g_err, "device compute capability %d.%d: this library is built for sm_100a", maj, mnr); return PM_ENODEV; }
+    g_cc_major = maj; g_cc_minor = mnr; g_smem_optin = (size_t)optin; g_sm_count = sm; g_dev = dev;
     return PM_OK;
 }
 #else
