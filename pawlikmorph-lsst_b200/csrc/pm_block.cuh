@@ -204,28 +204,63 @@ struct Arena {
 // its long latency is hidden by batching four chunks per step; the 9-ballot multisplit it replaces cost ~6 % of
 // all executed instructions of the kernel.
 PM_DEV unsigned same_digit_mask(unsigned d, bool valid) {
-    return pm::match_any(valid ? d : 256u + (unsigned)pm::lane());
+    return pm::match_any(valid ? d : 0x10000u + (unsigned)pm::lane());
 }
 
-// ---- stable LSD radix sort of (key, value) pairs, ascending, 8 bits per pass ----------------
-// hist: kWarps * 256 counters.  Returns 0 when the sorted data ends in (keyA, valA), 1 for B.
+// ---- stable LSD radix sort of (key, value) pairs, ascending ---------------------------------------------
+// Only the bits that differ somewhere in the batch are sorted (found with one OR-reduction), in the fewest
+// passes of at most max_digit_bits (<= kMaxDigitBits) bits.  hist: kWarps << max_digit_bits counters.
+// Returns 0 when the sorted data ends in (keyA, valA), 1 for B.
+constexpr int kMaxDigitBits = 9;
+constexpr int kMaxDigits = 1 << kMaxDigitBits;
+PM_DEV int high_bit(unsigned long long v) {          // position of the highest set bit, -1 for 0
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    return hi ? 63 - pm::clz(hi) : (lo ? 31 - pm::clz(lo) : -1);
+}
 template <typename K>
 PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* valB, unsigned* hist, int n,
-                            unsigned long long* dbg = nullptr) {
-    long long tlast = dbg ? pm::clock() : 0;
-    auto lap = [&](int slot) { if (dbg) { long long now = pm::clock(); if (pm::tid() == 0) dbg[slot] += (unsigned long long)(now - tlast); tlast = now; } };
+                            int max_digit_bits = kMaxDigitBits) {
     const int w = pm::warp(), l = pm::lane(), t = pm::tid();
+    if (n <= 1) return 0;
+    // bits that differ from the first key anywhere
+    unsigned dlo = 0, dhi = 0;
+    {
+        const K k0 = keyA[0];
+        for (int i = t; i < n; i += kThreads) {
+            const unsigned long long x = (unsigned long long)(keyA[i] ^ k0);
+            dlo |= (unsigned)x; dhi |= (unsigned)(x >> 32);
+        }
+        dlo = pm::warp_or(dlo); dhi = pm::warp_or(dhi);
+        unsigned* tmp = sh.scan_tmp[red_half(sh)];
+        if (l == 0) { tmp[w] = dlo; }
+        pm::sync();
+        unsigned a = 0;
+        for (int ww = 0; ww < kWarps; ww++) a |= tmp[ww];
+        dlo = a;
+        tmp = sh.scan_tmp[red_half(sh)];
+        if (l == 0) { tmp[w] = dhi; }
+        pm::sync();
+        a = 0;
+        for (int ww = 0; ww < kWarps; ww++) a |= tmp[ww];
+        dhi = a;
+    }
+    const int nbits = high_bit(((unsigned long long)dhi << 32) | dlo) + 1;
+    if (nbits == 0) return 0;                            // all keys equal: already sorted (stable)
+    const int passes = (nbits + max_digit_bits - 1) / max_digit_bits;
+    const int db = (nbits + passes - 1) / passes;       // bits per digit, <= max_digit_bits
+    const int D = 1 << db;
+    const unsigned mask = (unsigned)D - 1u;
     int tile = (n + kWarps - 1) / kWarps;
     tile = (tile + 31) & ~31;
     const int lo = min(n, w * tile), hi = min(n, lo + tile);
     K* src = keyA; unsigned* sv = valA; K* dst = keyB; unsigned* dv = valB;
     int where = 0;
-    for (int pass = 0; pass < (int)sizeof(K); pass++) {
-        const int shift = pass * 8;
-        for (int i = t; i < kWarps * 256; i += kThreads) hist[i] = 0;
+    for (int pass = 0; pass < passes; pass++) {
+        const int shift = pass * db;
+        for (int i = t; i < kWarps * D; i += kThreads) hist[i] = 0;
         pm::sync();
-        // sweep 1: per-warp digit counts.  Four chunks per step: their loads and ballot chains are independent
-        // (the loop is a chain of dependent ALU ops otherwise); counts go in with shared-memory atomics.
+        // sweep 1: per-warp digit counts.  Four chunks per step: their loads and MATCH chains are independent
+        // (the loop is a chain of dependent ops otherwise); counts go in with shared-memory atomics.
         for (int base = lo; base < hi; base += 128) {
             unsigned d[4], m[4];
             bool valid[4];
@@ -233,33 +268,38 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
             for (int u = 0; u < 4; u++) {
                 const int i = base + 32 * u + l;
                 valid[u] = i < hi;
-                d[u] = valid[u] ? (unsigned)((src[valid[u] ? i : lo] >> shift) & 0xff) : 0u;
+                d[u] = valid[u] ? ((unsigned)(src[valid[u] ? i : lo] >> shift) & mask) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) m[u] = same_digit_mask(d[u], valid[u]);
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (valid[u] && l == pm::ffs(m[u]) - 1) pm::atomic_add(&hist[w * 256 + d[u]], (unsigned)pm::popc(m[u]));
+                if (valid[u] && l == pm::ffs(m[u]) - 1) pm::atomic_add(&hist[w * D + d[u]], (unsigned)pm::popc(m[u]));
         }
         pm::sync();
-        lap(13);
-        unsigned total = 0;
-        if (t < 256) {
-            for (int ww = 0; ww < kWarps; ww++) {
-                unsigned c = hist[ww * 256 + t];
-                hist[ww * 256 + t] = total;
-                total += c;
+        // exclusive offsets in (digit-major, warp-minor) order; a thread owns digits t, t + kThreads, ...
+        int skip = 0;
+        unsigned carry = 0;
+        for (int dbase = 0; dbase < D; dbase += kThreads) {
+            const int dg = dbase + t;
+            unsigned total = 0;
+            if (dg < D) {
+                for (int ww = 0; ww < kWarps; ww++) {
+                    const unsigned c = hist[ww * D + dg];
+                    hist[ww * D + dg] = total;
+                    total += c;
+                }
             }
+            skip |= (dg < D && total == (unsigned)n) ? 1 : 0;
+            unsigned grand;
+            const unsigned basep = block_excl_prefix_u(sh, total, &grand) + carry;
+            if (dg < D) {
+                for (int ww = 0; ww < kWarps; ww++) hist[ww * D + dg] += basep;
+            }
+            carry += grand;
         }
-        int skip = pm::sync_or(t < 256 && total == (unsigned)n);
+        skip = pm::sync_or(skip);
         if (skip) continue;  // every key has the same digit: the pass is the identity
-        unsigned grand;
-        unsigned basep = block_excl_prefix_u(sh, total, &grand);
-        if (t < 256) {
-            for (int ww = 0; ww < kWarps; ww++) hist[ww * 256 + t] += basep;
-        }
-        pm::sync();
-        lap(14);
         // sweep 2: stable scatter.  Same four-chunk batching; only the short offset read / update is ordered.
         for (int base = lo; base < hi; base += 128) {
             K k[4];
@@ -271,25 +311,24 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
                 valid[u] = i < hi;
                 k[u] = src[valid[u] ? i : lo];
                 v[u] = sv[valid[u] ? i : lo];
-                d[u] = valid[u] ? (unsigned)((k[u] >> shift) & 0xff) : 0u;
+                d[u] = valid[u] ? ((unsigned)(k[u] >> shift) & mask) : 0u;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) m[u] = same_digit_mask(d[u], valid[u]);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 unsigned pos = 0;
-                if (valid[u]) pos = hist[w * 256 + d[u]] + (unsigned)pm::popc(m[u] & lt_mask());
+                if (valid[u]) pos = hist[w * D + d[u]] + (unsigned)pm::popc(m[u] & lt_mask());
                 pm::syncwarp();
                 if (valid[u]) {
                     dst[pos] = k[u];
                     dv[pos] = v[u];
-                    if (l == pm::ffs(m[u]) - 1) hist[w * 256 + d[u]] += (unsigned)pm::popc(m[u]);
+                    if (l == pm::ffs(m[u]) - 1) hist[w * D + d[u]] += (unsigned)pm::popc(m[u]);
                 }
                 pm::syncwarp();
             }
         }
         pm::sync();
-        lap(15);
         K* tk = src; src = dst; dst = tk;
         unsigned* tv = sv; sv = dv; dv = tv;
         where ^= 1;

@@ -1969,7 +1969,15 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         Arena::Mark mk_keys = c.ar.mark();
         K* skB = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
         unsigned* spB = (unsigned*)c.ar.alloc((size_t)n_g * 4);
-        unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+        // 9-bit digits (3 passes for typical float keys) when their histogram fits shared memory, else 8-bit digits
+        int sort_db = kMaxDigitBits;
+        Arena::Mark mk_hist = c.ar.mark();
+        unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * kMaxDigits * 4);
+        if (!c.ar.in_smem(hist)) {
+            c.ar.release(mk_hist);
+            sort_db = 8;
+            hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+        }
         const unsigned* cand = spA;
         if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }   // workspace contract violated
         SegStats st;
@@ -2002,7 +2010,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             // ---- sort ascending by (value, flat index); the reverse is the canonical descending order
             for (int i = pm::tid(); i < n_g; i += kThreads) spA[i] = c.posR[i];
             pm::sync();
-            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g);
+            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db);
             if (where) {
                 for (int i = pm::tid(); i < n_g; i += kThreads) { spA[i] = spB[i]; skA[i] = skB[i]; }
                 pm::sync();
