@@ -1836,7 +1836,22 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
     // ---- background box search (casgm.py:367-398); one candidate position per warp per round
     // positions are visited in the order (size 32: y = 0, 2, ..; x = 0, 2, ..), then size 16, then 8.
     int bx = 0, by = 0, bsz = 32;
+    // the very first box (size 32 at the origin) is accepted almost always: test it with the whole block first
+    bool first_ok = false;
     {
+        double bs = 0.0;
+        for (int i = pm::tid(); i < 32 * 32; i += kThreads) {
+            const int r = i >> 5, col = i & 31;
+            if (r < g.n && col < g.n) {
+                double v = bit_at(c.seg, g.nw, r, col) ? 0.0 : (ld(c, r, col) - c.sky);
+                if (v == 0.0) v = -99.0;
+                bs += v;
+            }
+        }
+        bs = block_sum1(sh, bs);
+        first_ok = fabs(sky_test) > fabs(bs / 1024.0);
+    }
+    if (!first_ok) {
         int size = 32;
         for (;;) {
             // candidate grid for this size: x in {0, 2, ..} with x < W - size, y likewise; (0, 0) always
