@@ -1632,7 +1632,7 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
 template <int K, typename T_> PM_DEV double strided_sum(const T_* p, int stride, double sky) {
     T_ x[K];
 #pragma unroll
-    for (int i = 0; i < K; i++) x[i] = pm::ldg(p + (size_t)i * stride);
+    for (int i = 0; i < K; i++) x[i] = p[(size_t)i * stride];      // generic load: global image or shared-memory crop
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < K; i++) s += (double)x[i] - sky;
@@ -1654,6 +1654,7 @@ PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int c
     const int R = max(1, min(2 * kWarps, vcap / E));
     const double inv = 1.0 / ((double)k * (double)k);
     const bool cols_inside = (ca - h >= clo) && (cb - 1 - h + k - 1 < clo + clen);     // no column reflection needed
+    const bool crop_cols = cols_inside && c.crop != nullptr && (ca - h >= c.crop_c0) && (cb - 1 - h + k - 1 < c.crop_c0 + c.crop_w);
     for (int band = ra; band < rb; band += R) {
         const int rows = min(R, rb - band);
         // stage 1: vertical window sums, one row of the band per warp, lanes along the columns (coalesced)
@@ -1664,16 +1665,20 @@ PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int c
                 const int cc = cols_inside ? ca - h + e : clo + refl(ca - clo - h + e, clen);
                 double sum = 0.0;
                 if (rows_inside && k <= 8) {
-                    const T_* p = c.img + (size_t)(r - h) * n + cc;
+                    // from the shared-memory crop when the window column lies inside it, else from global memory
+                    const bool in_crop = crop_cols && (r - h >= c.crop_r0) && (r - h + k - 1 < c.crop_r0 + c.crop_h);
+                    const T_* p = in_crop ? c.crop + (size_t)(r - h - c.crop_r0) * c.crop_w + (cc - c.crop_c0)
+                                          : c.img + (size_t)(r - h) * n + cc;
+                    const int stride = in_crop ? c.crop_w : n;
                     switch (k) {
-                        case 1: sum = strided_sum<1>(p, n, c.sky); break;
-                        case 2: sum = strided_sum<2>(p, n, c.sky); break;
-                        case 3: sum = strided_sum<3>(p, n, c.sky); break;
-                        case 4: sum = strided_sum<4>(p, n, c.sky); break;
-                        case 5: sum = strided_sum<5>(p, n, c.sky); break;
-                        case 6: sum = strided_sum<6>(p, n, c.sky); break;
-                        case 7: sum = strided_sum<7>(p, n, c.sky); break;
-                        default: sum = strided_sum<8>(p, n, c.sky); break;
+                        case 1: sum = strided_sum<1>(p, stride, c.sky); break;
+                        case 2: sum = strided_sum<2>(p, stride, c.sky); break;
+                        case 3: sum = strided_sum<3>(p, stride, c.sky); break;
+                        case 4: sum = strided_sum<4>(p, stride, c.sky); break;
+                        case 5: sum = strided_sum<5>(p, stride, c.sky); break;
+                        case 6: sum = strided_sum<6>(p, stride, c.sky); break;
+                        case 7: sum = strided_sum<7>(p, stride, c.sky); break;
+                        default: sum = strided_sum<8>(p, stride, c.sky); break;
                     }
                 } else {
                     int dr = 0;
@@ -1803,8 +1808,11 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
             const int h = k / 2;
             double bs = 0.0;
             if (k <= 8 && r - h >= 0 && r - h + k - 1 < g.n && col - h >= 0 && col - h + k - 1 < g.n) {
+                const bool in_crop = c.crop != nullptr && r - h >= c.crop_r0 && r - h + k - 1 < c.crop_r0 + c.crop_h &&
+                                     col - h >= c.crop_c0 && col - h + k - 1 < c.crop_c0 + c.crop_w;
                 for (int dr = 0; dr < k; dr++) {
-                    const T_* p = c.img + (size_t)(r - h + dr) * g.n + (col - h);
+                    const T_* p = in_crop ? c.crop + (size_t)(r - h + dr - c.crop_r0) * c.crop_w + (col - h - c.crop_c0)
+                                          : c.img + (size_t)(r - h + dr) * g.n + (col - h);
                     double rs;
                     switch (k) {
                         case 1: rs = strided_sum<1>(p, 1, c.sky); break;
