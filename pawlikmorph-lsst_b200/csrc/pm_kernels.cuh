@@ -1638,79 +1638,101 @@ template <int K, typename T_> PM_DEV double strided_sum(const T_* p, int stride,
     for (int i = 0; i < K; i++) s += (double)x[i] - sky;
     return s;
 }
-template <int K> PM_DEV double run_sum(const double* v) {
-    double s = 0.0;
+
+// One band of rows of box_means() without any reflection (the common case), compile-time window size K.  Every warp
+// works on TWO rows of the band at once so that two independent load / add chains are in flight per lane.
+template <int K, typename T_, typename W_, typename F>
+PM_DEV void box_band_fast(const Ctx<T_>& c, int band, int rows, int ca, int W, int E, double* vbuf, double inv, W_& want, F& fn) {
+    const int h = K / 2, n = c.g.n;
+    const int c_first = ca - h;                                   // image column of vbuf column 0
+    const bool in_crop = c.crop != nullptr && c_first >= c.crop_c0 && c_first + E <= c.crop_c0 + c.crop_w &&
+                         band - h >= c.crop_r0 && band + rows - 1 - h + K - 1 < c.crop_r0 + c.crop_h;
+    const T_* base = in_crop ? c.crop + (size_t)(band - h - c.crop_r0) * c.crop_w + (c_first - c.crop_c0)
+                             : c.img + (size_t)(band - h) * n + c_first;
+    const int stride = in_crop ? c.crop_w : n;
+    for (int q0 = pm::warp(); q0 < rows; q0 += 2 * kWarps) {
+        const int q1 = q0 + kWarps;
+        const bool two = q1 < rows;
+        const T_* p0 = base + (size_t)q0 * stride;
+        const T_* p1 = base + (size_t)(two ? q1 : q0) * stride;
+        for (int e = pm::lane(); e < E; e += 32) {
+            T_ x0[K], x1[K];
 #pragma unroll
-    for (int i = 0; i < K; i++) s += v[i];
-    return s;
+            for (int i = 0; i < K; i++) { x0[i] = p0[(size_t)i * stride + e]; x1[i] = p1[(size_t)i * stride + e]; }
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; i++) { s0 += (double)x0[i] - c.sky; s1 += (double)x1[i] - c.sky; }
+            vbuf[q0 * E + e] = s0;
+            if (two) vbuf[q1 * E + e] = s1;
+        }
+    }
+    pm::sync();
+    for (int q0 = pm::warp(); q0 < rows; q0 += 2 * kWarps) {
+        const int q1 = q0 + kWarps;
+        const bool two = q1 < rows;
+        for (int x = pm::lane(); x < W; x += 32) {
+            const bool w0 = want(band + q0, ca + x), w1 = two && want(band + q1, ca + x);
+            if (!w0 && !w1) continue;
+            const double* v0 = vbuf + q0 * E + x;
+            const double* v1 = vbuf + (two ? q1 : q0) * E + x;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; i++) { s0 += v0[i]; s1 += v1[i]; }
+            if (w0) fn(band + q0, ca + x, s0 * inv);
+            if (w1) fn(band + q1, ca + x, s1 * inv);
+        }
+    }
+    pm::sync();
 }
 
 template <typename T_, typename W_, typename F>
 PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int clen, int ra, int rb, int ca, int cb,
                       double* vbuf, int vcap, W_ want, F fn) {
-    const int h = k / 2, n = c.g.n;
+    const int h = k / 2;
     const int W = cb - ca, E = W + k - 1;
     if (W <= 0 || rb <= ra) return;
     const int R = max(1, min(2 * kWarps, vcap / E));
     const double inv = 1.0 / ((double)k * (double)k);
     const bool cols_inside = (ca - h >= clo) && (cb - 1 - h + k - 1 < clo + clen);     // no column reflection needed
-    const bool crop_cols = cols_inside && c.crop != nullptr && (ca - h >= c.crop_c0) && (cb - 1 - h + k - 1 < c.crop_c0 + c.crop_w);
     for (int band = ra; band < rb; band += R) {
         const int rows = min(R, rb - band);
-        // stage 1: vertical window sums, one row of the band per warp, lanes along the columns (coalesced)
+        if (cols_inside && k <= 8 && band - h >= rlo && band + rows - 1 - h + k - 1 < rlo + rlen) {
+            switch (k) {
+                case 1: box_band_fast<1>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                case 2: box_band_fast<2>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                case 3: box_band_fast<3>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                case 4: box_band_fast<4>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                case 5: box_band_fast<5>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                case 6: box_band_fast<6>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                case 7: box_band_fast<7>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+                default: box_band_fast<8>(c, band, rows, ca, W, E, vbuf, inv, want, fn); break;
+            }
+            continue;
+        }
+        // general band: reflection at the borders of the sub-image and / or a large window
         for (int q = pm::warp(); q < rows; q += kWarps) {
             const int r = band + q;
-            const bool rows_inside = (r - h >= rlo) && (r - h + k - 1 < rlo + rlen);      // no row reflection needed
             for (int e = pm::lane(); e < E; e += 32) {
                 const int cc = cols_inside ? ca - h + e : clo + refl(ca - clo - h + e, clen);
                 double sum = 0.0;
-                if (rows_inside && k <= 8) {
-                    // from the shared-memory crop when the window column lies inside it, else from global memory
-                    const bool in_crop = crop_cols && (r - h >= c.crop_r0) && (r - h + k - 1 < c.crop_r0 + c.crop_h);
-                    const T_* p = in_crop ? c.crop + (size_t)(r - h - c.crop_r0) * c.crop_w + (cc - c.crop_c0)
-                                          : c.img + (size_t)(r - h) * n + cc;
-                    const int stride = in_crop ? c.crop_w : n;
-                    switch (k) {
-                        case 1: sum = strided_sum<1>(p, stride, c.sky); break;
-                        case 2: sum = strided_sum<2>(p, stride, c.sky); break;
-                        case 3: sum = strided_sum<3>(p, stride, c.sky); break;
-                        case 4: sum = strided_sum<4>(p, stride, c.sky); break;
-                        case 5: sum = strided_sum<5>(p, stride, c.sky); break;
-                        case 6: sum = strided_sum<6>(p, stride, c.sky); break;
-                        case 7: sum = strided_sum<7>(p, stride, c.sky); break;
-                        default: sum = strided_sum<8>(p, stride, c.sky); break;
-                    }
-                } else {
-                    int dr = 0;
-                    for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
-                        const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
-                                     x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
-                        sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
-                    }
-                    for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
+                int dr = 0;
+                for (; dr + 3 < k; dr += 4) {          // four independent loads in flight
+                    const double x0 = ld(c, rlo + refl(r - rlo - h + dr, rlen), cc), x1 = ld(c, rlo + refl(r - rlo - h + dr + 1, rlen), cc),
+                                 x2 = ld(c, rlo + refl(r - rlo - h + dr + 2, rlen), cc), x3 = ld(c, rlo + refl(r - rlo - h + dr + 3, rlen), cc);
+                    sum += x0 - c.sky; sum += x1 - c.sky; sum += x2 - c.sky; sum += x3 - c.sky;
                 }
+                for (; dr < k; dr++) sum += ld(c, rlo + refl(r - rlo - h + dr, rlen), cc) - c.sky;
                 vbuf[q * E + e] = sum;
             }
         }
         pm::sync();
-        // stage 2: horizontal sums for the pixels the caller wants
         for (int q = pm::warp(); q < rows; q += kWarps) {
             const int r = band + q;
             for (int x = pm::lane(); x < W; x += 32) {
                 if (!want(r, ca + x)) continue;
                 const double* v = vbuf + q * E + x;
-                double sum;
-                switch (k) {
-                    case 1: sum = run_sum<1>(v); break;
-                    case 2: sum = run_sum<2>(v); break;
-                    case 3: sum = run_sum<3>(v); break;
-                    case 4: sum = run_sum<4>(v); break;
-                    case 5: sum = run_sum<5>(v); break;
-                    case 6: sum = run_sum<6>(v); break;
-                    case 7: sum = run_sum<7>(v); break;
-                    case 8: sum = run_sum<8>(v); break;
-                    default: sum = 0.0; for (int dc = 0; dc < k; dc++) sum += v[dc]; break;
-                }
+                double sum = 0.0;
+                for (int dc = 0; dc < k; dc++) sum += v[dc];
                 fn(r, ca + x, sum * inv);
             }
         }
