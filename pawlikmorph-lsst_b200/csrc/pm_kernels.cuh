@@ -1263,21 +1263,37 @@ template <typename T_> PM_DEV void build_fold(Ctx<T_>& c, int cx, int cy, Fold& 
     const Geo& g = c.g;
     const int A = f.A;
     const int entries = (A + 1) * (A + 2) / 2;
-    for (int e = pm::tid(); e < entries; e += kThreads) {
-        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);     // invert the triangular index
+    // masked value at offset (dr, dc) from the centre; an unconditional (clamped) load so that the 8 mirror-image
+    // loads of an entry — and those of a second entry — are all in flight together
+    auto fetch = [&](int dr, int dc, bool valid) -> double {
+        const int r = cy + dr, col = cx + dc;
+        const bool ok = valid && r >= c.r0 && r <= c.r1 && col >= c.c0 && col <= c.c1;    // the window lies inside the image
+        const T_ w = c.mw[ok ? (r - c.r0) * c.bw + (col - c.c0) : 0];
+        return (ok && w == w) ? (double)w - c.sky : 0.0;
+    };
+    auto entry_ab = [&](int e, int& a, int& b) {
+        a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);     // invert the triangular index
         while (tri(a + 1, 0) <= e) a++;
         while (tri(a, 0) > e) a--;
-        const int b = e - tri(a, 0);
-        double s = 0.0;
-        auto at = [&](int dr, int dc) {
-            const int r = cy + dr, col = cx + dc;
-            if (r >= 0 && r < g.n && col >= 0 && col < g.n) s += mval(c, r, col);
-        };
-        if (a == 0) at(0, 0);
-        else if (b == 0) { at(a, 0); at(-a, 0); at(0, a); at(0, -a); }
-        else if (a == b) { at(a, a); at(a, -a); at(-a, a); at(-a, -a); }
-        else { at(a, b); at(a, -b); at(-a, b); at(-a, -b); at(b, a); at(b, -a); at(-b, a); at(-b, -a); }
-        f.T[e] = s;
+        b = e - tri(a, 0);
+    };
+    // the (up to 8) mirror images of (a, b), duplicates masked out: a == b, b == 0, a == 0
+    auto entry_sum = [&](int a, int b) -> double {
+        const bool nz_a = a > 0, nz_b = b > 0, off = a != b;
+        const double v0 = fetch(a, b, true), v1 = fetch(a, -b, nz_b), v2 = fetch(-a, b, nz_a), v3 = fetch(-a, -b, nz_a && nz_b);
+        const double v4 = fetch(b, a, off), v5 = fetch(b, -a, off && nz_a), v6 = fetch(-b, a, off && nz_b), v7 = fetch(-b, -a, off && nz_b);
+        double sum = v0;
+        sum += v1; sum += v2; sum += v3; sum += v4; sum += v5; sum += v6; sum += v7;
+        return sum;
+    };
+    for (int e0 = pm::tid(); e0 < entries; e0 += 2 * kThreads) {
+        const int e1 = e0 + kThreads;
+        int a0, b0, a1 = 0, b1 = 0;
+        entry_ab(e0, a0, b0);
+        if (e1 < entries) entry_ab(e1, a1, b1);
+        const double s0 = entry_sum(a0, b0), s1 = entry_sum(a1, b1);
+        f.T[e0] = s0;
+        if (e1 < entries) f.T[e1] = s1;
     }
     pm::sync();
     double asum = 0.0;
@@ -1311,22 +1327,12 @@ PM_DEV void fold_range_i(int a, int d_in, int d_out, int* b_lo_out, int* b_hi_ou
 PM_DEV int count_below(int a, int lim) {              // number of b >= 0 with a^2 + b^2 <= lim  (integers only)
     const int t = lim - a * a;
     if (t < 0) return 0;
-    int b = (int)sqrtf((float)t);
-    while (b * b > t) b--;
-    while ((b + 1) * (b + 1) <= t) b++;
+    int b = (int)sqrtf((float)t);                      // exact to +-1 for t < 2^24 * 4 ...
+    b -= (b * b > t) ? 1 : 0;                          // ... so one correction step each way is enough,
+    b += ((b + 1) * (b + 1) <= t) ? 1 : 0;             //     and a second one covers the large-t rounding
+    b -= (b * b > t) ? 1 : 0;
+    b += ((b + 1) * (b + 1) <= t) ? 1 : 0;
     return b + 1;
-}
-// lim_in: squared distances <= lim_in are certainly inside; > lim_out certainly outside
-PM_DEV void fold_column_bounds(const Fold& f, int a, int lim_in, int lim_out, double* lo, double* hi) {
-    const int b_in = min(count_below(a, lim_in), a + 1);                         // certainly inside
-    const int b_out = min(max(count_below(a, lim_out), b_in), a + 1);           // from here on certainly outside
-    const double s = b_in > 0 ? f.P[tri(a, b_in - 1)] : 0.0;
-    double l = s, h = s;
-    for (int b = b_in; b < b_out; b++) {
-        const double t = f.T[tri(a, b)];
-        if (t < 0.0) l += t; else h += t;
-    }
-    *lo = l; *hi = h;
 }
 // exact F(r) for nr <= kRedSlots radii; results in acc[0..nr) of every thread.  Pass 1: one (radius, column) item per
 // thread finds the cut range and adds the fully-inside prefix; pass 2: the cut pixels of all columns are
@@ -1373,20 +1379,35 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
 // d2 is certainly inside when d2 <= floor((r - pr - 1e-9)^2) - 1 and certainly outside when d2 > ceil((r + pr + 1e-9)^2).
 PM_DEV void eval_flux_bounds(Sh& sh, const Fold& f, int K) {
     const double pr = 0.5 * sqrt(2.0);
-    for (int k = 1 + pm::warp(); k <= K; k += kWarps) {
-        const double r = sh.rk[k];
-        const double rin = r - pr - 1e-9, rout = r + pr + 1e-9;
-        const int lim_in = rin > 0.0 ? (int)floor(rin * rin) - 1 : -1;
-        const int lim_out = (int)ceil(rout * rout);
-        double lo = 0.0, hi = 0.0;
-        const int amax = min(f.A, (int)(r + 2.0));
+    // two radii per warp-step: the two column scans are independent chains (ILP)
+    for (int k0 = 1 + pm::warp(); k0 <= K; k0 += 2 * kWarps) {
+        const int k1 = k0 + kWarps;
+        const bool two = k1 <= K;
+        const double r0 = sh.rk[k0], r1 = sh.rk[two ? k1 : k0];
+        const double in0 = r0 - pr - 1e-9, out0 = r0 + pr + 1e-9, in1 = r1 - pr - 1e-9, out1 = r1 + pr + 1e-9;
+        const int li0 = in0 > 0.0 ? (int)floor(in0 * in0) - 1 : -1, lo0_ = (int)ceil(out0 * out0);
+        const int li1 = in1 > 0.0 ? (int)floor(in1 * in1) - 1 : -1, lo1_ = (int)ceil(out1 * out1);
+        double lo0 = 0.0, hi0 = 0.0, lo1 = 0.0, hi1 = 0.0;
+        const int amax = min(f.A, (int)(fmax(r0, r1) + 2.0));
         for (int a = pm::lane(); a <= amax; a += 32) {
-            double l, h;
-            fold_column_bounds(f, a, lim_in, lim_out, &l, &h);
-            lo += l; hi += h;
+            const int bi0 = min(count_below(a, li0), a + 1), bo0 = min(max(count_below(a, lo0_), bi0), a + 1);
+            const int bi1 = min(count_below(a, li1), a + 1), bo1 = min(max(count_below(a, lo1_), bi1), a + 1);
+            const double s0 = bi0 > 0 ? f.P[tri(a, bi0 - 1)] : 0.0, s1 = bi1 > 0 ? f.P[tri(a, bi1 - 1)] : 0.0;
+            double l0 = s0, h0 = s0, l1 = s1, h1 = s1;
+            const int steps = max(bo0 - bi0, bo1 - bi1);
+            for (int i = 0; i < steps; i++) {
+                const bool p0 = bi0 + i < bo0, p1 = bi1 + i < bo1;
+                const double t0 = p0 ? f.T[tri(a, bi0 + i)] : 0.0, t1 = p1 ? f.T[tri(a, bi1 + i)] : 0.0;
+                if (t0 < 0.0) l0 += t0; else h0 += t0;
+                if (t1 < 0.0) l1 += t1; else h1 += t1;
+            }
+            lo0 += l0; hi0 += h0; lo1 += l1; hi1 += h1;
         }
-        lo = pm::warp_sum(lo); hi = pm::warp_sum(hi);
-        if (pm::lane() == 0) { sh.fk[k] = lo; sh.fh[k] = hi; }
+        lo0 = pm::warp_sum(lo0); hi0 = pm::warp_sum(hi0); lo1 = pm::warp_sum(lo1); hi1 = pm::warp_sum(hi1);
+        if (pm::lane() == 0) {
+            sh.fk[k0] = lo0; sh.fh[k0] = hi0;
+            if (two) { sh.fk[k1] = lo1; sh.fh[k1] = hi1; }
+        }
     }
     pm::sync();
 }
