@@ -211,15 +211,17 @@ def run_ours(args):
     if args.phases and rank == 0:
         # tuning aid: per-phase clock64() cycles summed over the CTAs of one extra (untimed) step
         names = ("pixelmap", "list+window", "rmax+aperture", "sort", "gini/m20/cands", "minapix", "calcA:loop", "r20:brentq",
-                 "S:bkg", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "S:interior", "S:cut", "S:boxsearch")
-        buf = torch.zeros((592, 16), dtype=torch.int64, device=dev)
+                 "S:bkg", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "S:interior", "S:cut", "S:boxsearch",
+                 "sort:bits", "sort:count", "sort:scan", "sort:scatter", "minapix:first", "minapix:stage", "minapix:compact", "p23")
+        names += tuple(f"#alive@stage{k}" for k in range(8))
+        buf = torch.zeros((592, 32), dtype=torch.int64, device=dev)
         pm._lib.lib().pm_debug_phase_cycles(buf.data_ptr())
         step()
         torch.cuda.synchronize(dev)
         pm._lib.lib().pm_debug_phase_cycles(None)
-        cyc = buf.sum(dim=0).cpu().numpy()[:16].astype(float)
+        cyc = buf.sum(dim=0).cpu().numpy().astype(float)
         tot = cyc.sum()
-        print("phase cycles per galaxy: " + ", ".join(f"{nm} {c / B:.0f} ({100 * c / tot:.1f}%)" for nm, c in zip(names, cyc))
+        print("phase cycles per galaxy: " + ", ".join(f"{nm} {c / B:.0f} ({100 * c / tot:.1f}%)" for nm, c in zip(names, cyc) if c > 0)
               + f"; total {tot / B:.0f}", file=sys.stderr, flush=True)
     sampler = ClockSampler(local)
     if rank == 0:

@@ -17,7 +17,7 @@ namespace pmk {
 #define PM_MIN_CTAS 2
 #endif
 constexpr int kThreads = PM_THREADS;
-static_assert(kThreads >= 256 && kThreads % 32 == 0, "the radix sort needs >= 256 threads");
+static_assert(kThreads >= 128 && kThreads % 32 == 0, "whole warps, at least four");
 constexpr int kWarps = kThreads / 32;
 constexpr int kRedSlots = 8;
 
@@ -217,9 +217,10 @@ PM_DEV int high_bit(unsigned long long v) {          // position of the highest 
     const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
     return hi ? 63 - pm::clz(hi) : (lo ? 31 - pm::clz(lo) : -1);
 }
-template <typename K>
+struct NoLap { PM_DEV void operator()(int) const {} };     // lap(phase): optional tuning probe
+template <typename K, typename Lap = NoLap>
 PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* valB, unsigned* hist, int n,
-                            int max_digit_bits = kMaxDigitBits) {
+                            int max_digit_bits = kMaxDigitBits, Lap lap = Lap()) {
     const int w = pm::warp(), l = pm::lane(), t = pm::tid();
     if (n <= 1) return 0;
     // bits that differ from the first key anywhere
@@ -244,6 +245,7 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
         for (int ww = 0; ww < kWarps; ww++) a |= tmp[ww];
         dhi = a;
     }
+    lap(16);
     const int nbits = high_bit(((unsigned long long)dhi << 32) | dlo) + 1;
     if (nbits == 0) return 0;                            // all keys equal: already sorted (stable)
     const int passes = (nbits + max_digit_bits - 1) / max_digit_bits;
@@ -277,6 +279,7 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
                 if (valid[u] && l == pm::ffs(m[u]) - 1) pm::atomic_add(&hist[w * D + d[u]], (unsigned)pm::popc(m[u]));
         }
         pm::sync();
+        lap(17);
         // exclusive offsets in (digit-major, warp-minor) order; a thread owns digits t, t + kThreads, ...
         int skip = 0;
         unsigned carry = 0;
@@ -299,6 +302,7 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
             carry += grand;
         }
         skip = pm::sync_or(skip);
+        lap(18);
         if (skip) continue;  // every key has the same digit: the pass is the identity
         // sweep 2: stable scatter.  Same four-chunk batching; only the short offset read / update is ordered.
         for (int base = lo; base < hi; base += 128) {
@@ -329,6 +333,7 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
             }
         }
         pm::sync();
+        lap(19);
         K* tk = src; src = dst; dst = tk;
         unsigned* tv = sv; sv = dv; dv = tv;
         where ^= 1;

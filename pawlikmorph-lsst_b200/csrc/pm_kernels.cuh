@@ -111,6 +111,7 @@ template <> struct KeyT<double> { typedef uint64_t type; };
 PM_DEV float nan_of(float) { return pm::bits2f(0x7fc00000u); }
 PM_DEV double nan_of(double) { return pm::bits2d(0x7ff8000000000000ll); }
 
+constexpr int kPhaseSlots = 32;      // per CTA; 0..15 phases of analyse_one, 16.. sub-phases and counters (bench.py --phases)
 struct PhaseClock {
     unsigned long long* slot;
     long long last;
@@ -121,6 +122,7 @@ struct PhaseClock {
         if (pm::tid() == 0) slot[phase] += (unsigned long long)(now - last);
         last = now;
     }
+    PM_DEV void count(int phase, int v) { if (slot && pm::tid() == 0) slot[phase] += (unsigned long long)v; }
 };
 // Per-cutout context (registers / local; identical in every thread) ---------------------------------
 template <typename T> struct Ctx {
@@ -1002,6 +1004,7 @@ PM_DEV void phase_minapix_pruned(Ctx<T>& c, const unsigned* cand, int n_cand, do
         }
         pm::sync();
     }
+    c.pc.lap(20);   // (minapix: first group)
     double astar = 1.7976931348623157e308 * 2.0;
     bool any_nan = false;
     for (int k = 0; k < min(kCandBlock, n_cand); k++) {
@@ -1025,6 +1028,8 @@ PM_DEV void phase_minapix_pruned(Ctx<T>& c, const unsigned* cand, int n_cand, do
             minapix_group(c, cand, cidx, lo + pm::lane(), hi, 32, parts + 8 * kWarps + 8 * grp);
         }
         pm::sync();
+        c.pc.lap(21);   // (minapix: stage sums)
+        c.pc.count(24 + st, n_alive);
         // accumulate, decide, compact the survivors (order preserved)
         for (int k = pm::tid(); k < n_alive; k += kThreads) {
             const int ci = alive[k];
@@ -1041,6 +1046,7 @@ PM_DEV void phase_minapix_pruned(Ctx<T>& c, const unsigned* cand, int n_cand, do
         pm::sync();
         { int* t = alive; alive = alive2; alive2 = t; }
         n_alive = keep;
+        c.pc.lap(22);   // (minapix: decide + compact)
     }
     // ---- first minimum over the completely evaluated candidates (dropped ones are strictly larger than a*)
     double amin = 1.7976931348623157e308 * 2.0;
@@ -1986,7 +1992,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
     pm_row_t row;
     row_defaults(row);
     PhaseClock& pc = c.pc;
-    pc.start(p.phase_cycles ? p.phase_cycles + (size_t)pm::block() * 16 : nullptr);
+    pc.start(p.phase_cycles ? p.phase_cycles + (size_t)pm::block() * kPhaseSlots : nullptr);
     uint8_t* seg_out = p.out.segmap_out ? p.out.segmap_out + (size_t)b * plane_elems : nullptr;
     int32_t* sidx_out = p.out.sorted_idx_out ? p.out.sorted_idx_out + (size_t)b * plane_elems : nullptr;
 
@@ -2076,7 +2082,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             // ---- sort ascending by (value, flat index); the reverse is the canonical descending order
             for (int i = pm::tid(); i < n_g; i += kThreads) spA[i] = c.posR[i];
             pm::sync();
-            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db);
+            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db, [&](int ph) { pc.lap(ph); });
             if (where) {
                 for (int i = pm::tid(); i < n_g; i += kThreads) { spA[i] = spB[i]; skA[i] = skB[i]; }
                 pm::sync();
