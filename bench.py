@@ -214,7 +214,8 @@ def run_ours(args):
                  "S:bkg", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "S:interior", "S:cut", "S:boxsearch",
                  "sort:bits", "sort:count", "sort:scan", "sort:scatter", "minapix:first", "minapix:stage", "minapix:compact", "p23")
         names += tuple(f"#alive@stage{k}" for k in range(8))
-        buf = torch.zeros((592, 32), dtype=torch.int64, device=dev)
+        names += ("gini:sums", "gini:thresh", "gini:moments", "gini:cands", "gini:reverse", "list:rowscan", "list:fill", "r20:total", "rmax2", "ef:thr", "ef:items", "ef:scan", "ef:overlap", "ef:sum", "r20:rk", "q47")
+        buf = torch.zeros((592, 48), dtype=torch.int64, device=dev)
         pm._lib.lib().pm_debug_phase_cycles(buf.data_ptr())
         step()
         torch.cuda.synchronize(dev)

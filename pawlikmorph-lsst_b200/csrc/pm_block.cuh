@@ -357,74 +357,52 @@ PM_DEV double area_arc(double x1, double y1, double x2, double y2, double r) {
 PM_DEV double area_tri(double x1, double y1, double x2, double y2, double x3, double y3) {
     return 0.5 * fabs(x1 * (y2 - y3) + x2 * (y3 - y1) + x3 * (y1 - y2));
 }
-// rectangle in the first quadrant (0 <= xmin, 0 <= ymin)
-PM_DEV_NOINLINE double overlap_core(double xmin, double ymin, double xmax, double ymax, double r) {
+// rectangle in the first quadrant (0 <= xmin, 0 <= ymin).  photutils (circular_overlap_core) branches on which
+// corners lie inside the circle; here the four corner configurations share ONE instruction stream — the two
+// intersection points, the arc segment and the (up to two) triangles are formed from selected operands — so that
+// the lanes of a warp, which hold different pixels, do not serialise four copies of the sqrt / asin chain
+// (measured: 1915 -> ~500 cycles per call, profiles/microbench).  Per configuration the arithmetic is photutils'.
+PM_DEV double overlap_core(double xmin, double ymin, double xmax, double ymax, double r) {
     const double r2 = r * r;
-    if (xmin * xmin + ymin * ymin > r2) return 0.0;
-    if (xmax * xmax + ymax * ymax < r2) return (xmax - xmin) * (ymax - ymin);
+    const double full = (xmax - xmin) * (ymax - ymin);
+    const bool none = xmin * xmin + ymin * ymin > r2, all = xmax * xmax + ymax * ymax < r2;
     // corner tests on squared distances (photutils compares the square roots: same decisions up to rounding at
     // the exact boundary, where the area formulas agree anyway)
     const bool in1 = xmax * xmax + ymin * ymin < r2, in2 = xmin * xmin + ymax * ymax < r2;
-    if (in1 && in2) {
-        double x1 = fsqrt0(r2 - ymax * ymax), y1 = ymax;
-        double x2 = xmax, y2 = fsqrt0(r2 - xmax * xmax);
-        return (xmax - xmin) * (ymax - ymin) - area_tri(x1, y1, x2, y2, xmax, ymax) + area_arc(x1, y1, x2, y2, r);
-    }
-    if (in1) {
-        double x1 = xmin, y1 = fsqrt0(r2 - xmin * xmin);
-        double x2 = xmax, y2 = fsqrt0(r2 - xmax * xmax);
-        return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, x1, ymin, xmax, ymin) + area_tri(x1, y1, x2, ymin, x2, y2);
-    }
-    if (in2) {
-        double x1 = fsqrt0(r2 - ymin * ymin), y1 = ymin;
-        double x2 = fsqrt0(r2 - ymax * ymax), y2 = ymax;
-        return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, xmin, y1, xmin, ymax) + area_tri(x1, y1, xmin, y2, x2, y2);
-    }
-    double x1 = fsqrt0(r2 - ymin * ymin), y1 = ymin;
-    double x2 = xmin, y2 = fsqrt0(r2 - xmin * xmin);
-    return area_arc(x1, y1, x2, y2, r) + area_tri(x1, y1, x2, y2, xmin, ymin);
+    const bool cA = in1 && in2, cB = in1 && !in2, cC = !in1 && in2;       // else: neither far corner inside
+    // the two edges the circle crosses: P1 on (A: top, B: left, C / D: bottom), P2 on (A / B: right, C: top, D: left)
+    const double sa = cA ? ymax : (cB ? xmin : ymin);
+    const double sb = (cA || cB) ? xmax : (cC ? ymax : xmin);
+    const double qa = fsqrt0(r2 - sa * sa), qb = fsqrt0(r2 - sb * sb);
+    const double x1 = cB ? sa : qa, y1 = cB ? qa : sa;
+    const double x2 = cC ? qb : sb, y2 = cC ? sb : qb;
+    const double arc = area_arc(x1, y1, x2, y2, r);
+    // triangle 1: (P1, V2, V3); triangle 2 (configurations B and C only): (P1, W2, P2)
+    const double v2x = cB ? x1 : (cC ? xmin : x2), v2y = cB ? ymin : (cC ? y1 : y2);
+    const double v3x = (cA || cB) ? xmax : xmin, v3y = (cA || cC) ? ymax : ymin;
+    const double w2x = cB ? x2 : xmin, w2y = cB ? ymin : y2;
+    const double t1 = area_tri(x1, y1, v2x, v2y, v3x, v3y);
+    const double t2 = (cB || cC) ? area_tri(x1, y1, w2x, w2y, x2, y2) : 0.0;
+    const double cut = cA ? (full - t1) + arc : (arc + t1) + t2;
+    return none ? 0.0 : (all ? full : cut);
 }
-// unit pixel centred at (px, py) relative to the circle centre; any quadrant
-PM_DEV double overlap_pixel(double px, double py, double r) {
-    const double xmin = px - 0.5, xmax = px + 0.5, ymin = py - 0.5, ymax = py + 0.5;
-    double total = 0.0;
-#pragma unroll
-    for (int ix = 0; ix < 2; ix++) {
-        double xa, xb;
-        if (ix == 0) {
-            if (xmin >= 0.0) continue;
-            xa = xmin; xb = fmin(xmax, 0.0);
-        } else {
-            if (xmax <= 0.0) continue;
-            xa = fmax(xmin, 0.0); xb = xmax;
-        }
-#pragma unroll
-        for (int iy = 0; iy < 2; iy++) {
-            double ya, yb;
-            if (iy == 0) {
-                if (ymin >= 0.0) continue;
-                ya = ymin; yb = fmin(ymax, 0.0);
-            } else {
-                if (ymax <= 0.0) continue;
-                ya = fmax(ymin, 0.0); yb = ymax;
-            }
-            if (xa >= 0.0) {
-                if (ya >= 0.0) total += overlap_core(xa, ya, xb, yb, r);
-                else total += overlap_core(-yb, xa, -ya, xb, r);
-            } else {
-                if (ya >= 0.0) total += overlap_core(-xb, ya, -xa, yb, r);
-                else total += overlap_core(-xb, -yb, -xa, -ya, r);
-            }
-        }
-    }
-    return total;
+// unit pixel centred at the INTEGER offset (a, b) from the circle centre, any quadrant.  A pixel that straddles an
+// axis is split there by photutils and each part mapped to the first quadrant: for integer offsets the parts are
+// mirror images of each other, so one evaluation is doubled (a == 0 or b == 0) or quadrupled (a == b == 0).
+PM_DEV double overlap_pixel(int a, int b, double r) {
+    const int ia = a < 0 ? -a : a, ib = b < 0 ? -b : b;
+    const double px = (double)ia, py = (double)ib;
+    const double xmin = ia == 0 ? 0.0 : px - 0.5, ymin = ib == 0 ? 0.0 : py - 0.5;
+    const double part = overlap_core(xmin, ymin, px + 0.5, py + 0.5, r);
+    const double mult = (ia == 0 ? 2.0 : 1.0) * (ib == 0 ? 2.0 : 1.0);
+    return mult * part;
 }
 // photutils weight of the pixel at integer offset (dx, dy) from the circle centre
 PM_DEV double circle_weight(int dx, int dy, double r) {
     const double pr = 0.5 * sqrt(2.0);
     double d = sqrt((double)(dx * dx + dy * dy));
     if (d < r - pr) return 1.0;
-    if (d < r + pr) return overlap_pixel((double)dx, (double)dy, r);
+    if (d < r + pr) return overlap_pixel(dx, dy, r);
     return 0.0;
 }
 

@@ -111,7 +111,7 @@ template <> struct KeyT<double> { typedef uint64_t type; };
 PM_DEV float nan_of(float) { return pm::bits2f(0x7fc00000u); }
 PM_DEV double nan_of(double) { return pm::bits2d(0x7ff8000000000000ll); }
 
-constexpr int kPhaseSlots = 32;      // per CTA; 0..15 phases of analyse_one, 16.. sub-phases and counters (bench.py --phases)
+constexpr int kPhaseSlots = 48;      // per CTA; 0..15 phases of analyse_one, 16.. sub-phases and counters (bench.py --phases)
 struct PhaseClock {
     unsigned long long* slot;
     long long last;
@@ -565,6 +565,7 @@ PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
     }
     pm::sync();
     block_scan_excl_array(sh, c.rowoff, g.n);
+    c.pc.lap(37);
     double s = 0.0, sa = 0.0, m10 = 0.0, m01 = 0.0, vmax = -1.7976931348623157e308;
     int amax = 0x7fffffff;
     for (int r = pm::warp(); r < g.n; r += kWarps) {
@@ -587,6 +588,7 @@ PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
             off += (unsigned)pm::popc(bits);
         }
     }
+    c.pc.lap(38);
     double red[4] = {s, m10, m01, sa};
     block_sum<4>(sh, red);
     st->sum = red[0]; st->m10 = red[1]; st->m01 = red[2]; st->abs_sum = red[3];
@@ -760,6 +762,7 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
     gs = block_sum1(sh, gs);
     const double mean = st.sum / (double)n;
     out->gini = gs / (fabs(mean) * (double)n * (double)(n - 1));
+    c.pc.lap(32);
     // ---- m20 threshold: first element of the ascending order of ALL N values (zeros outside the map
     //      included) whose cumulative fraction exceeds 0.8  (casgm.py:261-263)
     double tot_seq;
@@ -794,6 +797,7 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
     if (!have_thresh) thresh = 0.0;
     else if (nzero > 0 && first_rank >= nneg && first_rank < nneg + nzero) thresh = 0.0;
     else thresh = val_of_key(sk[first_rank < nneg ? first_rank : first_rank - nzero], c.sky);
+    c.pc.lap(33);
     // ---- second moments about the flux centroid (casgm.py:253-271)
     const double rc = st.m10 / st.sum, cc = st.m01 / st.sum;
     double mt = 0.0, m2 = 0.0;
@@ -808,6 +812,7 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
     double red[2] = {mt, m2};
     block_sum<2>(sh, red);
     out->m20 = have_thresh ? log10(red[1] / red[0]) : nan_of(double());
+    c.pc.lap(34);
     // ---- candidates: walk the DESCENDING order while the running flux is below 20 % (asymmetry.py:101-108)
     const double t20 = 0.2 * st.sum;
     double dloc = 0.0;
@@ -828,6 +833,7 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
         }
     }
     out->n_cand = (int)block_sum_u(sh, nc);
+    c.pc.lap(35);
 }
 
 // ====================================================================================================
@@ -1343,7 +1349,7 @@ PM_DEV int count_below(int a, int lim) {              // number of b >= 0 with a
 // exact F(r) for nr <= kRedSlots radii; results in acc[0..nr) of every thread.  Pass 1: one (radius, column) item per
 // thread finds the cut range and adds the fully-inside prefix; pass 2: the cut pixels of all columns are
 // dealt out evenly, one exact circle/pixel overlap per thread-step.  off / blo: nr * (A + 1) + 1 entries each.
-PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo, double (&acc)[kRedSlots]) {
+PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo, double (&acc)[kRedSlots], PhaseClock* pc = nullptr) {
 #pragma unroll
     for (int q = 0; q < kRedSlots; q++) acc[q] = 0.0;
     const int ncol = f.A + 1, items = nr * ncol;
@@ -1353,6 +1359,7 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
         sh.ia[9 + 2 * pm::tid()] = d2_threshold(radii[pm::tid()] + pr);
     }
     pm::sync();
+    if (pc) pc->lap(41);
     for (int item = pm::tid(); item < items; item += kThreads) {
         const int q = item / ncol, a = item - q * ncol;
         const double r = radii[q];
@@ -1366,7 +1373,9 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
         off[item] = (unsigned)(b_hi - b_lo);
     }
     pm::sync();
+    if (pc) pc->lap(42);
     const int total = (int)block_scan_excl_array(sh, off, items);
+    if (pc) pc->lap(43);
     for (int e = pm::tid(); e < total; e += kThreads) {
         int lo = 0, hi = items - 1;          // last item with off[item] <= e
         while (lo < hi) {
@@ -1374,12 +1383,14 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
             if ((int)off[mid] <= e) lo = mid; else hi = mid - 1;
         }
         const int q = lo / ncol, a = lo - q * ncol, b = blo[lo] + (e - (int)off[lo]);
-        const double v = f.T[tri(a, b)] * overlap_pixel((double)a, (double)b, radii[q]);
+        const double v = f.T[tri(a, b)] * overlap_pixel(a, b, radii[q]);
 #pragma unroll
         for (int k = 0; k < kRedSlots; k++)
             if (k == q) acc[k] += v;
     }
-    block_sum<kRedSlots>(sh, acc);      // every thread now holds F(radii[q]) in acc[q]
+    if (pc) pc->lap(44);
+    block_sum<kRedSlots>(sh, acc);
+    if (pc) pc->lap(45);      // every thread now holds F(radii[q]) in acc[q]
 }
 // bounds lo <= F(r_k) <= hi for the walk radii rk[1..K]: one warp per radius.  A pixel at squared distance
 // d2 is certainly inside when d2 <= floor((r - pr - 1e-9)^2) - 1 and certainly outside when d2 > ceil((r + pr + 1e-9)^2).
@@ -1498,8 +1509,10 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     }
     pm::sync();
     double fv[kRedSlots];
-    eval_flux(sh, f, sh.rk, 1, eoff, eblo, fv);
+    c.pc.lap(46);
+    eval_flux(sh, f, sh.rk, 1, eoff, eblo, fv, &c.pc);
     const double total = fv[0];
+    c.pc.lap(39);
     // Walk down (casgm.py:61-73): first k with F(r_k) / total <= fraction.  Cheap bounds decide most radii;
     // only the undecided ones near the crossing are evaluated exactly.
     eval_flux_bounds(sh, f, K);
@@ -2062,6 +2075,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             phase_list(c, skA, &st);
             pc.lap(1);   // bbox, counts, window, raster list
             rmax2 = phase_rmax2(c, st, &cen_flat);
+            pc.lap(40);
             rmax = p.ov.radius_in ? p.ov.radius_in[b] : pm::dsqrt((double)rmax2);
             row.rmax = rmax;
             // ---- aperture plane (main.py:464) — uses the key buffers' neighbours as scratch before the sort
@@ -2106,6 +2120,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             }
             if (p.out.n_positive_out && pm::tid() == 0) p.out.n_positive_out[b] = so.n_pos;
             pm::sync();
+            pc.lap(36);
             // keep only the candidates (the first n_cand entries of the descending order)
             c.ar.release(mk_list);
             c.ar.keep(spA, (size_t)max(so.n_cand, 1) * 4);
