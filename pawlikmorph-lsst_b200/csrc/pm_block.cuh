@@ -17,7 +17,7 @@ namespace pmk {
 #define PM_MIN_CTAS 2
 #endif
 constexpr int kThreads = PM_THREADS;
-static_assert(kThreads >= 128 && kThreads % 32 == 0, "whole warps, at least four");
+static_assert(kThreads >= 160 && kThreads % 32 == 0, "whole warps; thread k holds walk radius k (k <= 130)");
 constexpr int kWarps = kThreads / 32;
 constexpr int kRedSlots = 8;
 
@@ -345,10 +345,38 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
 // Restates photutils/geometry/circular_overlap.pyx + core.pyx (photutils 0.7.x; the reference calls
 // CircularAperture(...).do_photometry(method="exact") at casgm.py:51-52, :66-67, :116-117, :333-336).
 PM_DEV double fsqrt0(double v) { return v > 0.0 ? sqrt(v) : 0.0; }
-PM_DEV double area_arc(double x1, double y1, double x2, double y2, double r) {
-    // photutils: a = chord, theta = 2 asin(a / 2r), area = r^2 (theta - sin theta) / 2.  sin(theta) is taken as
-    // 2 h sqrt(1 - h^2), h = a / 2r (independent of the asin: shorter dependency chain; same value to ~1 ulp)
-    const double a = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+// (theta - sin theta) / h^3 for theta = 2 asin(h), as a series in x = h^2 <= 1/4:
+//   theta - sin theta = 2 asin(h) - 2 h sqrt(1 - h^2) = sum_{k>=1} g_k h^(2k+1),  g_k = 2 C(2k,k)/4^k * 4k/((2k+1)(2k-1)).
+// 30 terms (truncation < 1e-18 at x = 1/4, all coefficients positive), Estrin's scheme: five FMA levels.
+PM_DEV double seg_series(double x) {
+    const double g[32] = {
+        1.3333333333333333, 0.4, 0.21428571428571427, 0.1388888888888889, 0.09943181818181818, 0.07572115384615384,
+        0.06015625, 0.04928768382352941, 0.04134328741776316, 0.035327729724702384, 0.030642965565557064, 0.02691009521484375,
+        0.023878556710702402, 0.02137669201554923, 0.019283352359648672, 0.017510842193256725, 0.015994278181876456,
+        0.014684730763169559, 0.013544676879134316, 0.012544909330289357, 0.011662389546007373, 0.010878726333127512,
+        0.010179079039942812, 0.00955135411245743, 0.008985608055959748, 0.008473597936544683, 0.008008438888979117,
+        0.007584340273350919, 0.007196400350168018, 0.006840444990846536, 0.0, 0.0};
+    const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8;
+    double p[16], q[8], o[4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) p[i] = fma(g[2 * i + 1], x, g[2 * i]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = fma(p[2 * i + 1], x2, p[2 * i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = fma(q[2 * i + 1], x4, q[2 * i]);
+    const double s0 = fma(o[1], x8, o[0]), s1 = fma(o[3], x8, o[2]);
+    return fma(s1, x16, s0);
+}
+// circular segment cut off by the chord (x1, y1)-(x2, y2): photutils takes a = chord, theta = 2 asin(a / 2r),
+// area = r^2 (theta - sin theta) / 2.  Here theta - sin theta comes from the series in h^2 = (a / 2r)^2 when
+// h <= 1/2 (every pixel-sized chord of a circle with r >= sqrt(2)): no asin, no division, no cancellation, and only
+// one square root on the dependency chain (the polynomial runs beside it).  Agrees with the closed form to < 1e-15
+// relative (the closed form itself loses ~1e-10 relative to cancellation for short chords).  inv4r2 = 1 / (4 r^2).
+PM_DEV double area_arc(double x1, double y1, double x2, double y2, double r, double inv4r2) {
+    const double c2 = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);      // chord^2
+    const double h2 = c2 * inv4r2;
+    if (h2 <= 0.25) return 0.125 * c2 * (sqrt(h2) * seg_series(h2));      // r^2 h^3 g / 2 = (a^2 / 8) h g
+    const double a = sqrt(c2);
     const double h = 0.5 * a / r;
     const double theta = 2.0 * asin(h);
     const double sin_theta = 2.0 * h * sqrt(fmax(1.0 - h * h, 0.0));
@@ -363,7 +391,7 @@ PM_DEV double area_tri(double x1, double y1, double x2, double y2, double x3, do
 // the lanes of a warp, which hold different pixels, do not serialise four copies of the sqrt / asin chain
 // (measured: 1915 -> ~500 cycles per call, profiles/microbench).  Per configuration the arithmetic is photutils'.
 PM_DEV double overlap_core(double xmin, double ymin, double xmax, double ymax, double r) {
-    const double r2 = r * r;
+    const double r2 = r * r, inv4r2 = 0.25 / r2;
     const double full = (xmax - xmin) * (ymax - ymin);
     const bool none = xmin * xmin + ymin * ymin > r2, all = xmax * xmax + ymax * ymax < r2;
     // corner tests on squared distances (photutils compares the square roots: same decisions up to rounding at
@@ -376,7 +404,7 @@ PM_DEV double overlap_core(double xmin, double ymin, double xmax, double ymax, d
     const double qa = fsqrt0(r2 - sa * sa), qb = fsqrt0(r2 - sb * sb);
     const double x1 = cB ? sa : qa, y1 = cB ? qa : sa;
     const double x2 = cC ? qb : sb, y2 = cC ? sb : qb;
-    const double arc = area_arc(x1, y1, x2, y2, r);
+    const double arc = area_arc(x1, y1, x2, y2, r, inv4r2);
     // triangle 1: (P1, V2, V3); triangle 2 (configurations B and C only): (P1, W2, P2)
     const double v2x = cB ? x1 : (cC ? xmin : x2), v2y = cB ? ymin : (cC ? y1 : y2);
     const double v3x = (cA || cB) ? xmax : xmin, v3y = (cA || cC) ? ymax : ymin;

@@ -1349,7 +1349,7 @@ PM_DEV int count_below(int a, int lim) {              // number of b >= 0 with a
 // exact F(r) for nr <= kRedSlots radii; results in acc[0..nr) of every thread.  Pass 1: one (radius, column) item per
 // thread finds the cut range and adds the fully-inside prefix; pass 2: the cut pixels of all columns are
 // dealt out evenly, one exact circle/pixel overlap per thread-step.  off / blo: nr * (A + 1) + 1 entries each.
-PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo, double (&acc)[kRedSlots], PhaseClock* pc = nullptr) {
+PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsigned* off, int* blo, double (&acc)[kRedSlots]) {
 #pragma unroll
     for (int q = 0; q < kRedSlots; q++) acc[q] = 0.0;
     const int ncol = f.A + 1, items = nr * ncol;
@@ -1359,7 +1359,6 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
         sh.ia[9 + 2 * pm::tid()] = d2_threshold(radii[pm::tid()] + pr);
     }
     pm::sync();
-    if (pc) pc->lap(41);
     for (int item = pm::tid(); item < items; item += kThreads) {
         const int q = item / ncol, a = item - q * ncol;
         const double r = radii[q];
@@ -1373,9 +1372,7 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
         off[item] = (unsigned)(b_hi - b_lo);
     }
     pm::sync();
-    if (pc) pc->lap(42);
     const int total = (int)block_scan_excl_array(sh, off, items);
-    if (pc) pc->lap(43);
     for (int e = pm::tid(); e < total; e += kThreads) {
         int lo = 0, hi = items - 1;          // last item with off[item] <= e
         while (lo < hi) {
@@ -1388,9 +1385,11 @@ PM_DEV void eval_flux(Sh& sh, const Fold& f, const double* radii, int nr, unsign
         for (int k = 0; k < kRedSlots; k++)
             if (k == q) acc[k] += v;
     }
-    if (pc) pc->lap(44);
-    block_sum<kRedSlots>(sh, acc);
-    if (pc) pc->lap(45);      // every thread now holds F(radii[q]) in acc[q]
+    // every thread ends up with F(radii[q]) in acc[q]; the reduction is as wide as the batch
+    if (nr <= 1) { double t[1] = {acc[0]}; block_sum<1>(sh, t); acc[0] = t[0]; }
+    else if (nr <= 2) { double t[2] = {acc[0], acc[1]}; block_sum<2>(sh, t); acc[0] = t[0]; acc[1] = t[1]; }
+    else if (nr <= 4) { double t[4] = {acc[0], acc[1], acc[2], acc[3]}; block_sum<4>(sh, t); acc[0] = t[0]; acc[1] = t[1]; acc[2] = t[2]; acc[3] = t[3]; }
+    else block_sum<kRedSlots>(sh, acc);
 }
 // bounds lo <= F(r_k) <= hi for the walk radii rk[1..K]: one warp per radius.  A pixel at squared distance
 // d2 is certainly inside when d2 <= floor((r - pr - 1e-9)^2) - 1 and certainly outside when d2 > ceil((r + pr + 1e-9)^2).
@@ -1504,13 +1503,20 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     const double delta = (radius / 200.0) * 2.0;
     int K = 0;   // number of walk radii that are > 0
     {
-        double r = radius - delta;
-        while (K < 130 && r > 0.0) { K++; if (pm::tid() == 0) sh.rk[K] = r; r -= delta; }
+        // the reference subtracts delta repeatedly (rounding accumulates): every thread runs the short serial chain in
+        // registers and thread k keeps r_k — no stores or branches on the chain
+        double r = radius, mine = 0.0;
+#pragma unroll 10
+        for (int k = 1; k <= 130; k++) {
+            r -= delta;
+            K += (r > 0.0) ? 1 : 0;                   // r decreases monotonically: counts the leading positive radii
+            if (k == pm::tid()) mine = r;
+        }
+        if (pm::tid() >= 1 && pm::tid() <= K) sh.rk[pm::tid()] = mine;
     }
     pm::sync();
     double fv[kRedSlots];
-    c.pc.lap(46);
-    eval_flux(sh, f, sh.rk, 1, eoff, eblo, fv, &c.pc);
+    eval_flux(sh, f, sh.rk, 1, eoff, eblo, fv);
     const double total = fv[0];
     c.pc.lap(39);
     // Walk down (casgm.py:61-73): first k with F(r_k) / total <= fraction.  Cheap bounds decide most radii;
@@ -1532,14 +1538,19 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     }
     pm::sync();
     int kfound[2] = {-1, -1};
-    for (int q = 0; q < 2; q++) {
-        int pos = 1;
-        while (pos <= K && kfound[q] < 0) {
-            // warp 0 scans the verdicts 32 at a time (ballots): undecided radii are collected until the first
-            // certain one (or kRedSlots of them); the outcome is broadcast through shared memory
-            if (pm::warp() == 0) {
-                int nl_ = 0, sure_ = -1, k_ = pos;
-                while (k_ <= K && nl_ < kRedSlots && sure_ < 0) {
+    int pos[2] = {1, 1};
+    // Both fractions advance together: per round warp 0 scans the verdicts of each unfinished fraction 32 at a time
+    // (ballots) and collects its undecided radii up to the first certain one — at most kRedSlots in total, half each
+    // while both are active — then ONE batched exact evaluation serves both; the outcome is broadcast through
+    // shared memory.  Per fraction the sequence of decisions is the reference's walk (casgm.py:61-73).
+    for (;;) {
+        const bool act[2] = {kfound[0] < 0 && pos[0] <= K, kfound[1] < 0 && pos[1] <= K};
+        if (!act[0] && !act[1]) break;
+        const int cap = (act[0] && act[1]) ? kRedSlots / 2 : kRedSlots;
+        if (pm::warp() == 0) {
+            for (int q = 0; q < 2; q++) {
+                int nl_ = 0, sure_ = -1, k_ = pos[q];
+                while (act[q] && k_ <= K && nl_ < cap && sure_ < 0) {
                     const int kk_ = k_ + pm::lane();
                     const int v = kk_ <= K ? (int)verdict[q * (K + 1) + kk_] : 0;
                     const unsigned m1 = pm::ballot(v == 1);
@@ -1547,36 +1558,45 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
                     const int f1 = m1 ? pm::ffs(m1) - 1 : 32;             // first certain radius of this group
                     if (f1 < 32) m2 &= (1u << f1) - 1u;
                     int consumed = 32;                                     // radii of this group dealt with
-                    while (m2 && nl_ < kRedSlots) {
+                    while (m2 && nl_ < cap) {
                         const int bpos = pm::ffs(m2) - 1;
-                        if (pm::lane() == 0) sh.ia[8 + nl_] = k_ + bpos;
+                        if (pm::lane() == 0) sh.ia[8 + (act[0] && act[1] ? q * (kRedSlots / 2) : 0) + nl_] = k_ + bpos;
                         nl_++;
                         m2 &= m2 - 1u;
-                        if (nl_ == kRedSlots) consumed = bpos + 1;
+                        if (nl_ == cap) consumed = bpos + 1;
                     }
-                    if (nl_ == kRedSlots && consumed <= f1) { k_ += consumed; break; }
+                    if (nl_ == cap && consumed <= f1) { k_ += consumed; break; }
                     if (f1 < 32) { sure_ = k_ + f1; break; }
                     k_ += 32;
                 }
-                if (pm::lane() == 0) { sh.ia[4] = nl_; sh.ia[5] = sure_; sh.ia[6] = min(k_, K + 1); }
+                if (pm::lane() == 0) { sh.ia[1 + 3 * q] = nl_; sh.ia[2 + 3 * q] = sure_; sh.ia[3 + 3 * q] = min(k_, K + 1); }
             }
+        }
+        pm::sync();
+        int list[kRedSlots], nl[2], sure[2], nxt[2];
+        for (int q = 0; q < 2; q++) { nl[q] = sh.ia[1 + 3 * q]; sure[q] = sh.ia[2 + 3 * q]; nxt[q] = sh.ia[3 + 3 * q]; }
+        const int ntot = nl[0] + nl[1];
+        for (int i = 0; i < kRedSlots; i++) {
+            // both active: fraction 0's entries sit at ia[8..], fraction 1's at ia[8 + kRedSlots/2 ..]; one active: at ia[8..]
+            const int src = (act[0] && act[1] && i >= nl[0]) ? kRedSlots / 2 + (i - nl[0]) : i;
+            list[i] = i < ntot ? sh.ia[8 + src] : 0;
+        }
+        pm::sync();
+        if (ntot > 0) {
+            if (pm::tid() == 0)
+                for (int i = 0; i < ntot; i++) sh.bc[8 + i] = sh.rk[list[i]];
             pm::sync();
-            int list[kRedSlots];
-            const int nl = sh.ia[4], sure = sh.ia[5];
-            const int k = sh.ia[6];
-            for (int i = 0; i < kRedSlots; i++) list[i] = i < nl ? sh.ia[8 + i] : 0;
-            pm::sync();
-            if (nl > 0) {
-                if (pm::tid() == 0)
-                    for (int i = 0; i < nl; i++) sh.bc[8 + i] = sh.rk[list[i]];
-                pm::sync();
-                eval_flux(sh, f, sh.bc + 8, nl, eoff, eblo2, fv);
-                for (int i = 0; i < nl && kfound[q] < 0; i++)
-                    if (fv[i] / total <= fr[q]) kfound[q] = list[i];
-                pm::sync();      // sh.bc[8..] is rewritten by the next batch
+            eval_flux(sh, f, sh.bc + 8, ntot, eoff, eblo2, fv);
+            for (int i = 0; i < ntot; i++) {
+                const int q = (act[0] && i < nl[0]) ? 0 : 1;
+                if (kfound[q] < 0 && fv[i] / total <= fr[q]) kfound[q] = list[i];
             }
-            if (kfound[q] < 0 && sure > 0) kfound[q] = sure;
-            pos = (sure > 0) ? K + 1 : k;
+            pm::sync();      // sh.bc[8..] is rewritten by the next batch
+        }
+        for (int q = 0; q < 2; q++) {
+            if (!act[q]) continue;
+            if (kfound[q] < 0 && sure[q] > 0) kfound[q] = sure[q];
+            pos[q] = (sure[q] > 0) ? K + 1 : nxt[q];
         }
     }
     const int k20 = kfound[0], k80 = kfound[1];
@@ -1618,9 +1638,10 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         ctv[e] = f.T[tri(a, bb)];
     }
     pm::sync();
-    // F_q(r_q) for the active fractions -> fq[q] (in every thread)
+    // F_q(r_q) for the active fractions -> fq[q] (in every thread).  (A variant that kept the few dozen cached pixels
+    // in the registers of warp 0 and reduced with shuffles only was slower: two overlap chains per lane, 62k vs 52k cycles.)
     double fq[2] = {0.0, 0.0};
-    auto eval_cached = [&](const double (&rq)[2], const bool (&act)[2]) {
+    auto eval_block = [&](const double (&rq)[2], const bool (&act)[2]) {
         double acc[2] = {0.0, 0.0};
         for (int e = pm::tid(); e < ncache; e += kThreads) {
             const unsigned ce = cent[e];
@@ -1633,28 +1654,31 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
         fq[0] = base[0] + acc[0]; fq[1] = base[1] + acc[1];
     };
     const double fr2[2] = {0.2, 0.8};
-    {
-        const bool both[2] = {true, true};
-        double flo[2], fhi[2];
-        eval_cached(blo_r, both);
-        flo[0] = fq[0]; flo[1] = fq[1];
-        eval_cached(bhi_r, both);
-        fhi[0] = fq[0]; fhi[1] = fq[1];
-        for (int q = 0; q < 2; q++) brent_init(b[q], blo_r[q], bhi_r[q], flo[q] / total - fr2[q], fhi[q] / total - fr2[q]);
-    }
-    for (;;) {
-        bool act[2];
-        double rq[2];
-        for (int q = 0; q < 2; q++) {
-            if (b[q].state == 0) brent_step(b[q]);
-            act[q] = b[q].state == 0;
-            rq[q] = b[q].xcur;
+    auto drive = [&](auto&& evalf) {       // brentq on both brackets in lock-step (uniform control flow)
+        {
+            const bool both[2] = {true, true};
+            double flo[2], fhi[2];
+            evalf(blo_r, both);
+            flo[0] = fq[0]; flo[1] = fq[1];
+            evalf(bhi_r, both);
+            fhi[0] = fq[0]; fhi[1] = fq[1];
+            for (int q = 0; q < 2; q++) brent_init(b[q], blo_r[q], bhi_r[q], flo[q] / total - fr2[q], fhi[q] / total - fr2[q]);
         }
-        if (!act[0] && !act[1]) break;
-        eval_cached(rq, act);
-        for (int q = 0; q < 2; q++)
-            if (act[q]) b[q].fcur = fq[q] / total - fr2[q];
-    }
+        for (;;) {
+            bool act[2];
+            double rq[2];
+            for (int q = 0; q < 2; q++) {
+                if (b[q].state == 0) brent_step(b[q]);
+                act[q] = b[q].state == 0;
+                rq[q] = b[q].xcur;
+            }
+            if (!act[0] && !act[1]) break;
+            evalf(rq, act);
+            for (int q = 0; q < 2; q++)
+                if (act[q]) b[q].fcur = fq[q] / total - fr2[q];
+        }
+    };
+    drive(eval_block);
     c.ar.release(mk);
     if (b[0].state != 1 || b[1].state != 1) return;
     if (!(fabs(b[0].root) < 1.7e308) || !(fabs(b[1].root) < 1.7e308)) return;
