@@ -200,9 +200,10 @@ struct Arena {
     }
 };
 
-// lanes of the warp that hold the same 8-bit digit as this lane (invalid lanes match nobody).  One MATCH.ANY:
-// its long latency is hidden by batching four chunks per step; the 9-ballot multisplit it replaces cost ~6 % of
-// all executed instructions of the kernel.
+// lanes of the warp that hold the same digit as this lane (invalid lanes match nobody).  One MATCH.ANY: ~11 cycles
+// per DISTINCT value (370-510 cycles for the typical all-different digits, profiles/microbench), partly hidden by
+// batching four chunks per step.  Measured alternatives for the scatter sweep: nine ballots per chunk (79k vs 50k
+// cycles), ranks taken from the counting sweep's atomics with a MATCH among colliding lanes only (68k + 27k).
 PM_DEV unsigned same_digit_mask(unsigned d, bool valid) {
     return pm::match_any(valid ? d : 0x10000u + (unsigned)pm::lane());
 }
@@ -261,10 +262,10 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
         const int shift = pass * db;
         for (int i = t; i < kWarps * D; i += kThreads) hist[i] = 0;
         pm::sync();
-        // sweep 1: per-warp digit counts.  Four chunks per step: their loads and MATCH chains are independent
-        // (the loop is a chain of dependent ops otherwise); counts go in with shared-memory atomics.
+        // sweep 1: per-warp digit counts, one shared-memory atomic per key (the digits of a warp's 32 keys are mostly
+        // different: little same-address serialisation, and no warp vote or MATCH is needed: 37k -> 16k cycles)
         for (int base = lo; base < hi; base += 128) {
-            unsigned d[4], m[4];
+            unsigned d[4];
             bool valid[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -273,10 +274,8 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
                 d[u] = valid[u] ? ((unsigned)(src[valid[u] ? i : lo] >> shift) & mask) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) m[u] = same_digit_mask(d[u], valid[u]);
-#pragma unroll
             for (int u = 0; u < 4; u++)
-                if (valid[u] && l == pm::ffs(m[u]) - 1) pm::atomic_add(&hist[w * D + d[u]], (unsigned)pm::popc(m[u]));
+                if (valid[u]) pm::atomic_add(&hist[w * D + d[u]], 1u);
         }
         pm::sync();
         lap(17);

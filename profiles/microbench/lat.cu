@@ -29,15 +29,22 @@ __global__ void k(double* out, long long* cyc, double seed, unsigned useed) {
     c = timed([&] { for (int i = 0; i < REP; i++) x = (double)((float)x) + 1e-3; }); if (threadIdx.x == 0) cyc[s] = c; s++; // 5 F2F.32.64 + F2F.64.32 + DADD
     // MATCH.ANY: all lanes distinct / all equal / 4 groups
     unsigned m = 0;
-    c = timed([&] { for (int i = 0; i < REP; i++) { m = __match_any_sync(0xffffffffu, u + m); } }); if (threadIdx.x == 0) cyc[s] = c; s++;          // 6 distinct
-    c = timed([&] { for (int i = 0; i < REP; i++) { m = __match_any_sync(0xffffffffu, (m & 0) + useed); } }); if (threadIdx.x == 0) cyc[s] = c; s++; // 7 equal
-    c = timed([&] { for (int i = 0; i < REP; i++) { m = __match_any_sync(0xffffffffu, (lane & 3) + (m & 0)); } }); if (threadIdx.x == 0) cyc[s] = c; s++; // 8 four groups
+    c = timed([&] { for (int i = 0; i < REP; i++) { m = __match_any_sync(0xffffffffu, u + (m >> 31)); } }); if (threadIdx.x == 0) cyc[s] = c; s++;          // 6 distinct
+    c = timed([&] { for (int i = 0; i < REP; i++) { m = __match_any_sync(0xffffffffu, (m >> 31) + useed - 1u); } }); if (threadIdx.x == 0) cyc[s] = c; s++; // 7 equal
+    c = timed([&] { for (int i = 0; i < REP; i++) { m = __match_any_sync(0xffffffffu, (lane & 3) + ((m >> 31) << 4)); } }); if (threadIdx.x == 0) cyc[s] = c; s++; // 8 four groups
+    // same-digit mask from 9 ballots (multisplit), dependent through the digit
+    c = timed([&] { for (int i = 0; i < REP; i++) {
+        const unsigned d = (u * 2654435761u + m) >> 23;
+        unsigned mm = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 9; b++) { const unsigned v = __ballot_sync(0xffffffffu, (d >> b) & 1u); mm &= ((d >> b) & 1u) ? v : ~v; }
+        m = mm; } }); if (threadIdx.x == 0) cyc[15] = c;
     // ballot chain
     c = timed([&] { for (int i = 0; i < REP; i++) { m = __ballot_sync(0xffffffffu, (m >> lane) & 1u) + 1u; } }); if (threadIdx.x == 0) cyc[s] = c; s++; // 9 ballot
     // shared atomics with return, spread addresses / same address
     unsigned r = u;
     c = timed([&] { for (int i = 0; i < REP; i++) { r = atomicAdd(&hist[(lane * 7 + r) & 511], 1u); } }); if (threadIdx.x == 0) cyc[s] = c; s++;   // 10 ATOMS spread (dependent)
-    c = timed([&] { for (int i = 0; i < REP; i++) { r = atomicAdd(&hist[r & 0], 1u); } }); if (threadIdx.x == 0) cyc[s] = c; s++;                   // 11 ATOMS same address
+    c = timed([&] { for (int i = 0; i < REP; i++) { r = atomicAdd(&hist[(r >> 30) & 1], 1u); } }); if (threadIdx.x == 0) cyc[s] = c; s++;                   // 11 ATOMS same address
     c = timed([&] { for (int i = 0; i < REP; i++) { r = hist[(r + lane) & 511] + 1u; } }); if (threadIdx.x == 0) cyc[s] = c; s++;                   // 12 LDS dependent
     c = timed([&] { for (int i = 0; i < REP; i++) { r = __shfl_xor_sync(0xffffffffu, r, 1) + 1u; } }); if (threadIdx.x == 0) cyc[s] = c; s++;      // 13 SHFL
     c = timed([&] { for (int i = 0; i < REP; i++) { __syncthreads(); } }); if (threadIdx.x == 0) cyc[s] = c; s++;                                  // 14 BAR
@@ -45,7 +52,7 @@ __global__ void k(double* out, long long* cyc, double seed, unsigned useed) {
 }
 int main() {
     const char* names[] = {"DADD", "DFMA", "DSQRT+DADD", "DDIV+DADD", "asin+DMUL", "F2F x2 + DADD", "MATCH.ANY distinct", "MATCH.ANY equal",
-                           "MATCH.ANY 4 groups", "VOTE.BALLOT(+shift,add)", "ATOMS spread (dep)", "ATOMS same addr (dep)", "LDS (dep)", "SHFL (dep)", "BAR.SYNC"};
+                           "MATCH.ANY 4 groups", "VOTE.BALLOT(+shift,add)", "ATOMS spread (dep)", "ATOMS same addr (dep)", "LDS (dep)", "SHFL (dep)", "BAR.SYNC", "9-ballot same-digit mask"};
     double* out; long long* cyc;
     cudaMalloc(&out, 1024 * 8); cudaMalloc(&cyc, 64 * 8);
     for (int threads : {32, 256}) {
@@ -53,7 +60,7 @@ int main() {
         long long h[64];
         cudaMemcpy(h, cyc, 64 * 8, cudaMemcpyDeviceToHost);
         printf("threads per CTA = %d (one CTA on the GPU)\n", threads);
-        for (int i = 0; i < 15; i++) printf("  %-26s %8.1f cycles/op\n", names[i], (double)h[i] / REP);
+        for (int i = 0; i < 16; i++) printf("  %-26s %8.1f cycles/op\n", names[i], (double)h[i] / REP);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
