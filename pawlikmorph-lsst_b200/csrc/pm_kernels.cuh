@@ -568,24 +568,35 @@ PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
     c.pc.lap(37);
     double s = 0.0, sa = 0.0, m10 = 0.0, m01 = 0.0, vmax = -1.7976931348623157e308;
     int amax = 0x7fffffff;
+    const int wlo = c.c0 >> 5, whi = c.c1 >> 5;          // words of the bounding box
     for (int r = pm::warp(); r < g.n; r += kWarps) {
         unsigned off = c.rowoff[r];
         if (c.rowoff[r + 1] == off) continue;
-        for (int w = 0; w < g.nw; w++) {
-            const unsigned bits = c.seg[r * g.nw + w];
-            if (bits == 0) continue;
-            if ((bits >> pm::lane()) & 1u) {
-                const int col = w * 32 + pm::lane();
-                const unsigned o = off + (unsigned)pm::popc(bits & lt_mask());
-                const T x = pm::ldg(c.img + (size_t)r * g.n + col);
-                c.posR[o] = ((unsigned)r << 16) | (unsigned)col;
-                keys[o] = key_of(x, c.sky);
-                const double v = (double)x - c.sky;
-                s += v; sa += fabs(v); m10 += (double)r * v; m01 += (double)col * v;
-                const int flat = r * g.n + col;
-                if (v > vmax || (v == vmax && flat < amax)) { vmax = v; amax = flat; }
+        // four words of the row per step: their image loads are issued together (the row is otherwise a chain of
+        // dependent L2 round trips)
+        for (int w0 = wlo; w0 <= whi; w0 += 4) {
+            unsigned bits[4];
+            T x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                bits[u] = w0 + u <= whi ? c.seg[r * g.nw + w0 + u] : 0u;
+                const bool mine = (bits[u] >> pm::lane()) & 1u;
+                x[u] = mine ? pm::ldg(c.img + (size_t)r * g.n + (w0 + u) * 32 + pm::lane()) : T(0);
             }
-            off += (unsigned)pm::popc(bits);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if ((bits[u] >> pm::lane()) & 1u) {
+                    const int col = (w0 + u) * 32 + pm::lane();
+                    const unsigned o = off + (unsigned)pm::popc(bits[u] & lt_mask());
+                    c.posR[o] = ((unsigned)r << 16) | (unsigned)col;
+                    keys[o] = key_of(x[u], c.sky);
+                    const double v = (double)x[u] - c.sky;
+                    s += v; sa += fabs(v); m10 += (double)r * v; m01 += (double)col * v;
+                    const int flat = r * g.n + col;
+                    if (v > vmax || (v == vmax && flat < amax)) { vmax = v; amax = flat; }
+                }
+                off += (unsigned)pm::popc(bits[u]);
+            }
         }
     }
     c.pc.lap(38);
