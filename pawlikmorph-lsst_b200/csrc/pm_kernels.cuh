@@ -1187,8 +1187,7 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     }
     const bool bgr_ok = noise && b.nb > 0 && b.nm > 1;      // asymmetry.py:225-226
     c.pc.lap(9);    // (calcA: dilation + row scan)
-    // compact list of the non-empty aperture words (deterministic order), two of them per warp-step so that
-    // their dependent chains (bit lookups -> rank/select -> image loads) overlap
+    // compact list of the non-empty aperture words (deterministic order)
     Arena::Mark mk_t = c.ar.mark();
     const int nwords = g.n * g.nw;
     unsigned* flag = (unsigned*)c.ar.alloc((size_t)(nwords + 1) * 4);
@@ -1201,54 +1200,74 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     pm::sync();
     double s[3] = {0.0, 0.0, 0.0};           // numA denA numB
     unsigned u180 = 0, uden = 0, u90 = 0;    // shape asymmetry: integer pixel counts
-    auto contrib = [&](unsigned task) {
-        const int r = (int)(task >> 16), col = (int)(task & 0xffffu) * 32 + pm::lane();
-        const unsigned bits = c.aper[r * g.nw + (int)(task & 0xffffu)];
-        if (!((bits >> pm::lane()) & 1u)) return;
-        // 180°: (r, c) -> (2cy - r, 2cx - c);  90° (skimage, counter-clockwise): (cy + (c - cx), cx - (r - cy))
-        const int r180 = 2 * cy - r, c180 = 2 * cx - col;
-        const int r90 = cy + (col - cx), c90 = cx - (r - cy);
-        const bool in180 = r180 >= 0 && r180 < g.n && c180 >= 0 && c180 < g.n;
-        const bool in90 = r90 >= 0 && r90 < g.n && c90 >= 0 && c90 < g.n;
-        if (do_img) {
-            // source indices first (shared-memory work only), then all image loads back to back
-            const int fI = r * g.n + col;
-            int fR = -1, fB = -1, fBr = -1;
-            int rR = r, cR = col;
-            if (rot90) { if (in90) { fR = 1; rR = r90; cR = c90; } }
-            else if (in180) { fR = 1; rR = r180; cR = c180; }
-            if (bgr_ok) {
-                // the background image is rotated about the SWAPPED centre (asymmetry.py:245)
-                const int rb = 2 * cx - r, cb = 2 * cy - col;
-                fB = bgr_source(g, b, r, col);
-                if (rb >= 0 && rb < g.n && cb >= 0 && cb < g.n) fBr = bgr_source(g, b, rb, cb);
+    // kTasks aperture words per warp-step, in three stages so that the image loads of all of them are in flight
+    // together: (1) source indices (shared-memory work only, branchy), (2) all loads back to back, (3) arithmetic
+    constexpr int kTasks = 2;
+    for (int k0 = pm::warp(); k0 < ntask; k0 += kTasks * kWarps) {
+        int r_[kTasks], col_[kTasks], fR[kTasks], fB[kTasks], fBr[kTasks], rR[kTasks], cR[kTasks];
+        bool on[kTasks], in180[kTasks], in90[kTasks];
+#pragma unroll
+        for (int u = 0; u < kTasks; u++) {
+            const int k = k0 + u * kWarps;
+            const unsigned task = tlist[min(k, ntask - 1)];
+            const int r = (int)(task >> 16), col = (int)(task & 0xffffu) * 32 + pm::lane();
+            const unsigned bits = c.aper[r * g.nw + (int)(task & 0xffffu)];
+            on[u] = k < ntask && ((bits >> pm::lane()) & 1u);
+            r_[u] = r; col_[u] = col;
+            // 180°: (r, c) -> (2cy - r, 2cx - c);  90° (skimage, counter-clockwise): (cy + (c - cx), cx - (r - cy))
+            const int r180 = 2 * cy - r, c180 = 2 * cx - col;
+            const int r90 = cy + (col - cx), c90 = cx - (r - cy);
+            in180[u] = r180 >= 0 && r180 < g.n && c180 >= 0 && c180 < g.n;
+            in90[u] = r90 >= 0 && r90 < g.n && c90 >= 0 && c90 < g.n;
+            fR[u] = -1; fB[u] = -1; fBr[u] = -1; rR[u] = r; cR[u] = col;
+            if (do_img && on[u]) {
+                if (rot90) { if (in90[u]) { fR[u] = 1; rR[u] = r90; cR[u] = c90; } }
+                else if (in180[u]) { fR[u] = 1; rR[u] = r180; cR[u] = c180; }
+                if (bgr_ok) {
+                    // the background image is rotated about the SWAPPED centre (asymmetry.py:245)
+                    const int rb = 2 * cx - r, cb = 2 * cy - col;
+                    fB[u] = bgr_source(g, b, r, col);
+                    if (rb >= 0 && rb < g.n && cb >= 0 && cb < g.n) fBr[u] = bgr_source(g, b, rb, cb);
+                }
             }
-            const T xI = ld_raw(c, r, col);
-            const T xR = ld_raw(c, rR, cR);
-            const T xB = pm::ldg(c.img + (fB >= 0 ? fB : fI));
-            const T xBr = pm::ldg(c.img + (fBr >= 0 ? fBr : fI));
-            const double I = (double)xI - c.sky;
-            const double Ir = fR >= 0 ? (double)xR - c.sky : 0.0;
-            s[0] += fabs(I - Ir);
-            s[1] += fabs(I);
-            if (bgr_ok) {
-                const double B = (double)xB - c.sky;
-                const double Br = fBr >= 0 ? (double)xBr - c.sky : 0.0;
-                s[2] += fabs(B - Br);
+        }
+        if (do_img) {
+            T xI[kTasks], xR[kTasks], xB[kTasks], xBr[kTasks];
+#pragma unroll
+            for (int u = 0; u < kTasks; u++) {
+                const int fI = r_[u] * g.n + col_[u];
+                xI[u] = on[u] ? ld_raw(c, r_[u], col_[u]) : T(0);
+                xR[u] = on[u] ? ld_raw(c, rR[u], cR[u]) : T(0);
+                xB[u] = (on[u] && bgr_ok) ? pm::ldg(c.img + (fB[u] >= 0 ? fB[u] : fI)) : T(0);
+                xBr[u] = (on[u] && bgr_ok) ? pm::ldg(c.img + (fBr[u] >= 0 ? fBr[u] : fI)) : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < kTasks; u++) {
+                if (!on[u]) continue;
+                const double I = (double)xI[u] - c.sky;
+                const double Ir = fR[u] >= 0 ? (double)xR[u] - c.sky : 0.0;
+                s[0] += fabs(I - Ir);
+                s[1] += fabs(I);
+                if (bgr_ok) {
+                    const double B = (double)xB[u] - c.sky;
+                    const double Br = fBr[u] >= 0 ? (double)xBr[u] - c.sky : 0.0;
+                    s[2] += fabs(B - Br);
+                }
             }
         }
         if (do_shape) {
-            const unsigned v = bit_at(c.seg, g.nw, r, col) ? 1u : 0u;
-            const unsigned v180 = in180 && bit_at(c.seg, g.nw, r180, c180) ? 1u : 0u;
-            const unsigned v90 = in90 && bit_at(c.seg, g.nw, r90, c90) ? 1u : 0u;
-            u180 += v ^ v180;
-            uden += v;
-            u90 += v ^ v90;
+#pragma unroll
+            for (int u = 0; u < kTasks; u++) {
+                if (!on[u]) continue;
+                const int r = r_[u], col = col_[u];
+                const unsigned v = bit_at(c.seg, g.nw, r, col) ? 1u : 0u;
+                const unsigned v180 = in180[u] && bit_at(c.seg, g.nw, 2 * cy - r, 2 * cx - col) ? 1u : 0u;
+                const unsigned v90 = in90[u] && bit_at(c.seg, g.nw, cy + (col - cx), cx - (r - cy)) ? 1u : 0u;
+                u180 += v ^ v180;
+                uden += v;
+                u90 += v ^ v90;
+            }
         }
-    };
-    for (int k = pm::warp(); k < ntask; k += 2 * kWarps) {
-        contrib(tlist[k]);
-        if (k + kWarps < ntask) contrib(tlist[k + kWarps]);
     }
     block_sum<3>(sh, s);
     const double n180 = (double)block_sum_u(sh, u180), nden = (double)block_sum_u(sh, uden), n90 = (double)block_sum_u(sh, u90);
