@@ -97,3 +97,19 @@ def test_large_cutout_with_large_filter_spills_staging():
     yy, xx = np.mgrid[0:n, 0:n]
     img = (100 + rng.normal(0, 5, (n, n)) + 900 * np.exp(-(((xx - 321) / 7.0) ** 2 + ((yy - 318) / 5.0) ** 2) / 2)).astype(np.float32)
     P.check_against_oracle(run, img[None], 100.0, 5.0, 15)
+
+
+@pytest.mark.parametrize("n", [15, 16, 31, 64, 141])
+def test_aperture_sweep_matches_oracle(n):
+    """aperpixmap (apertures.py:42-128) over integer-form (sqrt of an integer: what calcRmax yields) and
+    float-form radii, including none / all of the frame: the windowed edge search and its fallback."""
+    import math
+    from oracle import pm_oracle as O
+    from tests import emul_harness as H
+    rng = np.random.default_rng(n)
+    rads = [0.0, 0.3, 0.75, 1.0, math.sqrt(2.0), 2.5, float(n), 3.0 * n]
+    rads += [math.sqrt(float(k)) for k in rng.integers(1, (n // 2 + 2) ** 2, size=24)]
+    rads += [float(x) for x in rng.uniform(0.5, 0.75 * n, size=16)]
+    got = H.aperpixmap(n, np.asarray(rads, dtype=np.float64))
+    for k, r in enumerate(rads):
+        assert np.array_equal(got[k], O.aperpixmap(n, r, 9, 0.1)), f"n={n} rad={r!r}"
