@@ -297,7 +297,7 @@ def run_ours(args):
         rate, dt = cpu_pool_rate(sample_imgs, procs)
         cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                "sample": f"first {S} cutouts of the same synthetic batch, oracle port, multiprocessing.Pool({procs}), {dt:.1f} s"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC if args.n == 256 else METRIC.replace("256^2", f"{args.n}^2"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{B} synthetic Sersic+noise {n}x{n} float32 cutouts per GPU resident in HBM "

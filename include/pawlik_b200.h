@@ -137,10 +137,10 @@ int pm_aperpixmap_batch(int n, const double *rad, int64_t B, int nsubpix, double
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 const char *pm_last_cuda_error(void);
-/* Tuning aid: when set to a zeroed DEVICE buffer of PM_MAX_GRID x 32 uint64, subsequent pm_analyse_batch launches
+/* Tuning aid: when set to a zeroed DEVICE buffer of PM_MAX_GRID x 48 uint64, subsequent pm_analyse_batch launches
  * accumulate per-CTA clock64() cycles per phase (0 pixelmap, 1 list/window, 2 rmax/aperture, 3 sort, 4 gini/m20/
  * candidates, 5 minapix, 6 calcA, 7 r20/r80, 8 smoothness).  Pass NULL to switch it off (the default). */
-void pm_debug_phase_cycles(void *device_u64_grid_x32);
+void pm_debug_phase_cycles(void *device_u64_grid_x48);
 #define PM_MAX_GRID 592
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 uint64_t pm_launch_count(void);

@@ -75,7 +75,7 @@ static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
 extern "C" {
 
 int pm_abi_version(void) { return PM_ABI_VERSION; }
-void pm_debug_phase_cycles(void* device_u64_grid_x32) { g_phase_cycles = (unsigned long long*)device_u64_grid_x32; }
+void pm_debug_phase_cycles(void* device_u64_grid_x48) { g_phase_cycles = (unsigned long long*)device_u64_grid_x48; }
 const char* pm_last_cuda_error(void) { return g_err; }
 uint64_t pm_launch_count(void) { return g_launches.load(); }
 
