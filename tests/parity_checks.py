@@ -69,3 +69,24 @@ def check_against_oracle(run, images, sky, err, fs=3, flags=15, rtol=RTOL, dtype
 
 def synth_batch(B, n, seed):
     return synth.make_batch(B, n, seed).numpy()
+
+
+def check_small_radius_growth_curves(run, rtol=RTOL):
+    """calcR20_R80 (casgm.py:124-155) for apertures of a few pixels: the exact circle/pixel overlap then sees
+    chords that are long against the radius (the closed-form segment area instead of the series), pixels that
+    straddle both axes, and circles inside one pixel."""
+    n = 41
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float64)
+    rng = np.random.default_rng(7)
+    img = (200.0 * np.exp(-((xx - 20.3) ** 2 + (yy - 19.6) ** 2) / (2 * 2.2 ** 2)) + rng.normal(0, 0.5, (n, n))).astype(np.float32)
+    seg = np.ones((n, n), np.uint8)
+    radii = [1.2, 1.9, 2.6, 4.3, 9.7, 17.0]
+    B = len(radii)
+    x = np.repeat(img[None], B, axis=0)
+    res = run(x, 0.0, 0.0, 3, 4, segmap_in=np.repeat(seg[None], B, axis=0), centroid_in=np.tile([20.0, 20.0], (B, 1)),
+              radius_in=np.asarray(radii))
+    for i, rad in enumerate(radii):
+        got = rowd(res["rows"], i)
+        r20, r80 = O.calcR20_R80(img.astype(np.float64), seg.astype(np.float64), [20, 20], rad)
+        for name, want in (("r20", r20), ("r80", r80)):
+            assert abs(got[name] - want) <= rtol * abs(want) + 1e-13, f"radius {rad}: {name} {got[name]!r} != {want!r}"

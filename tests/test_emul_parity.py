@@ -113,3 +113,7 @@ def test_aperture_sweep_matches_oracle(n):
     got = H.aperpixmap(n, np.asarray(rads, dtype=np.float64))
     for k, r in enumerate(rads):
         assert np.array_equal(got[k], O.aperpixmap(n, r, 9, 0.1)), f"n={n} rad={r!r}"
+
+
+def test_small_radius_growth_curves():
+    P.check_small_radius_growth_curves(run)

@@ -248,3 +248,7 @@ def test_maximum_size_and_supplied_segmaps():
     rows_a, rows_b = a["rows"].copy(), b["rows"].copy()
     rows_a[:, 13] = 0      # object_edge is only set on the pixelmap path (main.py:427)
     assert np.array_equal(rows_a, rows_b)
+
+
+def test_small_radius_growth_curves():
+    P.check_small_radius_growth_curves(run)
