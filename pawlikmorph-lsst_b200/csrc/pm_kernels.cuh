@@ -1785,7 +1785,7 @@ PM_DEV void box_means(const Ctx<T_>& c, int k, int rlo, int rlen, int clo, int c
     const int h = k / 2;
     const int W = cb - ca, E = W + k - 1;
     if (W <= 0 || rb <= ra) return;
-    const int R = max(1, min(2 * kWarps, vcap / E));
+    const int R = max(1, min(4 * kWarps, vcap / E));
     const double inv = 1.0 / ((double)k * (double)k);
     const bool cols_inside = (ca - h >= clo) && (cb - 1 - h + k - 1 < clo + clen);     // no column reflection needed
     for (int band = ra; band < rb; band += R) {
@@ -1845,7 +1845,7 @@ PM_DEV double phase_smoothness(Ctx<T_>& c, int cx, int cy, double rmax, double r
     const int iymin = (int)floor((double)cy - rmax + 0.5), iymax = (int)ceil((double)cy + rmax + 0.5);
     const int x0 = max(ixmin, 0), x1 = min(ixmax, g.n), y0 = max(iymin, 0), y1 = min(iymax, g.n);
     Arena::Mark mk = c.ar.mark();
-    const int vcap = max(2 * (x1 - x0 + k), 2048);
+    const int vcap = max(2 * (x1 - x0 + k), 4096);
     double* vbuf = (double*)c.ar.alloc((size_t)vcap * 8);
     const int A = (int)(rmax + 0.5 * sqrt(2.0)) + 1;
     unsigned* eoff = (unsigned*)c.ar.alloc((size_t)(2 * (A + 1) + 1) * 4);
