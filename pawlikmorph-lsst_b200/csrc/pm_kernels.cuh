@@ -156,6 +156,17 @@ template <typename T> PM_DEV double ld(const Ctx<T>& c, int r, int col) { return
 PM_DEV bool bit_at(const unsigned* plane, int nw, int r, int c) {
     return (plane[r * nw + (c >> 5)] >> (c & 31)) & 1u;
 }
+// number of set bits of row r of a bit plane, read by ONE thread: the words are visited in an order rotated by r / 4 so
+// that the 32 rows a warp counts (lane stride nw words) fall on different banks (nw = 8: conflict-free instead of 8-way)
+PM_DEV unsigned row_popcount(const unsigned* plane, int nw, int r) {
+    unsigned cnt = 0;
+    int w = (r >> 2) % nw;
+    for (int k = 0; k < nw; k++) {
+        cnt += (unsigned)pm::popc(plane[r * nw + w]);
+        if (++w == nw) w = 0;
+    }
+    return cnt;
+}
 template <typename T> PM_DEV T mw_raw(const Ctx<T>& c, int r, int col) {
     if (r < c.r0 || r > c.r1 || col < c.c0 || col > c.c1) return nan_of(T());
     return c.mw[(r - c.r0) * c.bw + (col - c.c0)];
@@ -557,13 +568,7 @@ template <typename T>
 PM_DEV void phase_list(Ctx<T>& c, typename KeyT<T>::type* keys, SegStats* st) {
     const Geo& g = c.g;
     Sh& sh = *c.sh;
-    // per-row counts -> exclusive offsets
-    for (int r = pm::tid(); r < g.n; r += kThreads) {
-        unsigned cnt = 0;
-        for (int w = 0; w < g.nw; w++) cnt += (unsigned)pm::popc(c.seg[r * g.nw + w]);
-        c.rowoff[r] = cnt;
-    }
-    pm::sync();
+    // c.rowoff holds the per-row counts (the caller needed their sum for the allocations) -> exclusive offsets
     block_scan_excl_array(sh, c.rowoff, g.n);
     c.pc.lap(37);
     double s = 0.0, sa = 0.0, m10 = 0.0, m01 = 0.0, vmax = -1.7976931348623157e308;
@@ -761,16 +766,21 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
     const int chunk = (n + kThreads - 1) / kThreads;
     const int lo = min(n, pm::tid() * chunk), hi = min(n, lo + chunk);
     // ---- gini: Σ (2i - n - 1)|x_i| / (|mean| n (n - 1)), i = 1..n ascending (photutils.morphology.gini)
-    double gs = 0.0, loc = 0.0;
-    int npos = 0;
+    // one pass, one reduction: gini sum, Σ negatives and the counts of positive / negative values (exact in float64)
+    double gs = 0.0, loc = 0.0, negsum = 0.0;
+    int npos = 0, nneg = 0;
     for (int i = lo; i < hi; i++) {
         const double v = val_of_key(sk[i], c.sky);
         gs += (double)(2 * (i + 1) - n - 1) * fabs(v);
         loc += v;
         npos += v > 0.0;
+        if (v < 0.0) { nneg++; negsum += v; }
     }
-    out->n_pos = (int)block_sum_u(sh, (unsigned)npos);
-    gs = block_sum1(sh, gs);
+    {
+        double red4[4] = {gs, negsum, (double)npos, (double)nneg};
+        block_sum<4>(sh, red4);
+        gs = red4[0]; negsum = red4[1]; out->n_pos = (int)red4[2]; nneg = (int)red4[3];
+    }
     const double mean = st.sum / (double)n;
     out->gini = gs / (fabs(mean) * (double)n * (double)(n - 1));
     c.pc.lap(32);
@@ -793,14 +803,6 @@ PM_DEV void phase_gini_m20_cands(Ctx<T>& c, const typename KeyT<T>::type* sk, co
         }
     }
     // the block of outside zeros sits after the negatives: cumulative sum there = Σ negatives
-    int nneg = 0;
-    double negsum = 0.0;
-    for (int i = lo; i < hi; i++) {
-        const double v = val_of_key(sk[i], c.sky);
-        if (v < 0.0) { nneg++; negsum += v; }
-    }
-    nneg = (int)block_sum_u(sh, (unsigned)nneg);
-    negsum = block_sum1(sh, negsum);
     if (nzero > 0 && (negsum / st.sum > 0.8)) first_rank = min(first_rank, nneg);
     first_rank = block_min_i(sh, first_rank);
     double thresh;
@@ -1167,9 +1169,7 @@ PM_DEV void phase_calcA(Ctx<T>& c, int cx, int cy, AsymOut* out, unsigned* tmp_p
     if (noise) {
         dilate9(g, c.seg, c.dil, tmp_plane);
         for (int r = pm::tid(); r < g.n; r += kThreads) {
-            unsigned cnt = 0;
-            for (int w = 0; w < g.nw; w++) cnt += (unsigned)pm::popc(c.dil[r * g.nw + w]);
-            c.rowoff[r] = cnt;
+            c.rowoff[r] = row_popcount(c.dil, g.nw, r);
         }
         pm::sync();
         b.nm = (int)block_scan_excl_array(sh, c.rowoff, g.n);
@@ -2085,14 +2085,12 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
 
     if (!done) {
         // ---- raster list + keys, statistics
-        for (int r = pm::tid(); r < g.n; r += kThreads) {   // n_g first (for the allocations)
-            unsigned cnt = 0;
-            for (int w = 0; w < g.nw; w++) cnt += (unsigned)pm::popc(c.seg[r * g.nw + w]);
-            c.rowoff[r] = cnt;
-        }
-        pm::sync();
         unsigned ng = 0;
-        for (int r = pm::tid(); r < g.n; r += kThreads) ng += c.rowoff[r];
+        for (int r = pm::tid(); r < g.n; r += kThreads) {   // n_g first (for the allocations)
+            const unsigned cnt = row_popcount(c.seg, g.nw, r);
+            c.rowoff[r] = cnt;            // stays there for phase_list
+            ng += cnt;
+        }
         c.n_g = (int)block_sum_u(sh, ng);
         const int n_g = c.n_g;
         // arena plan: [raster list][sorted positions -> candidates][sort temporaries], then — once the sort
