@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("PM_BENCH_BATCH", 262144)),
                     help="galaxies resident per GPU (BASELINE.json configs[2]: 262144; reduced automatically if HBM is short)")
     ap.add_argument("--e2e-batch", type=int, default=8192)
-    ap.add_argument("--e2e-chunk", type=int, default=2048)
+    ap.add_argument("--e2e-chunk", type=int, default=1024)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase cycle shares to stderr (tuning aid)")

@@ -139,36 +139,59 @@ def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segma
     return res
 
 
+_host_cache = {}
+
+
+def _host_staging(dev, chunk, n, dtype, B):
+    """Reusable buffers of analyse_host: two device staging tensors and two streams (chunks alternate), device rows
+    and a pinned host copy of them.  Kept per (device, chunk, n, dtype) so that a steady stream of calls allocates
+    nothing (device allocations and pinning synchronise the device)."""
+    key = (dev.type, dev.index, int(chunk), int(n), dtype)
+    h = _host_cache.get(key)
+    if h is None:
+        h = dict(bufs=[torch.empty((chunk, n, n), dtype=dtype, device=dev) for _ in range(2)],
+                 streams=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)], rows_d=None, rows_h=None)
+        _host_cache[key] = h
+    if h["rows_d"] is None or h["rows_d"].shape[0] < B:
+        h["rows_d"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev)
+        h["rows_h"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
+    return h
+
+
 def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="cuda:0", chunk=8192, **kw):
     """The call a user of the reference's driver makes: HOST arrays in, HOST rows out.
 
-    `images` is a numpy array / CPU tensor [B, n, n]; every chunk is staged through pinned memory,
-    copied to the device, analysed and its rows copied back.  Returns a [B, 16] float64 numpy array
-    (columns = ROW_FIELDS)."""
+    `images` is a numpy array / CPU tensor [B, n, n] (pinned memory makes the copies asynchronous); chunks
+    alternate between two streams, each with its own device staging buffer, so that the host->device copy of
+    chunk i+1 overlaps the kernel of chunk i.  Returns a [B, 16] float64 numpy array (columns = ROW_FIELDS)."""
     dev = torch.device(device)
     x = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
     if x.dtype not in (torch.float32, torch.float64):
         x = x.to(torch.float64) if x.dtype in (torch.int64, torch.uint64) else x.to(torch.float32)
-    B = x.shape[0]
-    sky = np.broadcast_to(np.asarray(sky, dtype=np.float64), (B,))
-    sky_err = np.broadcast_to(np.asarray(sky_err, dtype=np.float64), (B,))
-    rows = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
-    # two streams, alternating chunks: the host->device copy of chunk i+1 overlaps the kernel of chunk i
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    B, n = int(x.shape[0]), int(x.shape[1])
+    chunk = max(1, min(int(chunk), B))
+    h = _host_staging(dev, chunk, n, x.dtype, B)
+    cur = torch.cuda.current_stream(dev)
+    sky_d = _per_galaxy(sky, B, dev, "sky")
+    err_d = _per_galaxy(sky_err, B, dev, "sky_err")
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    rows_d = h["rows_d"]
     for i, s in enumerate(range(0, B, chunk)):
         e = min(B, s + chunk)
-        xs = x[s:e]
-        if not xs.is_pinned():
-            xs = xs.pin_memory()
-        st = streams[i & 1]
+        st = h["streams"][i & 1]
+        if i < 2:
+            st.wait_event(ready)           # the sky vectors (and whatever the caller queued before)
         with torch.cuda.stream(st):
-            d = xs.to(dev, non_blocking=True)
-            r = analyse_batch(d, torch.from_numpy(sky[s:e].copy()), torch.from_numpy(sky_err[s:e].copy()),
-                              filter_size, flags, stream=st, **kw)
-            rows[s:e].copy_(r.rows, non_blocking=True)
-    for st in streams:
-        st.synchronize()
-    return rows.numpy()
+            d = h["bufs"][i & 1][:e - s]
+            d.copy_(x[s:e], non_blocking=True)
+            analyse_batch(d, sky_d[s:e], err_d[s:e], filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
+    for st in h["streams"]:
+        cur.wait_stream(st)
+    rows_h = h["rows_h"][:B]
+    rows_h.copy_(rows_d[:B], non_blocking=True)
+    cur.synchronize()
+    return rows_h.numpy().copy()
 
 
 # ---- multi-GPU: galaxies are independent, so the batch shards by galaxy (main.py:136-148 did the
