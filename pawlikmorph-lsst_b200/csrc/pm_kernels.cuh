@@ -521,10 +521,10 @@ template <typename T> PM_DEV int phase_pixelmap(Ctx<T>& c) {
     if (!exact) {
         double mn, mx;
         Arena::Mark mk = c.ar.mark();
-        int R = max(1, kThreads / g.m);                            // about one shrunk pixel per thread per band
-        for (;;) {                                                  // two staging buffers of <= 24 KB each
+        int R = max(1, 3 * kThreads / g.m);                        // about three shrunk pixels per thread per band
+        for (;;) {                                                  // two staging buffers of <= 32 KB each
             const int nr = (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3;
-            if (R == 1 || (size_t)nr * g.n * sizeof(T) <= 24576) break;
+            if (R == 1 || (size_t)nr * g.n * sizeof(T) <= 32768) break;
             R--;
         }
         const int nrows = min(g.n, (int)(((long long)(R - 1) * g.n) / g.m) + g.fs + 3);
