@@ -133,6 +133,14 @@ int pm_analyse_batch(const void *images, int dtype, int64_t B, int n, const doub
 int pm_aperpixmap_batch(int n, const double *rad, int64_t B, int nsubpix, double frac,
                         uint8_t *mask_out, void *cuda_stream);
 
+/* FITS image payload -> device floats: the input format of the path.  Replaces, for a batch of cutouts,
+ * `fits.getdata(...)` + `byteswap().newbyteorder()` + `astype(float64)` of Image.py:132-134, :148.
+ * payload: DEVICE pointer to `count` big-endian pixels of type BITPIX (8, 16, 32, -32, -64), headers stripped;
+ * out[i] = BZERO + BSCALE * stored[i] (float64 arithmetic), written as out_dtype (PM_F32 / PM_F64).
+ * BITPIX 16 with BZERO = 32768, BSCALE = 1 is the unsigned-16 convention of the bundled SDSS frames. */
+int pm_fits_decode_batch(const void *payload, int bitpix, double bzero, double bscale, int64_t count,
+                         void *out, int out_dtype, void *cuda_stream);
+
 /* Library / device introspection (HOST). */
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);

@@ -194,6 +194,51 @@ def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="c
     return rows_h.numpy().copy()
 
 
+def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0, filter_size=3, flags=PM_DO_ALL,
+                         device="cuda:0", chunk=8192, **kw):
+    """Like analyse_host, but from the big-endian FITS pixel blocks of B cutouts of n x n pixels (`payload`: uint8
+    numpy array / CPU tensor [B, n * n * bytes_per_pixel], pinned memory makes the copies asynchronous).  The bytes are
+    copied as they are and decoded on the device (image.decode_payload): 2 bytes per pixel on the wire for BITPIX 16."""
+    from .image import BYTES_PER_PIXEL, decode_payload
+    dev = torch.device(device)
+    x = payload if torch.is_tensor(payload) else torch.from_numpy(np.ascontiguousarray(payload))
+    if x.dtype != torch.uint8 or x.ndim != 2 or x.shape[1] != n * n * BYTES_PER_PIXEL[bitpix]:
+        raise ValueError("payload must be uint8 [B, n * n * bytes_per_pixel]")
+    B = int(x.shape[0])
+    chunk = max(1, min(int(chunk), B))
+    key = (dev.type, dev.index, int(chunk), int(x.shape[1]), "payload")
+    h = _host_cache.get(key)
+    if h is None:
+        h = dict(bufs=[torch.empty((chunk, x.shape[1]), dtype=torch.uint8, device=dev) for _ in range(2)],
+                 streams=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)], rows_d=None, rows_h=None)
+        _host_cache[key] = h
+    if h["rows_d"] is None or h["rows_d"].shape[0] < B:
+        h["rows_d"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev)
+        h["rows_h"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
+    cur = torch.cuda.current_stream(dev)
+    sky_d = _per_galaxy(sky, B, dev, "sky")
+    err_d = _per_galaxy(sky_err, B, dev, "sky_err")
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    rows_d = h["rows_d"]
+    for i, s in enumerate(range(0, B, chunk)):
+        e = min(B, s + chunk)
+        st = h["streams"][i & 1]
+        if i < 2:
+            st.wait_event(ready)
+        with torch.cuda.stream(st):
+            d = h["bufs"][i & 1][:e - s]
+            d.copy_(x[s:e], non_blocking=True)
+            img = decode_payload(d, bitpix, (e - s, n, n), bzero, bscale, torch.float32, stream=st)
+            analyse_batch(img, sky_d[s:e], err_d[s:e], filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
+    for st in h["streams"]:
+        cur.wait_stream(st)
+    rows_h = h["rows_h"][:B]
+    rows_h.copy_(rows_d[:B], non_blocking=True)
+    cur.synchronize()
+    return rows_h.numpy().copy()
+
+
 # ---- multi-GPU: galaxies are independent, so the batch shards by galaxy (main.py:136-148 did the
 # same with a process pool); the only collective is the gather of the result rows. -----------------
 def shard_bounds(B, world_size, rank):

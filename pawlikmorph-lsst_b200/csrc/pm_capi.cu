@@ -10,6 +10,7 @@
 #include <atomic>
 
 #include "pm_kernels.cuh"
+#include "pm_fits.cuh"
 
 using namespace pmk;
 
@@ -187,6 +188,37 @@ int pm_aperpixmap_batch(int n, const double* rad, int64_t B, int nsubpix, double
     (void)cuda_stream;
     for (long long blk = 0; blk < grid; blk++)
         pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { aperpixmap_body(n, rad, B, nsubpix, frac, mask_out, smem); });
+#endif
+    g_launches.fetch_add(1);
+    return PM_OK;
+}
+
+int pm_fits_decode_batch(const void* payload, int bitpix, double bzero, double bscale, int64_t count, void* out,
+                         int out_dtype, void* cuda_stream) {
+    g_err[0] = 0;
+    if (count == 0) return PM_OK;
+    if (!payload || !out || count < 0 || fits_bytes_per_pixel(bitpix) == 0 || (out_dtype != PM_F32 && out_dtype != PM_F64)) {
+        snprintf(g_err, sizeof g_err, "bad argument");
+        return PM_EINVAL;
+    }
+#ifndef PM_EMULATE
+    int rc = device_props();
+    if (rc != PM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const unsigned char* raw = (const unsigned char*)payload;
+    // HBM-bound byte work: 8 CTAs of 256 threads per SM, every thread streams 16-byte vectors
+    const long long want = ((long long)count / 8 + 255) / 256;
+    const unsigned grid = (unsigned)(want < 8LL * g_sm_count ? (want > 0 ? want : 1) : 8LL * g_sm_count);
+    if (out_dtype == PM_F32) pm_fits_decode_kernel<float><<<grid, 256, 0, st>>>(raw, bitpix, bzero, bscale, (size_t)count, (float*)out);
+    else pm_fits_decode_kernel<double><<<grid, 256, 0, st>>>(raw, bitpix, bzero, bscale, (size_t)count, (double*)out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_fits_decode_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
+#else
+    (void)cuda_stream;
+    for (int64_t i = 0; i < count; i++) {
+        const double v = fits_pixel((const unsigned char*)payload, (size_t)i, bitpix, bzero, bscale);
+        if (out_dtype == PM_F32) ((float*)out)[i] = (float)v; else ((double*)out)[i] = v;
+    }
 #endif
     g_launches.fetch_add(1);
     return PM_OK;

@@ -104,3 +104,13 @@ def aperpixmap(n, rads, nsubpix=9, frac=0.1):
     rc = L.pm_aperpixmap_batch(n, rads.ctypes.data, len(rads), nsubpix, frac, out.ctypes.data, None)
     abi.check(L, rc, "pm_aperpixmap_batch")
     return out
+
+
+def fits_decode(payload, bitpix, count, bzero=0.0, bscale=1.0, dtype=np.float32):
+    L = lib()
+    raw = np.ascontiguousarray(np.frombuffer(payload, dtype=np.uint8))
+    out = np.empty(count, dtype=dtype)
+    rc = L.pm_fits_decode_batch(raw.ctypes.data, int(bitpix), float(bzero), float(bscale), int(count), out.ctypes.data,
+                                abi.PM_F32 if dtype == np.float32 else abi.PM_F64, None)
+    abi.check(L, rc, "pm_fits_decode_batch")
+    return out
