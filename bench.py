@@ -267,6 +267,29 @@ def run_ours(args):
     e2e_value = world * E * e2e_steps / e2e_s
     assert np.array_equal(rows_h, rows[:E].cpu().numpy(), equal_nan=True), "e2e rows differ from the resident run"
 
+    # ---- the same call fed the way the reference's frames are stored: big-endian BITPIX 16 payloads (BZERO 32768,
+    # Image.py:132-134), 2 bytes per pixel over PCIe, decoded on the device (pm_fits_decode_batch).  The cutouts are
+    # the same ones rounded to integer counts and clipped to the unsigned-16 range; reported beside e2e, not as it.
+    xi = x[:E].round().clamp_(0, 65535)
+    pay = (xi.to(torch.int32) - 32768).to(torch.int16).cpu().numpy().astype(">i2")
+    pay_h = torch.from_numpy(pay.view(np.uint8).reshape(E, -1)).pin_memory()
+    want16 = pm.batch.analyse_host(xi.cpu().pin_memory(), synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL, device=dev, chunk=args.e2e_chunk)
+    kw16 = dict(bzero=32768.0, bscale=1.0, filter_size=3, flags=FLAGS_ALL, device=dev, chunk=args.e2e_chunk)
+    pm.batch.analyse_host_payload(pay_h, 16, n, synth.SKY, synth.SKY_ERR, **kw16)                            # warm
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rows16 = pm.batch.analyse_host_payload(pay_h, 16, n, synth.SKY, synth.SKY_ERR, **kw16)
+    torch.cuda.synchronize(dev)
+    f16_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([f16_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        f16_s = float(t.item())
+    f16_value = world * E * e2e_steps / f16_s
+    assert np.array_equal(rows16, want16, equal_nan=True), "payload rows differ from the float32 host call"
+    del xi
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -313,6 +336,9 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * per + 16 * E, "d2h_bytes_per_step": E * 128,
                     "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host"},
+            "e2e_fits16": {"value": f16_value, "unit": UNIT, "h2d_bytes_per_step": E * n * n * 2 + 16 * E, "d2h_bytes_per_step": E * 128,
+                           "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host_payload",
+                           "note": "same cutouts as integer counts in the FITS BITPIX 16 / BZERO 32768 wire format, decoded on the device"},
             "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,50 @@
+"""The file driver end to end on the GPU: the reference's 69 + 69 SDSS frames (rewritten as FITS files from the golden
+fixtures, BITPIX 16 / BZERO 32768 like sample/) -> calcMorphology -> parameters.csv, against the golden rows."""
+import ast
+import csv
+
+import numpy as np
+import pytest
+
+from tests import parity_checks as P
+from tests.fits_files import fits_bytes
+from tests.golden_util import compare_row
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["sdss_s", "sdss_l"])
+def test_calcMorphology_on_the_sdss_frames(name, tmp_path):
+    import pawlikmorph_lsst_b200 as pm
+    g = P.golden(name)
+    (tmp_path / "sample").mkdir()
+    lines = ["filename, ra, dec"]
+    for i in range(g.n):
+        fn = f"sample/{str(g.z['names'][i])}"
+        (tmp_path / fn).write_bytes(fits_bytes(g.image(i), -32 if i % 7 == 3 else 16))
+        lines.append(f"{fn}, {149.0 + i}, {0.5}")
+    (tmp_path / "images.csv").write_text("\n".join(lines) + "\n")
+    out = tmp_path / "output"
+    res = pm.main.calcMorphology(pm.helpers.getFiles(str(tmp_path / "images.csv")), out, filterSize=3, allAsymmetry=True, CAS=True,
+                                 smoothness=True, root=tmp_path)
+    assert len(res) == g.n
+    table = list(csv.reader(open(out / "parameters.csv")))
+    assert table[0] == pm.result.CSV_HEADER and len(table) == g.n + 1
+    for i, r in enumerate(res):
+        want = g.row(i)
+        assert (r.sky, r.sky_err) == g.sky(i)
+        got = dict(apix_col=r.apix[0], apix_row=r.apix[1], rmax=r.rmax, r20=r.r20, r80=r.r80, C=r.C, A=r.A[0], Abgr=r.A[1], S=r.S,
+                   As=r.As[0], As90=r.As90[0], gini=r.gini, m20=r.m20, object_edge=float(r.objectEdge), status=r.status)
+        errs = compare_row(got, want, P.RTOL, f"{name}[{i}] ")
+        assert not errs, "\n".join(errs)
+        d = dict(zip(table[0], table[i + 1]))                      # the CSV carries the same numbers (repr round-trips)
+        assert d["file"] == r.file and list(ast.literal_eval(d["apix"])) == list(r.apix)
+        for col, v in (("r_max", r.rmax), ("C", r.C), ("A", r.A[0]), ("Abgr", r.A[1]), ("As", r.As[0]), ("As90", r.As90[0]),
+                       ("Gini index", r.gini), ("M20", r.m20), ("r20", r.r20), ("r80", r.r80)):
+            assert float(d[col]) == float(v) or (float(d[col]) != float(d[col]) and v != v)
+        assert d["Object on image edge?"] == str(r.objectEdge)
+    # -A only (main.py:469-476): the CAS and shape columns keep their sentinels
+    res_a = pm.main.calcMorphology(list(pm.helpers.getFiles(str(tmp_path / "images.csv")))[:5], out, asymmetry=True, allAsymmetry=False,
+                                   CAS=False, paramsaveFile="a.csv", root=tmp_path)
+    for i, r in enumerate(res_a):
+        assert r.A == res[i].A and r.As == [-99., -99.] and r.C == -99. and r.gini == -99. and r.S == -99.
