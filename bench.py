@@ -270,11 +270,18 @@ def run_ours(args):
     # ---- the same call fed the way the reference's frames are stored: big-endian BITPIX 16 payloads (BZERO 32768,
     # Image.py:132-134), 2 bytes per pixel over PCIe, decoded on the device (pm_fits_decode_batch).  The cutouts are
     # the same ones rounded to integer counts and clipped to the unsigned-16 range; reported beside e2e, not as it.
-    xi = x[:E].round().clamp_(0, 65535)
-    pay = (xi.to(torch.int32) - 32768).to(torch.int16).cpu().numpy().astype(">i2")
-    pay_h = torch.from_numpy(pay.view(np.uint8).reshape(E, -1)).pin_memory()
-    want16 = pm.batch.analyse_host(xi.cpu().pin_memory(), synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL, device=dev, chunk=args.e2e_chunk)
-    kw16 = dict(bzero=32768.0, bscale=1.0, filter_size=3, flags=FLAGS_ALL, device=dev, chunk=args.e2e_chunk)
+    del xh
+    xi_h = torch.empty((E, n, n), dtype=torch.float32).pin_memory()
+    pay_h = torch.empty((E, n * n * 2), dtype=torch.uint8).pin_memory()
+    for s0 in range(0, E, 4096):
+        xc = x[s0:min(E, s0 + 4096)].round().clamp_(0, 65535)
+        xi_h[s0:s0 + xc.shape[0]].copy_(xc)
+        be = (xc.to(torch.int32) - 32768).to(torch.int16)
+        pay_h[s0:s0 + xc.shape[0]].copy_(be.view(torch.uint8).reshape(-1, 2).flip(1).reshape(xc.shape[0], -1))   # big-endian
+        del xc, be
+    want16 = pm.batch.analyse_host(xi_h, synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL, device=dev, chunk=args.e2e_chunk)
+    del xi_h
+    kw16 = dict(bzero=32768.0, bscale=1.0, filter_size=3, flags=FLAGS_ALL, device=dev, chunk=args.e2e_payload_chunk)
     pm.batch.analyse_host_payload(pay_h, 16, n, synth.SKY, synth.SKY_ERR, **kw16)                            # warm
     fence()
     t0 = time.perf_counter()
@@ -288,7 +295,21 @@ def run_ours(args):
         f16_s = float(t.item())
     f16_value = world * E * e2e_steps / f16_s
     assert np.array_equal(rows16, want16, equal_nan=True), "payload rows differ from the float32 host call"
-    del xi
+    # ---- the decode kernel alone (HBM-bound byte work): CUDA events on the launching stream, payload > L2
+    D = min(E, 8192)
+    pay_d = pay_h[:D].to(dev)
+    for _ in range(3):
+        img_d = pm.image.decode_payload(pay_d, 16, (D, n, n), 32768.0, 1.0, torch.float32)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    d0.record()
+    for _ in range(10):
+        img_d = pm.image.decode_payload(pay_d, 16, (D, n, n), 32768.0, 1.0, torch.float32)
+    d1.record()
+    torch.cuda.synchronize(dev)
+    dec_ms = d0.elapsed_time(d1) / 10
+    dec_bytes = D * n * n * 6
+    del pay_d, img_d
 
     if rank != 0:
         if world > 1:
@@ -337,8 +358,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * per + 16 * E, "d2h_bytes_per_step": E * 128,
                     "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host"},
             "e2e_fits16": {"value": f16_value, "unit": UNIT, "h2d_bytes_per_step": E * n * n * 2 + 16 * E, "d2h_bytes_per_step": E * 128,
-                           "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host_payload",
+                           "galaxies_per_step": E, "chunk": args.e2e_payload_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host_payload",
                            "note": "same cutouts as integer counts in the FITS BITPIX 16 / BZERO 32768 wire format, decoded on the device"},
+            "roofline_decode": {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / peak, "kernel": "pm_fits_decode_kernel<16, float>",
+                                "kernel_ms": dec_ms, "algorithmic_bytes_per_pixel": 6, "pixels": D * n * n, "traffic": None},
             "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -355,8 +379,9 @@ def main():
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--batch", type=int, default=int(os.environ.get("PM_BENCH_BATCH", 262144)),
                     help="galaxies resident per GPU (BASELINE.json configs[2]: 262144; reduced automatically if HBM is short)")
-    ap.add_argument("--e2e-batch", type=int, default=8192)
+    ap.add_argument("--e2e-batch", type=int, default=32768)
     ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--e2e-payload-chunk", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print per-phase cycle shares to stderr (tuning aid)")

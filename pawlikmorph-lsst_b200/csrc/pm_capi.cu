@@ -206,11 +206,10 @@ int pm_fits_decode_batch(const void* payload, int bitpix, double bzero, double b
     if (rc != PM_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const unsigned char* raw = (const unsigned char*)payload;
-    // HBM-bound byte work: 8 CTAs of 256 threads per SM, every thread streams 16-byte vectors
-    const long long want = ((long long)count / 8 + 255) / 256;
-    const unsigned grid = (unsigned)(want < 8LL * g_sm_count ? (want > 0 ? want : 1) : 8LL * g_sm_count);
-    if (out_dtype == PM_F32) pm_fits_decode_kernel<float><<<grid, 256, 0, st>>>(raw, bitpix, bzero, bscale, (size_t)count, (float*)out);
-    else pm_fits_decode_kernel<double><<<grid, 256, 0, st>>>(raw, bitpix, bzero, bscale, (size_t)count, (double*)out);
+    // HBM-bound byte work: up to 8 CTAs of 256 threads per SM (a multiple of the SM count), grid-stride beyond that
+    const unsigned max_ctas = 8u * (unsigned)g_sm_count;
+    if (out_dtype == PM_F32) fits_decode_launch<float>(raw, bitpix, bzero, bscale, (size_t)count, (float*)out, max_ctas, st);
+    else fits_decode_launch<double>(raw, bitpix, bzero, bscale, (size_t)count, (double*)out, max_ctas, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_fits_decode_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
 #else

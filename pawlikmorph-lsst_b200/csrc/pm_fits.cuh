@@ -14,6 +14,17 @@ PM_HOSTDEV int fits_bytes_per_pixel(int bitpix) {
 }
 PM_HOSTDEV unsigned bswap32(unsigned v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
 
+// stored -> physical value: a rounded multiply, then a rounded add (numpy's `a * bscale + bzero`; never an FMA)
+PM_HOSTDEV double fits_scale(double stored, double bzero, double bscale) {
+    if (bscale == 1.0 && bzero == 0.0) return stored;
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__dmul_rn(stored, bscale), bzero);
+#else
+    volatile double prod = stored * bscale;      // keeps -ffp-contract from fusing the two on the host build
+    return prod + bzero;
+#endif
+}
+
 // physical value of pixel i of the payload, float64: stored * bscale + bzero (exact for the unsigned-integer
 // convention and for unscaled data; the multiply-add is done in float64)
 PM_HOSTDEV double fits_pixel(const unsigned char* raw, size_t i, int bitpix, double bzero, double bscale) {
@@ -31,52 +42,94 @@ PM_HOSTDEV double fits_pixel(const unsigned char* raw, size_t i, int bitpix, dou
         for (int k = 0; k < 8; k++) u = (u << 8) | p[k];
         memcpy(&stored, &u, 8);
     }
-    if (bscale == 1.0 && bzero == 0.0) return stored;
-    return stored * bscale + bzero;
+    return fits_scale(stored, bzero, bscale);
 }
 
 #if !defined(PM_EMULATE)
-// grid-stride; the two common layouts take 16-byte loads (8 x int16 / 4 x float32 per thread-step)
-template <typename Out>
-__global__ void pm_fits_decode_kernel(const unsigned char* __restrict__ raw, int bitpix, double bzero, double bscale,
-                                      size_t count, Out* __restrict__ out) {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+template <int NB> struct RawWords;             // NB payload bytes (one output vector's worth) as 32-bit words
+template <> struct RawWords<2>  { unsigned w[1]; __device__ void load(const unsigned char* p) { w[0] = __ldg((const unsigned short*)p); } };
+template <> struct RawWords<4>  { unsigned w[1]; __device__ void load(const unsigned char* p) { w[0] = __ldg((const unsigned*)p); } };
+template <> struct RawWords<8>  { unsigned w[2]; __device__ void load(const unsigned char* p) { const uint2 q = __ldg((const uint2*)p); w[0] = q.x; w[1] = q.y; } };
+template <> struct RawWords<16> { unsigned w[4]; __device__ void load(const unsigned char* p) { const uint4 q = __ldg((const uint4*)p); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; } };
+template <> struct RawWords<32> { unsigned w[8]; __device__ void load(const unsigned char* p) {
+    const uint4 q = __ldg((const uint4*)p), r = __ldg((const uint4*)p + 1);
+    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; w[4] = r.x; w[5] = r.y; w[6] = r.z; w[7] = r.w; } };
+
+// stored value of pixel j of a vector held as little-endian words of big-endian pixels (byte swaps are one PRMT each)
+template <int BITPIX> __device__ __forceinline__ double stored_of(const unsigned* w, int j) {
+    if (BITPIX == 8) return (double)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    if (BITPIX == 16) return (double)(short)__byte_perm(w[j >> 1], 0, (j & 1) ? 0x4423 : 0x4401);
+    if (BITPIX == 32) return (double)(int)__byte_perm(w[j], 0, 0x0123);
+    if (BITPIX == -32) return (double)__uint_as_float(__byte_perm(w[j], 0, 0x0123));
+    return __hiloint2double((int)__byte_perm(w[2 * j], 0, 0x0123), (int)__byte_perm(w[2 * j + 1], 0, 0x0123));
+}
+
+template <int BITPIX> __device__ __forceinline__ int stored_int_of(const unsigned* w, int j) {
+    if (BITPIX == 8) return (int)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    return (int)(short)__byte_perm(w[j >> 1], 0, (j & 1) ? 0x4423 : 0x4401);
+}
+
+// One output vector = 16 bytes (4 floats / 2 doubles) per thread-step, so that stores AND loads of a warp are contiguous;
+// PM_FITS_UNROLL vectors per thread with all loads issued before the first conversion.  HBM-bound byte work: algorithmic
+// bytes per pixel = bytes_per_pixel read + sizeof(Out) written (6 for the 16-bit SDSS frames into float32).
+#ifndef PM_FITS_UNROLL
+#define PM_FITS_UNROLL 4
+#endif
+template <int BITPIX, typename Out>
+__global__ void __launch_bounds__(256) pm_fits_decode_kernel(const unsigned char* __restrict__ raw, double bzero, double bscale,
+                                                              size_t count, Out* __restrict__ out) {
+    constexpr int BPP = BITPIX == 8 ? 1 : BITPIX == 16 ? 2 : BITPIX == -64 ? 8 : 4;
+    constexpr int P = 16 / (int)sizeof(Out), NB = P * BPP, U = PM_FITS_UNROLL;
     const bool plain = bscale == 1.0 && bzero == 0.0;
-    if (bitpix == 16 && (((uintptr_t)raw) & 15) == 0) {
-        const size_t nvec = count / 8;
-        const uint4* v = (const uint4*)raw;
-        for (size_t k = tid; k < nvec; k += nthreads) {
-            const uint4 q = __ldg(v + k);
-            const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    // integer pixels with BSCALE 1 and an integer BZERO (the unsigned conventions, and unscaled data): the sum is exact in
+    // int32 and one int -> Out conversion rounds like the float64 route does
+    const bool ints = (BITPIX == 8 || BITPIX == 16) && bscale == 1.0 && bzero == rint(bzero) && fabs(bzero) <= 1073741824.0;
+    const int ibias = ints ? (int)bzero : 0;
+    const size_t nvec = ((((uintptr_t)raw) % NB) == 0 && (((uintptr_t)out) & 15) == 0) ? count / P : 0;   // unaligned views: scalar path
+    const size_t tile = (size_t)blockDim.x * U, stride = (size_t)gridDim.x * tile;
+    for (size_t base = (size_t)blockIdx.x * tile + threadIdx.x; base < nvec; base += stride) {
+        RawWords<NB> v[U];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // memory order b0 b1 b2 b3 = two big-endian int16: (b0 b1), (b2 b3); little-endian register = b3 b2 b1 b0
-                const short s0 = (short)__byte_perm(w[j], 0, 0x4401), s1 = (short)__byte_perm(w[j], 0, 0x4423);
-                const double d0 = plain ? (double)s0 : (double)s0 * bscale + bzero;
-                const double d1 = plain ? (double)s1 : (double)s1 * bscale + bzero;
-                out[8 * k + 2 * j] = (Out)d0;
-                out[8 * k + 2 * j + 1] = (Out)d1;
-            }
+        for (int u = 0; u < U; u++) {
+            const size_t k = base + (size_t)u * blockDim.x;
+            if (k < nvec) v[u].load(raw + k * NB);
         }
-        for (size_t i = nvec * 8 + tid; i < count; i += nthreads) out[i] = (Out)fits_pixel(raw, i, bitpix, bzero, bscale);
-        return;
-    }
-    if (bitpix == -32 && (((uintptr_t)raw) & 15) == 0) {
-        const size_t nvec = count / 4;
-        const uint4* v = (const uint4*)raw;
-        for (size_t k = tid; k < nvec; k += nthreads) {
-            const uint4 q = __ldg(v + k);
-            const unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float f = __uint_as_float(__byte_perm(w[j], 0, 0x0123));
-                out[4 * k + j] = plain ? (Out)f : (Out)((double)f * bscale + bzero);
+        for (int u = 0; u < U; u++) {
+            const size_t k = base + (size_t)u * blockDim.x;
+            if (k >= nvec) break;
+            Out o[P];
+            if (ints) {
+#pragma unroll
+                for (int j = 0; j < P; j++) o[j] = (Out)(stored_int_of<BITPIX>(v[u].w, j) + ibias);
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const double st = stored_of<BITPIX>(v[u].w, j);
+                    o[j] = (Out)(plain ? st : __dadd_rn(__dmul_rn(st, bscale), bzero));
+                }
             }
+            if constexpr (sizeof(Out) == 4) ((float4*)out)[k] = make_float4(o[0], o[1], o[2], o[3]);
+            else ((double2*)out)[k] = make_double2(o[0], o[1]);
         }
-        for (size_t i = nvec * 4 + tid; i < count; i += nthreads) out[i] = (Out)fits_pixel(raw, i, bitpix, bzero, bscale);
-        return;
     }
-    for (size_t i = tid; i < count; i += nthreads) out[i] = (Out)fits_pixel(raw, i, bitpix, bzero, bscale);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = nvec * P + tid; i < count; i += nthreads) out[i] = (Out)fits_pixel(raw, i, BITPIX, bzero, bscale);
+}
+
+template <typename Out>
+inline void fits_decode_launch(const unsigned char* raw, int bitpix, double bzero, double bscale, size_t count, Out* out,
+                               unsigned max_ctas, cudaStream_t st) {
+    constexpr int P = 16 / (int)sizeof(Out);
+    const size_t want = (count / P + 256 * PM_FITS_UNROLL - 1) / (256 * PM_FITS_UNROLL);
+    const unsigned grid = (unsigned)(want < max_ctas ? (want > 0 ? want : 1) : max_ctas);
+    switch (bitpix) {
+        case 8:   pm_fits_decode_kernel<8, Out><<<grid, 256, 0, st>>>(raw, bzero, bscale, count, out); break;
+        case 16:  pm_fits_decode_kernel<16, Out><<<grid, 256, 0, st>>>(raw, bzero, bscale, count, out); break;
+        case 32:  pm_fits_decode_kernel<32, Out><<<grid, 256, 0, st>>>(raw, bzero, bscale, count, out); break;
+        case -32: pm_fits_decode_kernel<-32, Out><<<grid, 256, 0, st>>>(raw, bzero, bscale, count, out); break;
+        default:  pm_fits_decode_kernel<-64, Out><<<grid, 256, 0, st>>>(raw, bzero, bscale, count, out); break;
+    }
 }
 #endif
 

@@ -11,7 +11,9 @@ def cases(count=4099, seed=5):
     out = []
     for bitpix, bzero, bscale in ((16, 32768.0, 1.0),      # unsigned-16 convention of the bundled SDSS frames
                                   (16, 0.0, 1.0), (16, 1000.5, 0.25), (-32, 0.0, 1.0), (-32, 3.0, 2.0),
-                                  (8, 0.0, 1.0), (32, 0.0, 1.0), (32, -7.0, 0.5), (-64, 0.0, 1.0)):
+                                  (8, 0.0, 1.0), (32, 0.0, 1.0), (32, -7.0, 0.5), (-64, 0.0, 1.0),
+                                  (8, -128.0, 1.0), (16, 0.5, 1.0),          # signed-byte convention; non-integer zero point
+                                  (16, 3.3, 0.1), (32, 1.7, 1e-3), (-64, 0.1, 1.1), (-32, 0.3, 0.7)):   # a rounded multiply THEN a rounded add
         if bitpix == 8:
             stored = rng.integers(0, 256, count).astype(np.uint8)
         elif bitpix == 16:
