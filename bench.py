@@ -324,12 +324,13 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     abytes = algorithmic_bytes(n)
     achieved = B * abytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = dec_traffic = None
     tpath = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             traffic = tj.get("dram_bytes_per_galaxy") and tj["dram_bytes_per_galaxy"] * B
+            dec_traffic = tj.get("decode16_f32_dram_bytes_per_pixel") and tj["decode16_f32_dram_bytes_per_pixel"] * D * n * n
         except Exception:
             traffic = None
     # ---- CPU baseline (bounded sample, N = 1 only)
@@ -362,7 +363,7 @@ def run_ours(args):
                            "note": "same cutouts as integer counts in the FITS BITPIX 16 / BZERO 32768 wire format, decoded on the device"},
             "roofline_decode": {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / peak, "kernel": "pm_fits_decode_kernel<16, float>",
-                                "kernel_ms": dec_ms, "algorithmic_bytes_per_pixel": 6, "pixels": D * n * n, "traffic": None},
+                                "kernel_ms": dec_ms, "algorithmic_bytes_per_pixel": 6, "pixels": D * n * n, "traffic": dec_traffic},
             "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -141,6 +141,14 @@ int pm_aperpixmap_batch(int n, const double *rad, int64_t B, int nsubpix, double
 int pm_fits_decode_batch(const void *payload, int bitpix, double bzero, double bscale, int64_t count,
                          void *out, int out_dtype, void *cuda_stream);
 
+/* The same decode restricted to one npix x npix window per frame: `Cutout2D(image, position, (npix, npix), mode="strict").data`
+ * of Image.py:175-186 fused with the decode.  payload: DEVICE pointer to B frames of H x W big-endian pixels (aligned to the
+ * pixel size); origin: DEVICE int32 [B, 2] = (first row, first column) of each window, 0-based, the window inside the frame
+ * (the caller validates: a window that leaves the frame is the reference's PartialOverlapError, raised on the host);
+ * out: DEVICE [B, npix, npix] of out_dtype. */
+int pm_fits_decode_window_batch(const void *payload, int bitpix, double bzero, double bscale, int64_t B, int H, int W,
+                                const int32_t *origin, int npix, void *out, int out_dtype, void *cuda_stream);
+
 /* Library / device introspection (HOST). */
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);

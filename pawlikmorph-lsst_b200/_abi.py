@@ -37,7 +37,8 @@ class Outputs(C.Structure):
 
 
 EXPORTS = ("pm_debug_phase_cycles", "pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
-           "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch")
+           "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch",
+           "pm_fits_decode_window_batch")
 
 
 def declare(lib):
@@ -62,6 +63,9 @@ def declare(lib):
     lib.pm_aperpixmap_batch.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     lib.pm_fits_decode_batch.restype = C.c_int
     lib.pm_fits_decode_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    lib.pm_fits_decode_window_batch.restype = C.c_int
+    lib.pm_fits_decode_window_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     return lib
 
 

@@ -195,15 +195,22 @@ def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="c
 
 
 def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0, filter_size=3, flags=PM_DO_ALL,
-                         device="cuda:0", chunk=8192, **kw):
+                         device="cuda:0", chunk=8192, frame=None, origins=None, **kw):
     """Like analyse_host, but from the big-endian FITS pixel blocks of B cutouts of n x n pixels (`payload`: uint8
     numpy array / CPU tensor [B, n * n * bytes_per_pixel], pinned memory makes the copies asynchronous).  The bytes are
-    copied as they are and decoded on the device (image.decode_payload): 2 bytes per pixel on the wire for BITPIX 16."""
-    from .image import BYTES_PER_PIXEL, decode_payload
+    copied as they are and decoded on the device (image.decode_payload): 2 bytes per pixel on the wire for BITPIX 16.
+    With `frame=(H, W)` and `origins` (int32 [B, 2]: first row, first column) every payload row is a whole H x W frame
+    and the n x n window at its origin is analysed (image.decode_window: the cut-out of Image.py:175-186 on the device)."""
+    from .image import BYTES_PER_PIXEL, decode_payload, decode_window
     dev = torch.device(device)
     x = payload if torch.is_tensor(payload) else torch.from_numpy(np.ascontiguousarray(payload))
-    if x.dtype != torch.uint8 or x.ndim != 2 or x.shape[1] != n * n * BYTES_PER_PIXEL[bitpix]:
-        raise ValueError("payload must be uint8 [B, n * n * bytes_per_pixel]")
+    H, W = (int(frame[0]), int(frame[1])) if frame is not None else (n, n)
+    if x.dtype != torch.uint8 or x.ndim != 2 or x.shape[1] != H * W * BYTES_PER_PIXEL[bitpix]:
+        raise ValueError("payload must be uint8 [B, rows * columns * bytes_per_pixel]")
+    if frame is not None:
+        origins = torch.as_tensor(origins, dtype=torch.int32).reshape(-1, 2)
+        if origins.shape[0] != x.shape[0]:
+            raise ValueError("one window origin per frame")
     B = int(x.shape[0])
     chunk = max(1, min(int(chunk), B))
     key = (dev.type, dev.index, int(chunk), int(x.shape[1]), "payload")
@@ -229,7 +236,10 @@ def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0
         with torch.cuda.stream(st):
             d = h["bufs"][i & 1][:e - s]
             d.copy_(x[s:e], non_blocking=True)
-            img = decode_payload(d, bitpix, (e - s, n, n), bzero, bscale, torch.float32, stream=st)
+            if frame is None:
+                img = decode_payload(d, bitpix, (e - s, n, n), bzero, bscale, torch.float32, stream=st)
+            else:
+                img = decode_window(d, bitpix, (H, W), origins[s:e], n, bzero, bscale, torch.float32, stream=st)
             analyse_batch(img, sky_d[s:e], err_d[s:e], filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
     for st in h["streams"]:
         cur.wait_stream(st)

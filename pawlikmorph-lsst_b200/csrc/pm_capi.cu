@@ -223,4 +223,45 @@ int pm_fits_decode_batch(const void* payload, int bitpix, double bzero, double b
     return PM_OK;
 }
 
+int pm_fits_decode_window_batch(const void* payload, int bitpix, double bzero, double bscale, int64_t B, int H, int W,
+                                const int32_t* origin, int npix, void* out, int out_dtype, void* cuda_stream) {
+    g_err[0] = 0;
+    if (B == 0) return PM_OK;
+    const int bpp = fits_bytes_per_pixel(bitpix);
+    if (!payload || !out || !origin || B < 0 || bpp == 0 || H <= 0 || W <= 0 || npix <= 0 || npix > H || npix > W ||
+        (out_dtype != PM_F32 && out_dtype != PM_F64) || ((uintptr_t)payload % (uintptr_t)bpp) != 0) {
+        snprintf(g_err, sizeof g_err, "bad argument");
+        return PM_EINVAL;
+    }
+#ifndef PM_EMULATE
+    int rc = device_props();
+    if (rc != PM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const unsigned char* raw = (const unsigned char*)payload;
+    const unsigned max_ctas = 8u * (unsigned)g_sm_count;
+    const bool vec = npix % 4 == 0 && (((uintptr_t)out) & 15) == 0;
+    if (out_dtype == PM_F32) {
+        if (vec) fits_window_launch<float, 4>(raw, bitpix, bzero, bscale, B, H, W, origin, npix, (float*)out, max_ctas, st);
+        else fits_window_launch<float, 1>(raw, bitpix, bzero, bscale, B, H, W, origin, npix, (float*)out, max_ctas, st);
+    } else {
+        if (vec) fits_window_launch<double, 4>(raw, bitpix, bzero, bscale, B, H, W, origin, npix, (double*)out, max_ctas, st);
+        else fits_window_launch<double, 1>(raw, bitpix, bzero, bscale, B, H, W, origin, npix, (double*)out, max_ctas, st);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_fits_decode_window_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
+#else
+    (void)cuda_stream;
+    for (int64_t b = 0; b < B; b++)
+        for (int r = 0; r < npix; r++)
+            for (int c = 0; c < npix; c++) {
+                const size_t src = ((size_t)b * H + (size_t)(origin[2 * b] + r)) * W + (size_t)(origin[2 * b + 1] + c);
+                const double v = fits_pixel((const unsigned char*)payload, src, bitpix, bzero, bscale);
+                const size_t dst = ((size_t)b * npix + r) * npix + c;
+                if (out_dtype == PM_F32) ((float*)out)[dst] = (float)v; else ((double*)out)[dst] = v;
+            }
+#endif
+    g_launches.fetch_add(1);
+    return PM_OK;
+}
+
 }  // extern "C"

@@ -117,6 +117,56 @@ __global__ void __launch_bounds__(256) pm_fits_decode_kernel(const unsigned char
     for (size_t i = nvec * P + tid; i < count; i += nthreads) out[i] = (Out)fits_pixel(raw, i, BITPIX, bzero, bscale);
 }
 
+// Cut-out decode: out[b, r, c] = pixel (origin[2b] + r, origin[2b+1] + c) of frame b (H x W pixels), npix x npix per frame —
+// `Cutout2D(...).data` of Image.py:175-186 fused with the decode.  V consecutive pixels of one window row per thread
+// (V | npix): pixel-sized loads that a warp coalesces, one 16-byte (float) / two 16-byte (double) stores.
+template <int BITPIX> __device__ __forceinline__ double stored_at(const unsigned char* raw, size_t i) {
+    if (BITPIX == 8) return (double)__ldg(raw + i);
+    if (BITPIX == 16) return (double)(short)__byte_perm((unsigned)__ldg((const unsigned short*)raw + i), 0, 0x4401);
+    if (BITPIX == 32) return (double)(int)__byte_perm(__ldg((const unsigned*)raw + i), 0, 0x0123);
+    if (BITPIX == -32) return (double)__uint_as_float(__byte_perm(__ldg((const unsigned*)raw + i), 0, 0x0123));
+    const uint2 q = __ldg((const uint2*)raw + i);
+    return __hiloint2double((int)__byte_perm(q.x, 0, 0x0123), (int)__byte_perm(q.y, 0, 0x0123));
+}
+
+template <int BITPIX, typename Out, int V>
+__global__ void __launch_bounds__(256) pm_fits_window_kernel(const unsigned char* __restrict__ raw, double bzero, double bscale,
+                                                              long long B, int H, int W, const int* __restrict__ origin, int npix,
+                                                              Out* __restrict__ out) {
+    const bool plain = bscale == 1.0 && bzero == 0.0;
+    const size_t per = (size_t)npix * npix / V, total = (size_t)B * per, nthreads = (size_t)gridDim.x * blockDim.x;
+    const int rowv = npix / V;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+        const size_t b = t / per;
+        const int q = (int)(t - b * per), r = q / rowv, c = (q - r * rowv) * V;
+        const size_t src = (b * H + (size_t)(__ldg(origin + 2 * b) + r)) * W + (size_t)(__ldg(origin + 2 * b + 1) + c);
+        double st[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) st[j] = stored_at<BITPIX>(raw, src + j);
+        Out o[V];
+#pragma unroll
+        for (int j = 0; j < V; j++) o[j] = (Out)(plain ? st[j] : __dadd_rn(__dmul_rn(st[j], bscale), bzero));
+        Out* dst = out + t * V;
+        if constexpr (V == 4 && sizeof(Out) == 4) *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+        else if constexpr (V == 4) { ((double2*)dst)[0] = make_double2(o[0], o[1]); ((double2*)dst)[1] = make_double2(o[2], o[3]); }
+        else dst[0] = o[0];
+    }
+}
+
+template <typename Out, int V>
+inline void fits_window_launch(const unsigned char* raw, int bitpix, double bzero, double bscale, long long B, int H, int W,
+                               const int* origin, int npix, Out* out, unsigned max_ctas, cudaStream_t st) {
+    const size_t want = ((size_t)B * npix * npix / V + 255) / 256;
+    const unsigned grid = (unsigned)(want < max_ctas ? (want > 0 ? want : 1) : max_ctas);
+    switch (bitpix) {
+        case 8:   pm_fits_window_kernel<8, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;
+        case 16:  pm_fits_window_kernel<16, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;
+        case 32:  pm_fits_window_kernel<32, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;
+        case -32: pm_fits_window_kernel<-32, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;
+        default:  pm_fits_window_kernel<-64, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;
+    }
+}
+
 template <typename Out>
 inline void fits_decode_launch(const unsigned char* raw, int bitpix, double bzero, double bscale, size_t count, Out* out,
                                unsigned max_ctas, cudaStream_t st) {

@@ -6,8 +6,10 @@ What is kept: argument names and meaning of `calcMorphology` for this path (filt
 allAsymmetry, CAS, paramsaveFile), the flag logic of `_analyseImage` (main.py:469-491: A for -A/-Aall/-cas, As and As90
 for -As/-Aall, r20/r80/C/Gini/M20 for -cas, S never — main.py:494 is commented out — unless `smoothness=True`), the
 default Result for a frame whose centre is too faint (main.py:420-424), the CSV header and row format.
-What is not here: the WCS cut-out (frames are analysed whole, which is what `npix` larger
-than the frame gives, Image.py:135-138), `skybgr` (sky / sky_err are inputs, or the clipped border estimate below,
+The cut-out of Image.py:135-138, :175-186 is kept too: with `npix` not larger than the frame and truthy ra / dec the
+npix x npix window around the catalogue position is analysed (sky -> pixel on the host, the copy fused with the decode
+on the device); otherwise the whole frame, like the reference.
+What is not here: `skybgr` (sky / sky_err are inputs, or the clipped border estimate below,
 which is also what the committed goldens used), `maskstarsSEG` cleaning (unseeded noise, imageutils.py:86), star
 catalogues, Sersic fits, diagnostic plots.  Options that would need them raise NotImplementedError.
 """
@@ -18,7 +20,7 @@ import time
 import numpy as np
 
 from . import _abi
-from .image import BYTES_PER_PIXEL, payload_of
+from .image import BYTES_PER_PIXEL, cutout_origin, payload_of, sky_to_pixel
 from .result import CSV_HEADER, Result
 
 _NP = {8: ">u1", 16: ">i2", 32: ">i4", -32: ">f4", -64: ">f8"}
@@ -70,7 +72,9 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
 
     sky: None (border_sky of every frame), a callable image -> (sky, sky_err), or a sequence of (sky, sky_err) pairs.
     root: folder the file names are relative to.  parallelLibrary / cores are accepted and ignored: the batch is the
-    parallelism.  ra / dec are carried but unused (no WCS cut-out: whole frames)."""
+    parallelism.  npix: None analyses whole frames; a number takes the npix x npix window around (ra, dec) whenever the
+    frame has at least npix rows and ra and dec are truthy (Image.py:135 — a declination of exactly 0 gives the whole
+    frame, as upstream); a window that leaves the frame raises image.PartialOverlapError like `Cutout2D(mode="strict")`."""
     for name, val in (("calculateSersic", calculateSersic), ("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
                       ("catalogue", catalogue), ("largeImage", largeImage), ("segmap", segmap), ("starMask", starMask)):
         if val:
@@ -83,23 +87,41 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
         path = f if root is None or os.path.isabs(f) else os.path.join(str(root), f)
         with open(path, "rb") as fh:
             payload, hdr = payload_of(fh.read())
-        if hdr.get("NAXIS", 2) != 2 or hdr["NAXIS1"] != hdr["NAXIS2"]:
-            raise ValueError(f"{f}: the path analyses square 2-D frames, got NAXIS1={hdr.get('NAXIS1')} NAXIS2={hdr.get('NAXIS2')}")
+        if hdr.get("NAXIS", 2) != 2:
+            raise ValueError(f"{f}: not a 2-D image")
+        H, W = hdr["NAXIS2"], hdr["NAXIS1"]
+        ra, dec = infos[i][1], infos[i][2]
+        if npix is not None and H >= npix and ra and dec:                      # Image.py:135-136
+            n = int(npix)
+            x, y = sky_to_pixel(hdr, ra, dec)
+            if str(hdr.get("CTYPE1", ""))[:1] == "D":                             # Image.py:179-182: upstream swaps the position
+                x, y = y, x                                                       # for reversed-axis headers (astropy #10468)
+            origin = cutout_origin(x, y, n, (H, W))
+        else:
+            if H != W:
+                raise ValueError(f"{f}: whole frames must be square, got {H} x {W}")
+            n, origin = H, None
+        pixels = None
         if sky is None or callable(sky):
-            s = (sky or border_sky)(_host_pixels(payload, hdr))
+            pixels = _host_pixels(payload, hdr)
+            if origin is not None:
+                pixels = pixels[origin[0]:origin[0] + n, origin[1]:origin[1] + n]
+            s = (sky or border_sky)(pixels)
         else:
             s = sky[i]
-        frames.append((payload, float(s[0]), float(s[1])))
-        key = (hdr["NAXIS1"], hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)))
+        frames.append((payload, float(s[0]), float(s[1]), origin))
+        key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)))
         groups.setdefault(key, []).append(i)
     flags = path_flags(asymmetry, shapeAsymmetry, allAsymmetry, CAS, smoothness)
     rows = np.empty((len(infos), _abi.ROW_DOUBLES))
-    for (n, bitpix, bzero, bscale), idx in groups.items():
-        pay = np.empty((len(idx), n * n * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
+    for (n, H, W, windowed, bitpix, bzero, bscale), idx in groups.items():
+        pay = np.empty((len(idx), H * W * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
         for k, i in enumerate(idx):
             pay[k] = np.frombuffer(frames[i][0], dtype=np.uint8)
+        win = dict(frame=(H, W), origins=np.array([frames[i][3] for i in idx], dtype=np.int32)) if windowed else {}
         rows[idx] = analyse_host_payload(pay, bitpix, n, np.array([frames[i][1] for i in idx]), np.array([frames[i][2] for i in idx]),
-                                         bzero=bzero, bscale=bscale, filter_size=filterSize, flags=flags, device=device, chunk=chunk)
+                                         bzero=bzero, bscale=bscale, filter_size=filterSize, flags=flags, device=device, chunk=chunk,
+                                         **win)
     per_image = (time.time() - t0) / max(1, len(infos))
     results = []
     for i, (f, _, _) in enumerate(infos):

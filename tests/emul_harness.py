@@ -114,3 +114,15 @@ def fits_decode(payload, bitpix, count, bzero=0.0, bscale=1.0, dtype=np.float32)
                                 abi.PM_F32 if dtype == np.float32 else abi.PM_F64, None)
     abi.check(L, rc, "pm_fits_decode_batch")
     return out
+
+
+def fits_decode_window(payload, bitpix, B, H, W, origins, npix, bzero=0.0, bscale=1.0, dtype=np.float32):
+    L = lib()
+    raw = np.ascontiguousarray(np.frombuffer(payload, dtype=np.uint8))
+    org = np.ascontiguousarray(np.asarray(origins, dtype=np.int32).reshape(B, 2))
+    out = np.empty((B, npix, npix), dtype=dtype)
+    rc = L.pm_fits_decode_window_batch(raw.ctypes.data, int(bitpix), float(bzero), float(bscale), int(B), int(H), int(W),
+                                       org.ctypes.data, int(npix), out.ctypes.data,
+                                       abi.PM_F32 if dtype == np.float32 else abi.PM_F64, None)
+    abi.check(L, rc, "pm_fits_decode_window_batch")
+    return out

@@ -32,3 +32,11 @@ def cases(count=4099, seed=5):
             want = want * bscale + bzero
         out.append((bitpix, bzero, bscale, payload, want))
     return out
+
+
+def window_cases(B=3, H=37, W=41, seed=9):
+    """(bitpix, bzero, bscale, payload bytes of B frames, float64 frames [B, H, W]) for the cut-out decode."""
+    out = []
+    for bitpix, bzero, bscale, payload, want in cases(B * H * W, seed):
+        out.append((bitpix, bzero, bscale, payload, want.reshape(B, H, W)))
+    return out

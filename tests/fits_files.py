@@ -13,7 +13,8 @@ def _card(key, val, comment=""):
     return f"{key:<8}= {v}{' / ' + comment if comment else ''}".ljust(80)[:80]
 
 
-def fits_bytes(img, bitpix=16):
+def fits_bytes(img, bitpix=16, extra=None):
+    """extra: further header cards (e.g. the WCS cards of tests/golden/sdss_wcs.json) in place of the bare CTYPE1."""
     img = np.asarray(img)
     cards = [_card("SIMPLE", True, "conforms to FITS standard"), _card("BITPIX", bitpix), _card("NAXIS", 2),
              _card("NAXIS1", img.shape[1]), _card("NAXIS2", img.shape[0])]
@@ -24,7 +25,11 @@ def fits_bytes(img, bitpix=16):
         data = img.astype(">f4").tobytes()
     else:
         raise ValueError(bitpix)
-    cards += [_card("CTYPE1", "RA---TAN"), "END".ljust(80)]
+    if extra:
+        cards += [_card(k, v) for k, v in extra.items() if not k.startswith("NAXIS")]
+    else:
+        cards.append(_card("CTYPE1", "RA---TAN"))
+    cards.append("END".ljust(80))
     head = "".join(cards).encode("ascii")
     head += b" " * (-len(head) % 2880)
     return head + data + b"\0" * (-len(data) % 2880)

@@ -86,3 +86,55 @@ def test_driver_dataflow_on_the_emulator_build(tmp_path, monkeypatch):
     import pytest
     with pytest.raises(NotImplementedError):
         pm.main.calcMorphology(infos, tmp_path / "out", calculateSersic=True, root=tmp_path)
+
+
+def _wcs_by_name():
+    import json
+    import os
+    J = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdss_wcs.json")))
+    return {e["file"].split("/")[-1]: e for e in J}
+
+
+def test_driver_cutout_on_the_emulator_build(tmp_path, monkeypatch):
+    """-s 128 (imganalysis.py:36): the 128 x 128 window around the catalogue position, cut on the 'device' (CPU build of
+    the window decode), analysed by the CPU build of the kernel, against the oracle run on the numpy slice."""
+    from oracle import pm_oracle as O
+    from tests import emul_harness as H
+    from tests.golden_util import compare_row
+    g = P.golden("sdss_l")
+    wcs = _wcs_by_name()
+    seen = {}
+
+    def fake(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0, filter_size=3, flags=15, frame=None, origins=None, **kw):
+        assert frame is not None and n == 128
+        x = np.concatenate([H.fits_decode_window(p.tobytes(), bitpix, 1, frame[0], frame[1], origins[k], n, bzero, bscale, np.float32)
+                            for k, p in enumerate(payload)])
+        seen[frame] = x
+        return H.analyse(x, sky, sky_err, filter_size, flags, want=("segmap",))["rows"]
+
+    import pawlikmorph_lsst_b200.batch as batch
+    monkeypatch.setattr(batch, "analyse_host_payload", fake)
+    infos, pick = [], [29, 31]                                           # the 177- and 180-pixel frames
+    for i in pick:
+        name = str(g.z["names"][i])
+        (tmp_path / name).write_bytes(fits_bytes(g.image(i), 16, extra=wcs[name]["header"]))
+        infos.append((name, wcs[name]["ra"], wcs[name]["dec"]))
+    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, smoothness=True, root=tmp_path)
+    for k, i in enumerate(pick):
+        h = wcs[infos[k][0]]["header"]
+        r0, c0 = pm.image.cutout_origin(*pm.image.sky_to_pixel(h, infos[k][1], infos[k][2]), 128, g.image(i).shape)
+        win = g.image(i)[r0:r0 + 128, c0:c0 + 128].astype(np.float64)
+        assert np.array_equal(seen[g.image(i).shape][0], win)
+        assert (res[k].sky, res[k].sky_err) == pm.main.border_sky(win)
+        want, _, _ = O.analyse(win, res[k].sky, res[k].sky_err, 3)
+        r = res[k]
+        got = dict(apix_col=r.apix[0], apix_row=r.apix[1], rmax=r.rmax, r20=r.r20, r80=r.r80, C=r.C, A=r.A[0], Abgr=r.A[1], S=r.S,
+                   As=r.As[0], As90=r.As90[0], gini=r.gini, m20=r.m20, object_edge=float(r.objectEdge), status=r.status)
+        errs = compare_row(got, want, P.RTOL, f"sdss_l[{i}] window ")
+        assert not errs, "\n".join(errs)
+    # dec == 0 is falsy upstream (Image.py:135): the whole frame is analysed
+    seen.clear()
+    monkeypatch.setattr(batch, "analyse_host_payload", lambda payload, bitpix, n, *a, frame=None, **kw: (
+        seen.setdefault("n", n), np.full((len(payload), 16), -99.0))[1])
+    pm.main.calcMorphology([(infos[0][0], infos[0][1], 0.0)], tmp_path / "out", npix=128, root=tmp_path)
+    assert seen["n"] == 177

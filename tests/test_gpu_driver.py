@@ -48,3 +48,42 @@ def test_calcMorphology_on_the_sdss_frames(name, tmp_path):
                                    CAS=False, paramsaveFile="a.csv", root=tmp_path)
     for i, r in enumerate(res_a):
         assert r.A == res[i].A and r.As == [-99., -99.] and r.C == -99. and r.gini == -99. and r.S == -99.
+
+
+def test_calcMorphology_cutouts_of_the_catalogue_positions(tmp_path):
+    """imganalysis.py's default -s 128: the window around every row of images.csv (WCS cards of the reference's frames,
+    tests/golden/sdss_wcs.json), cut and decoded on the device — bit-identical to the float host call on numpy slices, and
+    within tolerance of the oracle on a few of them."""
+    import json
+    import os
+
+    import pawlikmorph_lsst_b200 as pm
+    from oracle import pm_oracle as O
+    g = P.golden("sdss_l")
+    J = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdss_wcs.json")))
+    index = {str(nm): i for i, nm in enumerate(g.z["names"])}
+    infos, wins = [], []
+    (tmp_path / "sample").mkdir()
+    for k, e in enumerate(J):
+        i = index[e["file"].split("/")[-1]]
+        img = g.image(i)
+        (tmp_path / e["file"]).write_bytes(fits_bytes(img, -32 if k % 5 == 2 else 16, extra=e["header"]))
+        infos.append((e["file"], e["ra"], e["dec"]))
+        r0, c0 = pm.image.cutout_origin(*pm.image.sky_to_pixel(e["header"], e["ra"], e["dec"]), 128, img.shape)
+        wins.append(img[r0:r0 + 128, c0:c0 + 128].astype(np.float32))
+    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, smoothness=True, root=tmp_path)
+    sky = np.array([r.sky for r in res]), np.array([r.sky_err for r in res])
+    for k, r in enumerate(res):
+        assert (r.sky, r.sky_err) == pm.main.border_sky(wins[k])
+    rows = pm.batch.analyse_host(np.stack(wins), sky[0], sky[1], 3, 15)
+    for k, r in enumerate(res):
+        d = dict(zip(pm._abi.ROW_FIELDS, rows[k]))
+        if d["status"] == 1:
+            assert r.status == 1 and r.A == [-99., -99.]
+            continue
+        assert [r.apix[0], r.apix[1], r.rmax, r.r20, r.r80, r.C, r.A[0], r.A[1], r.S, r.As[0], r.As90[0], r.gini, r.m20] == \
+            [d[f] for f in ("apix_col", "apix_row", "rmax", "r20", "r80", "C", "A", "Abgr", "S", "As", "As90", "gini", "m20")], infos[k][0]
+    for k in (0, 17, 40):
+        want, _, _ = O.analyse(wins[k].astype(np.float64), res[k].sky, res[k].sky_err, 3)
+        errs = compare_row(dict(zip(pm._abi.ROW_FIELDS, rows[k])), want, P.RTOL, f"window[{k}] ")
+        assert not errs, "\n".join(errs)

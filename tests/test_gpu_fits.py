@@ -37,3 +37,20 @@ def test_payload_host_api_equals_the_float_api():
     f = pm.batch.analyse_host_payload(np.frombuffer(x.astype(">f4").tobytes(), dtype=np.uint8).reshape(6, -1), -32, 64, 100.0, 5.0,
                                       filter_size=3, flags=15, chunk=4)
     assert np.array_equal(a, f)
+
+
+@pytest.mark.parametrize("npix", [20, 7, 36])
+def test_window_decode_every_bitpix_on_the_gpu(npix):
+    import torch
+
+    import pawlikmorph_lsst_b200 as pm
+    from tests.fits_cases import window_cases
+    org = np.array([[0, 0], [1, 5], [0, 3]], dtype=np.int32)
+    for bitpix, bzero, bscale, payload, frames in window_cases():
+        raw = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
+        for dt, npdt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+            got = pm.image.decode_window(raw, bitpix, (37, 41), org, npix, bzero, bscale, dt).cpu().numpy()
+            want = np.stack([frames[b, org[b, 0]:org[b, 0] + npix, org[b, 1]:org[b, 1] + npix] for b in range(3)]).astype(npdt)
+            assert np.array_equal(got, want), (bitpix, bzero, bscale, dt)
+    with pytest.raises(pm.image.PartialOverlapError):
+        pm.image.decode_window(raw, bitpix, (37, 41), org + 10, 36)
