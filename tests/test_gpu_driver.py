@@ -87,3 +87,9 @@ def test_calcMorphology_cutouts_of_the_catalogue_positions(tmp_path):
         want, _, _ = O.analyse(wins[k].astype(np.float64), res[k].sky, res[k].sky_err, 3)
         errs = compare_row(dict(zip(pm._abi.ROW_FIELDS, rows[k])), want, P.RTOL, f"window[{k}] ")
         assert not errs, "\n".join(errs)
+
+
+def test_calcMorphology_with_an_empty_list_writes_the_header(tmp_path):
+    import pawlikmorph_lsst_b200 as pm
+    assert pm.main.calcMorphology([], tmp_path / "o") == []
+    assert list(csv.reader(open(tmp_path / "o" / "parameters.csv"))) == [pm.result.CSV_HEADER]
