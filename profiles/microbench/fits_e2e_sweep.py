@@ -64,6 +64,8 @@ print(json.dumps({"kernel": "pm_fits_window_kernel<16, float, 4>", "frames": Bw,
 del raw, out, org_d
 
 # ---- (2) host calls
+if "--kernels-only" in sys.argv:
+    sys.exit(0)
 for E, chunk in ((8192, 512), (8192, 1024), (8192, 2048), (32768, 1024), (32768, 2048), (32768, 4096)):
     x = torch.cat([synth.make_batch(4096, n, 7 + k, device=dev) for k in range(E // 4096)]).round_().clamp_(0, 65535)
     pay = (x.to(torch.int32) - 32768).to(torch.int16).cpu().numpy().astype(">i2")
