@@ -149,6 +149,16 @@ int pm_fits_decode_batch(const void *payload, int bitpix, double bzero, double b
 int pm_fits_decode_window_batch(const void *payload, int bitpix, double bzero, double bscale, int64_t B, int H, int W,
                                 const int32_t *origin, int npix, void *out, int out_dtype, void *cuda_stream);
 
+/* Sky-region statistics of skyBackground._calcSkybgr (skyBackground.py:134-164, `_getSkyRegion` :265-303) for a batch:
+ * pixels whose centre lies outside the ellipse of semi-axes a, b (= 2 min / 2 max of the fitted FWHMs) and angle theta
+ * about (n/2 + 1, n/2 + 1); count, mean, median, population std; when mean > median, sigma_clipped_stats(sigma=3,
+ * maxiters=5) and sky = 3 median - 2 mean, else sky = mean.  images: DEVICE [B, n, n] of dtype; ellipse: DEVICE double
+ * [B, 4] = (a, b, cos theta, sin theta); out: DEVICE double [B, PM_SKY_COLS] = count, mean, median, std, clip iterations,
+ * clipped count, mean, median, std, sky, sky_err, status (1 = fewer than 100 sky pixels, the reference's _SkyError).
+ * The Gaussian fit that yields (fwhms, theta) is the caller's (skyBackground.py:306-395). */
+#define PM_SKY_COLS 12
+int pm_sky_stats_batch(const void *images, int dtype, int64_t B, int n, const double *ellipse, double *out, void *cuda_stream);
+
 /* Library / device introspection (HOST). */
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);

@@ -38,7 +38,10 @@ class Outputs(C.Structure):
 
 EXPORTS = ("pm_debug_phase_cycles", "pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
            "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch",
-           "pm_fits_decode_window_batch")
+           "pm_fits_decode_window_batch", "pm_sky_stats_batch")
+PM_SKY_COLS = 12
+SKY_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_count", "clipped_mean", "clipped_median", "clipped_std",
+              "sky", "sky_err", "status")
 
 
 def declare(lib):
@@ -63,6 +66,8 @@ def declare(lib):
     lib.pm_aperpixmap_batch.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     lib.pm_fits_decode_batch.restype = C.c_int
     lib.pm_fits_decode_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    lib.pm_sky_stats_batch.restype = C.c_int
+    lib.pm_sky_stats_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_fits_decode_window_batch.restype = C.c_int
     lib.pm_fits_decode_window_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]

@@ -8,7 +8,7 @@ REPO = os.path.dirname(HERE)
 # PM_LIB_VARIANT=<threads>x<ctas> selects an experimental build (tuning runs only), e.g. 256x2
 VARIANT = os.environ.get("PM_LIB_VARIANT", "")
 SO = os.path.join(HERE, "libpawlik_b200.so" if not VARIANT else f"libpawlik_b200_{VARIANT}.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh", "pm_sky.cuh")] + \
     [os.path.join(REPO, "include", "pawlik_b200.h")]
 
 

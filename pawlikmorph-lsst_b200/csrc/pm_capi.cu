@@ -11,6 +11,7 @@
 
 #include "pm_kernels.cuh"
 #include "pm_fits.cuh"
+#include "pm_sky.cuh"
 
 using namespace pmk;
 
@@ -27,6 +28,10 @@ template <typename T> __global__ void __launch_bounds__(kThreads, PM_MIN_CTAS) p
 __global__ void __launch_bounds__(kThreads, 1)
 pm_aperpixmap_kernel(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out, unsigned smem_bytes) {
     aperpixmap_body(n, rad, B, ns, frac, mask_out, smem_bytes);
+}
+template <typename T> __global__ void __launch_bounds__(kThreads, 2)
+pm_sky_stats_kernel(const T* images, long long B, int n, const double* ellipse, double* out) {
+    sky_body<T>(images, B, n, ellipse, out);
 }
 static thread_local int g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0, g_dev = -1;
 static thread_local size_t g_smem_optin = 0;
@@ -259,6 +264,35 @@ int pm_fits_decode_window_batch(const void* payload, int bitpix, double bzero, d
                 const size_t dst = ((size_t)b * npix + r) * npix + c;
                 if (out_dtype == PM_F32) ((float*)out)[dst] = (float)v; else ((double*)out)[dst] = v;
             }
+#endif
+    g_launches.fetch_add(1);
+    return PM_OK;
+}
+
+int pm_sky_stats_batch(const void* images, int dtype, int64_t B, int n, const double* ellipse, double* out, void* cuda_stream) {
+    g_err[0] = 0;
+    if (B == 0) return PM_OK;
+    if (!images || !ellipse || !out || B < 0 || n < 1 || n > 4096 || (dtype != PM_F32 && dtype != PM_F64)) {
+        snprintf(g_err, sizeof g_err, "bad argument");
+        return PM_EINVAL;
+    }
+    const unsigned smem = sky_smem_bytes();
+#ifndef PM_EMULATE
+    int rc = device_props();
+    if (rc != PM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long grid = B < 8LL * g_sm_count ? B : 8LL * g_sm_count;
+    if (dtype == PM_F32) pm_sky_stats_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, ellipse, out);
+    else pm_sky_stats_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, B, n, ellipse, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_sky_stats_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
+#else
+    (void)cuda_stream;
+    const long long grid = B < 4 ? B : 4;
+    for (long long blk = 0; blk < grid; blk++) {
+        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { sky_body<float>((const float*)images, B, n, ellipse, out); });
+        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { sky_body<double>((const double*)images, B, n, ellipse, out); });
+    }
 #endif
     g_launches.fetch_add(1);
     return PM_OK;

@@ -126,3 +126,19 @@ def fits_decode_window(payload, bitpix, B, H, W, origins, npix, bzero=0.0, bscal
                                        abi.PM_F32 if dtype == np.float32 else abi.PM_F64, None)
     abi.check(L, rc, "pm_fits_decode_window_batch")
     return out
+
+
+def sky_stats(images, fwhms, theta):
+    import math
+    L = lib()
+    x = np.ascontiguousarray(images)
+    B, n = x.shape[0], x.shape[1]
+    f = np.asarray(fwhms, dtype=np.float64).reshape(B, 2)
+    ell = np.empty((B, 4))
+    ell[:, 0], ell[:, 1] = 2.0 * f.min(axis=1), 2.0 * f.max(axis=1)
+    ell[:, 2], ell[:, 3] = [math.cos(v) for v in theta], [math.sin(v) for v in theta]
+    out = np.empty((B, abi.PM_SKY_COLS))
+    rc = L.pm_sky_stats_batch(x.ctypes.data, abi.PM_F32 if x.dtype == np.float32 else abi.PM_F64, B, n, ell.ctypes.data,
+                              out.ctypes.data, None)
+    abi.check(L, rc, "pm_sky_stats_batch")
+    return out
