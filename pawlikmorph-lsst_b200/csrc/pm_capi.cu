@@ -272,19 +272,24 @@ int pm_fits_decode_window_batch(const void* payload, int bitpix, double bzero, d
 int pm_sky_stats_batch(const void* images, int dtype, int64_t B, int n, const double* ellipse, double* out, void* cuda_stream) {
     g_err[0] = 0;
     if (B == 0) return PM_OK;
-    if (!images || !ellipse || !out || B < 0 || n < 1 || n > 4096 || (dtype != PM_F32 && dtype != PM_F64)) {
+    if (!images || !ellipse || !out || B < 0 || n < 1 || n > PM_MAX_N || (dtype != PM_F32 && dtype != PM_F64)) {
         snprintf(g_err, sizeof g_err, "bad argument");
         return PM_EINVAL;
     }
-    const unsigned smem = sky_smem_bytes();
+    const unsigned smem = sky_smem_bytes(n);
 #ifndef PM_EMULATE
     int rc = device_props();
     if (rc != PM_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const long long grid = B < 8LL * g_sm_count ? B : 8LL * g_sm_count;
-    if (dtype == PM_F32) pm_sky_stats_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, ellipse, out);
-    else pm_sky_stats_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, B, n, ellipse, out);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = dtype == PM_F32
+        ? cudaFuncSetAttribute(pm_sky_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(pm_sky_stats_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        if (dtype == PM_F32) pm_sky_stats_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, ellipse, out);
+        else pm_sky_stats_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, B, n, ellipse, out);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_sky_stats_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
 #else
     (void)cuda_stream;

@@ -17,6 +17,8 @@ def cases(n=64, B=6, seed=3, dtype=np.float32):
     x[1] = 100.0 + rng.normal(0, 5, (n, n))
     x[1][rng.integers(0, n, 40), rng.integers(0, n, 40)] -= 80.0                 # negative outliers: mean < median
     x[2] = np.rint(x[2])                                                           # ties in the median
+    x[3] -= 100.0                                                                  # values of both signs
+    x[3][5, 7], x[3][6, 9], x[3][n - 2, 3] = -0.0, 0.0, -0.0
     fw = np.array([[3.0, 4.5], [2.0, 2.0], [5.0, 3.0], [1.5, 1.0], [n * 0.3, n * 0.45], [2.5, 6.0]])[:B]
     th = np.array([0.3, 0.0, 1.2, -0.7, 0.9, 2.5])[:B]
     return x.astype(dtype), fw, th
