@@ -45,16 +45,29 @@ template <typename T> struct SkySet {      // the statistics set: sky-region pix
     double lo, hi;
 };
 
-// f(x) for every member of the set: one row per warp, one 32-column word per step (coalesced loads)
+// f(x) for every member of the set: one row per warp, 32 columns per word; the loads of kSkyGroup words are issued
+// together (unconditionally, the object pixels are few) so that a lane has that many L2 requests in flight
+constexpr int kSkyGroup = 8;
 template <typename T, typename F> PM_DEV void sky_for_each(const SkySet<T>& s, F&& f) {
     for (int r = pm::warp(); r < s.n; r += kWarps) {
         const T* row = s.img + (size_t)r * s.n;
-        for (int wi = 0; wi < s.nw; wi++) {
-            const unsigned bits = s.mask[r * s.nw + wi];
-            if ((bits >> pm::lane()) & 1u) {
-                const T x = pm::ldg(row + wi * 32 + pm::lane());
-                const double v = (double)x;
-                if (v >= s.lo && v <= s.hi) f(x);
+        const unsigned* mrow = s.mask + r * s.nw;
+        for (int w0 = 0; w0 < s.nw; w0 += kSkyGroup) {
+            T xv[kSkyGroup];
+            unsigned bits[kSkyGroup];
+#pragma unroll
+            for (int j = 0; j < kSkyGroup; j++) {
+                const int wi = w0 + j, c = wi * 32 + pm::lane();
+                const bool ok = wi < s.nw && c < s.n;
+                xv[j] = ok ? pm::ldg(row + c) : (T)0;
+                bits[j] = wi < s.nw ? mrow[wi] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < kSkyGroup; j++) {
+                if ((bits[j] >> pm::lane()) & 1u) {
+                    const double v = (double)xv[j];
+                    if (v >= s.lo && v <= s.hi) f(xv[j]);
+                }
             }
         }
     }
