@@ -195,12 +195,15 @@ def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="c
 
 
 def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0, filter_size=3, flags=PM_DO_ALL,
-                         device="cuda:0", chunk=8192, frame=None, origins=None, **kw):
+                         device="cuda:0", chunk=8192, frame=None, origins=None, gauss=None, sky_rows_out=None, **kw):
     """Like analyse_host, but from the big-endian FITS pixel blocks of B cutouts of n x n pixels (`payload`: uint8
     numpy array / CPU tensor [B, n * n * bytes_per_pixel], pinned memory makes the copies asynchronous).  The bytes are
     copied as they are and decoded on the device (image.decode_payload): 2 bytes per pixel on the wire for BITPIX 16.
     With `frame=(H, W)` and `origins` (int32 [B, 2]: first row, first column) every payload row is a whole H x W frame
-    and the n x n window at its origin is analysed (image.decode_window: the cut-out of Image.py:175-186 on the device)."""
+    and the n x n window at its origin is analysed (image.decode_window: the cut-out of Image.py:175-186 on the device).
+    With `gauss=(fwhms [B, 2], theta [B])` — the Gaussian fit of skyBackground.py:167-262 — `sky` / `sky_err` are not
+    read: they are measured on the device from the sky region of every decoded cutout (skyBackground.sky_stats_batch)
+    and feed the analysis without leaving the GPU; `sky_rows_out` (numpy [B, 12]) receives the statistics."""
     from .image import BYTES_PER_PIXEL, decode_payload, decode_window
     dev = torch.device(device)
     x = payload if torch.is_tensor(payload) else torch.from_numpy(np.ascontiguousarray(payload))
@@ -223,8 +226,15 @@ def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0
         h["rows_d"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev)
         h["rows_h"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
     cur = torch.cuda.current_stream(dev)
-    sky_d = _per_galaxy(sky, B, dev, "sky")
-    err_d = _per_galaxy(sky_err, B, dev, "sky_err")
+    if gauss is None:
+        sky_d = _per_galaxy(sky, B, dev, "sky")
+        err_d = _per_galaxy(sky_err, B, dev, "sky_err")
+        skyrows_d = None
+    else:
+        from .skyBackground import sky_stats_batch
+        g_fw = np.asarray(gauss[0], dtype=np.float64).reshape(B, 2)
+        g_th = np.broadcast_to(np.asarray(gauss[1], dtype=np.float64), (B,))
+        skyrows_d = torch.empty((B, _abi.PM_SKY_COLS), dtype=torch.float64, device=dev)
     ready = torch.cuda.Event()
     ready.record(cur)
     rows_d = h["rows_d"]
@@ -240,12 +250,20 @@ def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0
                 img = decode_payload(d, bitpix, (e - s, n, n), bzero, bscale, torch.float32, stream=st)
             else:
                 img = decode_window(d, bitpix, (H, W), origins[s:e], n, bzero, bscale, torch.float32, stream=st)
-            analyse_batch(img, sky_d[s:e], err_d[s:e], filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
+            if gauss is None:
+                sk, er = sky_d[s:e], err_d[s:e]
+            else:
+                sr = sky_stats_batch(img, g_fw[s:e], g_th[s:e], stream=st)
+                skyrows_d[s:e].copy_(sr)
+                sk, er = sr[:, 9].contiguous(), sr[:, 10].contiguous()
+            analyse_batch(img, sk, er, filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
     for st in h["streams"]:
         cur.wait_stream(st)
     rows_h = h["rows_h"][:B]
     rows_h.copy_(rows_d[:B], non_blocking=True)
     cur.synchronize()
+    if skyrows_d is not None and sky_rows_out is not None:
+        sky_rows_out[...] = skyrows_d.cpu().numpy()
     return rows_h.numpy().copy()
 
 

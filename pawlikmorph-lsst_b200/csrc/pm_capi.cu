@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 pm_aperpixmap_kernel(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out, unsigned smem_bytes) {
     aperpixmap_body(n, rad, B, ns, frac, mask_out, smem_bytes);
 }
-template <typename T> __global__ void __launch_bounds__(kThreads, 2)
+template <typename T> __global__ void __launch_bounds__(kThreads, 3)
 pm_sky_stats_kernel(const T* images, long long B, int n, const double* ellipse, double* out) {
     sky_body<T>(images, B, n, ellipse, out);
 }

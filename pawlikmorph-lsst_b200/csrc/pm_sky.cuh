@@ -47,6 +47,8 @@ template <typename T> struct SkySet {      // the statistics set: sky-region pix
 
 // f(x) for every member of the set: one row per warp, 32 columns per word; the loads of kSkyGroup words are issued
 // together (unconditionally, the object pixels are few) so that a lane has that many L2 requests in flight
+// (Measured alternatives at 256^2: the plane walked as one flat list of words, 8 per step: 417k cutouts/s; 16 per step:
+// 127 registers, 2 CTAs per SM, 419k; this row form: 516k; one word per step with a predicated load: 180k.)
 constexpr int kSkyGroup = 8;
 template <typename T, typename F> PM_DEV void sky_for_each(const SkySet<T>& s, F&& f) {
     for (int r = pm::warp(); r < s.n; r += kWarps) {

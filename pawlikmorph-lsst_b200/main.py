@@ -66,11 +66,15 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                    numberSigmas=5., asymmetry=False, shapeAsymmetry=False, allAsymmetry=True, calculateSersic=False,
                    saveSegMap=False, saveCleanImage=False, imageSource=None, catalogue=None, largeImage=False,
                    paramsaveFile="parameters.csv", occludedSaveFile="occluded-object-locations.csv", segmap=False,
-                   starMask=False, CAS=True, *, sky=None, smoothness=False, root=None, device="cuda:0", chunk=8192):
+                   starMask=False, CAS=True, *, sky=None, gauss=None, smoothness=False, root=None, device="cuda:0", chunk=8192):
     """Analyse the frames of `imageInfos` (iterable of (filename, ra, dec), e.g. helpers.getFiles) and write
     `outfolder/paramsaveFile`; returns the list of Result in input order.
 
     sky: None (border_sky of every frame), a callable image -> (sky, sky_err), or a sequence of (sky, sky_err) pairs.
+    gauss: a sequence of (fwhms, theta) per image — the Gaussian fit of skyBackground.py:167-262, which is the caller's —
+    makes sky / sky_err the reference's own estimate: the statistics of the pixels outside the ellipse of semi-axes
+    2 min(fwhms), 2 max(fwhms) (skyBackground.py:134-164), measured on the device from the decoded cutout
+    (pm_sky_stats_batch); a sky region of fewer than 100 pixels raises skyBackground._SkyError like upstream.
     root: folder the file names are relative to.  parallelLibrary / cores are accepted and ignored: the batch is the
     parallelism.  npix: None analyses whole frames; a number takes the npix x npix window around (ra, dec) whenever the
     frame has at least npix rows and ra and dec are truthy (Image.py:135 — a declination of exactly 0 gives the whole
@@ -102,14 +106,16 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                 raise ValueError(f"{f}: whole frames must be square, got {H} x {W}")
             n, origin = H, None
         pixels = None
-        if sky is None or callable(sky):
+        if gauss is not None:
+            s = (float("nan"), float("nan"))                                  # measured on the device below
+        elif sky is None or callable(sky):
             pixels = _host_pixels(payload, hdr)
             if origin is not None:
                 pixels = pixels[origin[0]:origin[0] + n, origin[1]:origin[1] + n]
             s = (sky or border_sky)(pixels)
         else:
             s = sky[i]
-        frames.append((payload, float(s[0]), float(s[1]), origin))
+        frames.append([payload, float(s[0]), float(s[1]), origin])
         key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)))
         groups.setdefault(key, []).append(i)
     flags = path_flags(asymmetry, shapeAsymmetry, allAsymmetry, CAS, smoothness)
@@ -119,9 +125,19 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
         for k, i in enumerate(idx):
             pay[k] = np.frombuffer(frames[i][0], dtype=np.uint8)
         win = dict(frame=(H, W), origins=np.array([frames[i][3] for i in idx], dtype=np.int32)) if windowed else {}
+        if gauss is not None:
+            sky_rows = np.empty((len(idx), _abi.PM_SKY_COLS))
+            win.update(gauss=(np.array([gauss[i][0] for i in idx], dtype=np.float64), np.array([gauss[i][1] for i in idx], dtype=np.float64)),
+                       sky_rows_out=sky_rows)
         rows[idx] = analyse_host_payload(pay, bitpix, n, np.array([frames[i][1] for i in idx]), np.array([frames[i][2] for i in idx]),
                                          bzero=bzero, bscale=bscale, filter_size=filterSize, flags=flags, device=device, chunk=chunk,
                                          **win)
+        if gauss is not None:
+            for k, i in enumerate(idx):
+                if sky_rows[k, 11] != 0:
+                    from .skyBackground import _SkyError
+                    raise _SkyError(f"Error! Sky region too small {int(sky_rows[k, 0])} ({infos[i][0]})")      # skyBackground.py:147-148
+                frames[i][1], frames[i][2] = float(sky_rows[k, 9]), float(sky_rows[k, 10])
     per_image = (time.time() - t0) / max(1, len(infos))
     results = []
     for i, (f, _, _) in enumerate(infos):

@@ -93,3 +93,35 @@ def test_calcMorphology_with_an_empty_list_writes_the_header(tmp_path):
     import pawlikmorph_lsst_b200 as pm
     assert pm.main.calcMorphology([], tmp_path / "o") == []
     assert list(csv.reader(open(tmp_path / "o" / "parameters.csv"))) == [pm.result.CSV_HEADER]
+
+
+def test_calcMorphology_with_the_sky_measured_on_the_device(tmp_path):
+    """gauss=(fwhms, theta) per image: sky / sky_err from the sky region of the decoded frame (pm_sky_stats_batch), fed to
+    the analysis on the device — equal to the oracle's sky statistics, and the rows equal to the float host call given
+    those numbers."""
+    import pawlikmorph_lsst_b200 as pm
+    from oracle import sky_oracle as SO
+    g = P.golden("sdss_s")
+    pick = list(range(0, 24))
+    rng = np.random.default_rng(12)
+    gauss = [([float(rng.uniform(3, 9)), float(rng.uniform(3, 9))], float(rng.uniform(-3, 3))) for _ in pick]
+    infos = []
+    for k, i in enumerate(pick):
+        fn = f"g{k}.fits"
+        (tmp_path / fn).write_bytes(fits_bytes(g.image(i), 16 if k % 3 else -32))
+        infos.append((fn, 10.0, 1.0))
+    res = pm.main.calcMorphology(infos, tmp_path / "o", gauss=gauss, smoothness=True, root=tmp_path)
+    imgs = np.stack([g.image(i).astype(np.float32) for i in pick])
+    for k, r in enumerate(res):
+        w = SO.calc_sky(imgs[k].astype(np.float64), gauss[k][0], gauss[k][1])
+        assert abs(r.sky - w["sky"]) <= 1e-9 * abs(w["sky"]) and abs(r.sky_err - w["sky_err"]) <= 1e-9 * w["sky_err"], k
+    rows = pm.batch.analyse_host(imgs, np.array([r.sky for r in res]), np.array([r.sky_err for r in res]), 3, 15)
+    for k, r in enumerate(res):
+        d = dict(zip(pm._abi.ROW_FIELDS, rows[k]))
+        if d["status"] == 1:
+            assert r.status == 1
+            continue
+        assert [r.apix[0], r.apix[1], r.rmax, r.C, r.A[0], r.A[1], r.S, r.As[0], r.gini, r.m20] == \\
+            [d[f] for f in ("apix_col", "apix_row", "rmax", "C", "A", "Abgr", "S", "As", "gini", "m20")], k
+    with pytest.raises(pm.skyBackground._SkyError):
+        pm.main.calcMorphology(infos[:2], tmp_path / "o", gauss=[([60.0, 60.0], 0.0)] * 2, root=tmp_path)
