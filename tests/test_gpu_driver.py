@@ -121,7 +121,7 @@ def test_calcMorphology_with_the_sky_measured_on_the_device(tmp_path):
         if d["status"] == 1:
             assert r.status == 1
             continue
-        assert [r.apix[0], r.apix[1], r.rmax, r.C, r.A[0], r.A[1], r.S, r.As[0], r.gini, r.m20] == \\
+        assert [r.apix[0], r.apix[1], r.rmax, r.C, r.A[0], r.A[1], r.S, r.As[0], r.gini, r.m20] == \
             [d[f] for f in ("apix_col", "apix_row", "rmax", "C", "A", "Abgr", "S", "As", "gini", "m20")], k
     with pytest.raises(pm.skyBackground._SkyError):
         pm.main.calcMorphology(infos[:2], tmp_path / "o", gauss=[([60.0, 60.0], 0.0)] * 2, root=tmp_path)
