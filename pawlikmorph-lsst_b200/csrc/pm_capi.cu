@@ -281,7 +281,13 @@ int pm_sky_stats_batch(const void* images, int dtype, int64_t B, int n, const do
     int rc = device_props();
     if (rc != PM_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const long long grid = B < 8LL * g_sm_count ? B : 8LL * g_sm_count;
+    // persistent CTAs, one wave: 3 per SM is what the registers allow.  Measured at 256^2 (cutouts/s): 1 per SM 293k, 2 470k,
+    // 3 528k, 4 420k (a second, unbalanced wave), 8 516k.  Keeping the cutouts in flight inside the L2 (2 per SM) does not pay:
+    // the passes are bound by instruction issue (67 % of the issue slots, profiles/r1i_sky_ncu_summary.txt), not by DRAM.
+    long long per_sm = 3;
+    if (const char* env = getenv("PM_SKY_CTAS_PER_SM")) per_sm = atoll(env);      // tuning hook
+    per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
+    const long long grid = B < per_sm * g_sm_count ? B : per_sm * g_sm_count;
     cudaError_t e = dtype == PM_F32
         ? cudaFuncSetAttribute(pm_sky_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
         : cudaFuncSetAttribute(pm_sky_stats_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
