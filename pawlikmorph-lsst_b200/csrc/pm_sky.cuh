@@ -43,6 +43,15 @@ template <typename T> struct SkySet {      // the statistics set: sky-region pix
     const unsigned* mask;
     int n, nw;
     double lo, hi;
+    decltype(sky_key(T())) klo, khi;   // [lo, hi] as a key range: membership is two integer compares
+    PM_DEV void set_bounds(double lo_, double hi_) {
+        typedef decltype(sky_key(T())) K;
+        lo = lo_; hi = hi_;
+        klo = sky_key((T)lo_);
+        if (sky_val(klo, T()) < lo_) klo += (K)1;        // (T)lo rounded down: the next key up is the first one inside
+        khi = sky_key((T)hi_);
+        if (sky_val(khi, T()) > hi_) khi -= (K)1;
+    }
 };
 
 // f(x) for every member of the set: one row per warp, 32 columns per word; the loads of kSkyGroup words are issued
@@ -67,8 +76,8 @@ template <typename T, typename F> PM_DEV void sky_for_each(const SkySet<T>& s, F
 #pragma unroll
             for (int j = 0; j < kSkyGroup; j++) {
                 if ((bits[j] >> pm::lane()) & 1u) {
-                    const double v = (double)xv[j];
-                    if (v >= s.lo && v <= s.hi) f(xv[j]);
+                    const auto key = sky_key(xv[j]);
+                    if (key >= s.klo && key <= s.khi) f(xv[j], key);     // NaNs sort outside every range
                 }
             }
         }
@@ -105,8 +114,7 @@ template <typename T, typename K> PM_DEV K sky_select(Sh& sh, SkyScratch& sc, co
         pm::sync();
         const unsigned long long prefix = sc.prefix;
         const bool all = rem >= (int)(8 * sizeof(K));
-        sky_for_each(s, [&](T x) {
-            const K key = sky_key(x);
+        sky_for_each(s, [&](T, K key) {
             if (all || (unsigned long long)(key >> rem) == prefix) pm::atomic_add(&sc.hist[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
         });
         pm::sync();
@@ -142,12 +150,13 @@ template <typename T> PM_DEV SkyStats sky_stats(Sh& sh, SkyScratch& sc, const Sk
     typedef decltype(sky_key(T())) K;
     double a[3] = {0.0, 0.0, 0.0};
     K kmin = ~(K)0, kmax = (K)0;
-    sky_for_each(s, [&](T x) {
+    unsigned mine = 0;
+    sky_for_each(s, [&](T x, K key) {
         const double d = (double)x - shift;
-        a[0] += 1.0; a[1] += d; a[2] += d * d;
-        const K key = sky_key(x);
+        mine++; a[1] += d; a[2] += d * d;
         kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
     });
+    a[0] = (double)mine;
     block_sum<3>(sh, a);
     SkyStats st;
     st.cnt = a[0];
@@ -165,8 +174,8 @@ template <typename T> PM_DEV SkyStats sky_stats(Sh& sh, SkyScratch& sc, const Sk
     if ((cnt & 1u) == 0u) {       // even count: mean of the two middle values; the upper one is k1 again or the next larger key
         unsigned le = 0;
         double nxt = 1.7976931348623157e308 * 2.0;
-        sky_for_each(s, [&](T x) {
-            if (sky_key(x) <= k1) le++; else nxt = fmin(nxt, (double)x);
+        sky_for_each(s, [&](T x, K key) {
+            if (key <= k1) le++; else nxt = fmin(nxt, (double)x);
         });
         le = block_sum_u(sh, le);
         nxt = block_min(sh, nxt);
@@ -194,7 +203,7 @@ PM_DEV void sky_body(const T* images, long long B, int n, const double* ellipse,
         s.nw = (n + 31) / 32;
         // cos / sin of theta come from the caller's libm, like photutils
         sky_build_mask(mask, n, s.nw, ellipse[4 * b], ellipse[4 * b + 1], ellipse[4 * b + 2], ellipse[4 * b + 3]);
-        s.lo = -inf; s.hi = inf;
+        s.set_bounds(-inf, inf);
         SkyStats cur = sky_stats(sh, sc, s, (double)pm::ldg(s.img));
         const SkyStats all = cur;
         double iters = 0.0, sky, err;
@@ -205,8 +214,7 @@ PM_DEV void sky_body(const T* images, long long B, int n, const double* ellipse,
             double changed = 1.0;
             while (changed != 0.0 && iters < 5.0) {
                 iters += 1.0;
-                s.lo = fmax(s.lo, cur.median - cur.std * 3.0);
-                s.hi = fmin(s.hi, cur.median + cur.std * 3.0);
+                s.set_bounds(fmax(s.lo, cur.median - cur.std * 3.0), fmin(s.hi, cur.median + cur.std * 3.0));
                 const SkyStats nxt = sky_stats(sh, sc, s, cur.median);
                 changed = cur.cnt - nxt.cnt;
                 cur = nxt;
