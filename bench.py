@@ -310,6 +310,21 @@ def run_ours(args):
     dec_ms = d0.elapsed_time(d1) / 10
     dec_bytes = D * n * n * 6
     del pay_d, img_d
+    # ---- sky-region statistics (the per-pixel half of skybgr) on resident cutouts: CUDA events, 3 launches
+    S_ = min(B, 16384)
+    rng_ = np.random.default_rng(1)
+    fw_, th_ = rng_.uniform(4.0, 16.0, (S_, 2)), rng_.uniform(-3.0, 3.0, S_)
+    for _ in range(2):
+        sky_rows = pm.skyBackground.sky_stats_batch(x[:S_], fw_, th_)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    s0.record()
+    for _ in range(3):
+        sky_rows = pm.skyBackground.sky_stats_batch(x[:S_], fw_, th_)
+    s1.record()
+    torch.cuda.synchronize(dev)
+    sky_ms = s0.elapsed_time(s1) / 3
+    sky_iters = float(sky_rows[:, 4].mean().item())
 
     if rank != 0:
         if world > 1:
@@ -364,6 +379,9 @@ def run_ours(args):
             "roofline_decode": {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / peak, "kernel": "pm_fits_decode_kernel<16, float>",
                                 "kernel_ms": dec_ms, "algorithmic_bytes_per_pixel": 6, "pixels": D * n * n, "traffic": dec_traffic},
+            "sky_stats": {"value": S_ / (sky_ms * 1e-3), "unit": "cutouts/s", "kernel": "pm_sky_stats_kernel<float>", "kernel_ms": sky_ms,
+                          "cutouts": S_, "mean_clip_iterations": sky_iters, "per_gpu": True,
+                          "note": "sky-region statistics of skyBackground._calcSkybgr with random fitted ellipses; L2/issue bound, see profiles/r1i_sky_ncu_summary.txt"},
             "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
