@@ -101,13 +101,19 @@ def sky_to_pixel(hdr, ra, dec):
     """0-based pixel coordinates (x = column, y = row) of the sky position (ra, dec) in degrees for a `RA---TAN` /
     `DEC--TAN` header with a PC (+ CDELT) or CD matrix — what `wcs.utils.skycoord_to_pixel(position, wcs)` returns at
     Image.py:177-178 for the bundled frames (all of them TAN, LONPOLE 180, no distortion terms)."""
-    t1, t2 = str(hdr.get("CTYPE1", "")), str(hdr.get("CTYPE2", ""))
-    if t1.startswith("RA---TAN") and t2.startswith("DEC--TAN"):
+    t1, t2 = str(hdr.get("CTYPE1", "")).strip(), str(hdr.get("CTYPE2", "")).strip()
+    if t1 == "RA---TAN" and t2 == "DEC--TAN":
         lon = 1
-    elif t1.startswith("DEC--TAN") and t2.startswith("RA---TAN"):
+    elif t1 == "DEC--TAN" and t2 == "RA---TAN":
         lon = 2                                                                               # reversed axes (Image.py:179-182)
     else:
         raise NotImplementedError(f"only RA---TAN / DEC--TAN headers are handled, got {t1!r}, {t2!r}")
+    # astropy (which the reference calls) applies SIP / TPV distortions and a CROTA2 rotation; they are not implemented
+    # here, so such headers are refused instead of being projected a few pixels off
+    if any(k in hdr for k in ("A_ORDER", "B_ORDER")) or any(str(k).startswith(("PV1_", "PV2_")) for k in hdr):
+        raise NotImplementedError("distorted TAN headers (SIP / PV terms) are not handled")
+    if "CROTA2" in hdr and float(hdr["CROTA2"]) != 0.0 and not any(k in hdr for k in ("PC1_1", "PC1_2", "PC2_1", "PC2_2", "CD1_1")):
+        raise NotImplementedError("CROTA2 rotation without a PC / CD matrix is not handled")
     a0, d0 = math.radians(float(hdr[f"CRVAL{lon}"])), math.radians(float(hdr[f"CRVAL{3 - lon}"]))
     a, d = math.radians(float(ra)), math.radians(float(dec))
     cosc = math.sin(d0) * math.sin(d) + math.cos(d0) * math.cos(d) * math.cos(a - a0)

@@ -20,7 +20,7 @@ import time
 import numpy as np
 
 from . import _abi
-from .image import BYTES_PER_PIXEL, cutout_origin, payload_of, sky_to_pixel
+from .image import BYTES_PER_PIXEL, PartialOverlapError, cutout_origin, payload_of, sky_to_pixel
 from .result import CSV_HEADER, Result
 
 _NP = {8: ">u1", 16: ">i2", 32: ">i4", -32: ">f4", -64: ">f8"}
@@ -78,7 +78,8 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     root: folder the file names are relative to.  parallelLibrary / cores are accepted and ignored: the batch is the
     parallelism.  npix: None analyses whole frames; a number takes the npix x npix window around (ra, dec) whenever the
     frame has at least npix rows and ra and dec are truthy (Image.py:135 — a declination of exactly 0 gives the whole
-    frame, as upstream); a window that leaves the frame raises image.PartialOverlapError like `Cutout2D(mode="strict")`."""
+    frame, as upstream); a frame that cannot be read, or whose window leaves it (image.PartialOverlapError, the
+    `Cutout2D(mode="strict")` error), gets the default Result and the run carries on (main.py:331-339)."""
     for name, val in (("calculateSersic", calculateSersic), ("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
                       ("catalogue", catalogue), ("largeImage", largeImage), ("segmap", segmap), ("starMask", starMask)):
         if val:
@@ -86,25 +87,33 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     from .batch import analyse_host_payload      # needs torch + the CUDA library; fails loudly without them
     infos = [(str(f), ra, dec) for f, ra, dec in imageInfos]
     t0 = time.time()
-    frames, groups = [], {}
+    frames, groups, failed = [], {}, set()
     for i, (f, _, _) in enumerate(infos):
         path = f if root is None or os.path.isabs(f) else os.path.join(str(root), f)
-        with open(path, "rb") as fh:
-            payload, hdr = payload_of(fh.read())
-        if hdr.get("NAXIS", 2) != 2:
-            raise ValueError(f"{f}: not a 2-D image")
-        H, W = hdr["NAXIS2"], hdr["NAXIS1"]
-        ra, dec = infos[i][1], infos[i][2]
-        if npix is not None and H >= npix and ra and dec:                      # Image.py:135-136
-            n = int(npix)
-            x, y = sky_to_pixel(hdr, ra, dec)
-            if str(hdr.get("CTYPE1", ""))[:1] == "D":                             # Image.py:179-182: upstream swaps the position
-                x, y = y, x                                                       # for reversed-axis headers (astropy #10468)
-            origin = cutout_origin(x, y, n, (H, W))
-        else:
-            if H != W:
-                raise ValueError(f"{f}: whole frames must be square, got {H} x {W}")
-            n, origin = H, None
+        # main.py:331-339: an image that cannot be read or cut (IOError, AttributeError, PartialOverlapError) gets the
+        # default Result and the run carries on with the others
+        try:
+            with open(path, "rb") as fh:
+                payload, hdr = payload_of(fh.read())
+            if hdr.get("NAXIS", 2) != 2:
+                raise ValueError(f"{f}: not a 2-D image")
+            H, W = hdr["NAXIS2"], hdr["NAXIS1"]
+            ra, dec = infos[i][1], infos[i][2]
+            if npix is not None and H >= npix and ra and dec:                      # Image.py:135-136
+                n = int(npix)
+                # sky_to_pixel returns the true (x = column, y = row) for RA-first and DEC-first headers alike; the
+                # reference's position[::-1] (Image.py:179-182) only undoes astropy #10468 and has no counterpart here
+                x, y = sky_to_pixel(hdr, ra, dec)
+                origin = cutout_origin(x, y, n, (H, W))
+            else:
+                if H != W:
+                    raise ValueError(f"{f}: whole frames must be square, got {H} x {W}")
+                n, origin = H, None
+        except (OSError, AttributeError, PartialOverlapError, KeyError, ValueError) as e:
+            print(f"{f}: {type(e).__name__}: {e} -- default Result")
+            frames.append([None, -99., 99., None])
+            failed.add(i)
+            continue
         pixels = None
         if gauss is not None:
             s = (float("nan"), float("nan"))                                  # measured on the device below
@@ -119,7 +128,9 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
         key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)))
         groups.setdefault(key, []).append(i)
     flags = path_flags(asymmetry, shapeAsymmetry, allAsymmetry, CAS, smoothness)
-    rows = np.empty((len(infos), _abi.ROW_DOUBLES))
+    rows = np.full((len(infos), _abi.ROW_DOUBLES), -99.0)
+    for i in failed:
+        rows[i, _abi.ROW_FIELDS.index("status")] = 1.0                         # -> the default Result (main.py:331-339)
     for (n, H, W, windowed, bitpix, bzero, bscale), idx in groups.items():
         pay = np.empty((len(idx), H * W * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
         for k, i in enumerate(idx):
@@ -141,7 +152,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     per_image = (time.time() - t0) / max(1, len(infos))
     results = []
     for i, (f, _, _) in enumerate(infos):
-        r = Result.from_row(rows[i], file=f, sky=frames[i][1], sky_err=frames[i][2])
+        r = Result.from_row(rows[i], file=os.path.basename(f), sky=frames[i][1], sky_err=frames[i][2])      # main.py:341: file.name
         r.outfolder = str(outfolder)
         r.time = per_image
         results.append(r)

@@ -138,3 +138,51 @@ def test_driver_cutout_on_the_emulator_build(tmp_path, monkeypatch):
         seen.setdefault("n", n), np.full((len(payload), 16), -99.0))[1])
     pm.main.calcMorphology([(infos[0][0], infos[0][1], 0.0)], tmp_path / "out", npix=128, root=tmp_path)
     assert seen["n"] == 177
+
+
+def test_driver_dec_first_header_and_bad_frames(tmp_path, monkeypatch):
+    """A DEC-first copy of a bundled frame is cut at the same origin as the RA-first one (sky_to_pixel already returns
+    (column, row); no second swap), and a frame that cannot be read / whose window leaves it gets the default Result
+    while the others are analysed (main.py:331-339).  The file column holds the base name (main.py:341)."""
+    g = P.golden("sdss_l")
+    wcs = _wcs_by_name()
+    name = str(g.z["names"][29])
+    h = wcs[name]["header"]
+    hr = dict(h, CTYPE1=h["CTYPE2"], CTYPE2=h["CTYPE1"], CRVAL1=h["CRVAL2"], CRVAL2=h["CRVAL1"],
+              PC1_1=h["PC2_1"], PC1_2=h["PC2_2"], PC2_1=h["PC1_1"], PC2_2=h["PC1_2"])
+    hr = {k: v for k, v in hr.items() if not k.startswith("CD")}
+    sub = tmp_path / "sub"
+    sub.mkdir()
+    (sub / "ra_first.fits").write_bytes(fits_bytes(g.image(29), 16, extra=h))
+    (sub / "dec_first.fits").write_bytes(fits_bytes(g.image(29), 16, extra=hr))
+    (sub / "edge.fits").write_bytes(fits_bytes(g.image(29), 16, extra=dict(h, CRPIX1=float(h["CRPIX1"]) + 80.0)))
+    seen = []
+
+    def fake(payload, bitpix, n, sky, sky_err, frame=None, origins=None, **kw):
+        seen.append(np.asarray(origins).copy())
+        rows = np.full((len(payload), 16), -99.0)
+        rows[:, 14] = 0.0
+        rows[:, 2] = 7.0
+        return rows
+
+    import pawlikmorph_lsst_b200.batch as batch
+    monkeypatch.setattr(batch, "analyse_host_payload", fake)
+    ra, dec = wcs[name]["ra"], wcs[name]["dec"]
+    infos = [("sub/ra_first.fits", ra, dec), ("sub/missing.fits", ra, dec), ("sub/dec_first.fits", ra, dec), ("sub/edge.fits", ra, dec)]
+    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, root=tmp_path)
+    assert len(seen) == 1 and seen[0].shape == (2, 2) and np.array_equal(seen[0][0], seen[0][1])
+    assert [r.file for r in res] == ["ra_first.fits", "missing.fits", "dec_first.fits", "edge.fits"]
+    assert [r.status for r in res] == [0, 1, 0, 1] and res[1].rmax == -99 and res[3].rmax == -99 and res[0].rmax == 7.0
+    table = list(csv.reader(open(tmp_path / "out" / "parameters.csv")))
+    assert len(table) == 5 and table[2][0] == "missing.fits" and table[2][2] == "-99"
+
+
+def test_sky_to_pixel_refuses_distorted_headers():
+    import pytest
+    h = _wcs_by_name()[next(iter(_wcs_by_name()))]["header"]
+    for bad in (dict(h, CTYPE1="RA---TAN-SIP", CTYPE2="DEC--TAN-SIP"), dict(h, A_ORDER=2), dict(h, PV1_1=0.1)):
+        with pytest.raises(NotImplementedError):
+            pm.image.sky_to_pixel(bad, 1.0, 2.0)
+    bare = {k: v for k, v in h.items() if not k.startswith(("PC", "CD"))}
+    with pytest.raises(NotImplementedError):
+        pm.image.sky_to_pixel(dict(bare, CROTA2=12.0), 1.0, 2.0)
