@@ -214,12 +214,10 @@ def run_ours(args):
                  "S:bkg", "calcA:dilate", "r20:fold", "r20:bounds", "r20:walk", "S:interior", "S:cut", "S:boxsearch",
                  "sort:bits", "sort:count", "sort:scan", "sort:scatter", "minapix:first", "minapix:stage", "minapix:compact", "p23")
         names += tuple(f"#alive@stage{k}" for k in range(8))
-        names += ("gini:sums", "gini:thresh", "gini:moments", "gini:cands", "gini:reverse", "list:rowscan", "list:fill", "r20:total", "rmax2", "ef:thr", "ef:items", "ef:scan", "ef:overlap", "ef:sum", "r20:rk", "q47")
-        buf = torch.zeros((592, 48), dtype=torch.int64, device=dev)
-        pm._lib.lib().pm_debug_phase_cycles(buf.data_ptr())
-        step()
+        names += ("gini:sums", "gini:thresh", "gini:moments", "gini:cands", "gini:reverse", "list:rowscan", "list:fill", "r20:total", "rmax2", "minapix:load", "tail:planes", "q43", "q44", "q45", "q46", "q47")
+        buf = torch.zeros((pm._abi.PM_PHASE_ROWS, 48), dtype=torch.int64, device=dev)
+        pm.batch.analyse_batch(x, sky, err, 3, FLAGS_ALL, rows_out=rows, segmap_out=segmap, stream=stream, phase_cycles_out=buf)
         torch.cuda.synchronize(dev)
-        pm._lib.lib().pm_debug_phase_cycles(None)
         cyc = buf.sum(dim=0).cpu().numpy().astype(float)
         tot = cyc.sum()
         print("phase cycles per galaxy: " + ", ".join(f"{nm} {c / B:.0f} ({100 * c / tot:.1f}%)" for nm, c in zip(names, cyc) if c > 0)

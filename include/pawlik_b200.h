@@ -19,7 +19,7 @@
  *  - Images are [B, n, n] row-major, float32 (PM_F32) or float64 (PM_F64), WITH the
  *    sky still in them; `sky[b]` is subtracted on the fly in float64 exactly where
  *    main.py:442 does `img -= sky`.  Pass sky = 0 for already-subtracted images.
- *  - Re-entrant, no global state.  n <= PM_MAX_N.
+ *  - Re-entrant, no global state (a launch counter aside).  n <= PM_MAX_N.
  */
 #ifndef PAWLIK_B200_H
 #define PAWLIK_B200_H
@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 1
+#define PM_ABI_VERSION 2
 #define PM_MAX_N 640
 
 /* dtype of `images` */
@@ -63,6 +63,10 @@ extern "C" {
 #define PM_NO_NOISECORRECT 0x1000u    /* calcA(..., noisecorrect=False): Abgr = 0, A not corrected */
 #define PM_NO_PRUNE 0x4000u           /* tuning/test: evaluate every minapix candidate completely (no exact pruning) */
 #define PM_L2_PREFETCH 0x2000u        /* tuning: TMA-prefetch the next cutout into L2 while the current one runs (off) */
+#define PM_PATH_MONOLITH 0x8000u      /* tuning/test: one fused kernel per batch (one CTA per cutout through every phase)
+                                         instead of the three kernels split by resource class */
+#define PM_TAIL_CTA 0x10000u          /* tuning/test: the tail kernel (r20/r80, calcA, S) with one CTA per cutout instead of
+                                         one warp per cutout */
 
 /* pm_row_t.status */
 #define PM_ST_OK 0
@@ -110,17 +114,24 @@ typedef struct {
     uint8_t *apermask_out;   /* [B,n,n]  the aperture mask used (apertures.aperpixmap) */
     double *cand_a_out;      /* [B,cand_cap] parity aid: asymmetry of each candidate in order (asymmetry.py:125) */
     int32_t cand_cap;
+    uint64_t *phase_cycles_out; /* tuning aid: zeroed DEVICE buffer of PM_PHASE_ROWS x 48 uint64; the launches of this call
+                                   accumulate per-group clock64() cycles per phase (0 pixelmap, 1 list, 2 rmax/aperture,
+                                   3 sort, 4 gini/m20/candidates, 5 minapix, 6 calcA, 7 r20/r80, 8 smoothness, 9.. parts) */
 } pm_outputs_t;
+#define PM_PHASE_ROWS 8192
 
 /* Bytes of device scratch pm_analyse_batch needs for (B, n, dtype).  HOST call, no CUDA work. */
 size_t pm_workspace_bytes(int64_t B, int n, int dtype);
 
-/* The whole hot path for a batch of cutouts, one CTA per cutout, image read from HBM once:
+/* The whole hot path for a batch of cutouts:
  *   pixmap.pixelmap + checkPixelmapEdges  (pixmap.py:130-213, :91-127)       main.py:421,427
  *   pixmap.calcRmax, apertures.aperpixmap (pixmap.py:26-55, apertures.py:42-128) main.py:463-464
  *   asymmetry.minapix                     (asymmetry.py:50-129)               main.py:467
  *   asymmetry.calcA x3                    (asymmetry.py:132-257)              main.py:470-478
  *   casgm.calcR20_R80, concentration, gini, m20, smoothness (casgm.py)        main.py:490-495
+ * Three kernels per chunk of the batch, split by resource class: front (one CTA per cutout: pixelmap ..
+ * candidates; the only pass that streams the image from HBM), minapix (one CTA per cutout at higher occupancy), tail
+ * (one warp per cutout: r20/r80, calcA x3, smoothness).  The hand-over state lives in `workspace`.
  * images  [B,n,n] dtype;  sky, sky_err [B] float64;  filter_size odd in 1..15;
  * ov / out may be NULL;  rows [B];  workspace >= pm_workspace_bytes(B,n,dtype). */
 int pm_analyse_batch(const void *images, int dtype, int64_t B, int n, const double *sky,
@@ -163,10 +174,6 @@ int pm_sky_stats_batch(const void *images, int dtype, int64_t B, int n, const do
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 const char *pm_last_cuda_error(void);
-/* Tuning aid: when set to a zeroed DEVICE buffer of PM_MAX_GRID x 48 uint64, subsequent pm_analyse_batch launches
- * accumulate per-CTA clock64() cycles per phase (0 pixelmap, 1 list/window, 2 rmax/aperture, 3 sort, 4 gini/m20/
- * candidates, 5 minapix, 6 calcA, 7 r20/r80, 8 smoothness).  Pass NULL to switch it off (the default). */
-void pm_debug_phase_cycles(void *device_u64_grid_x48);
 #define PM_MAX_GRID 592
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 uint64_t pm_launch_count(void);

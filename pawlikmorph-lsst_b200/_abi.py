@@ -6,7 +6,7 @@ same sources (tests/emul) to exercise the kernel logic without a GPU.
 """
 import ctypes as C
 
-PM_ABI_VERSION = 1
+PM_ABI_VERSION = 2
 PM_MAX_N = 640
 PM_F32, PM_F64 = 0, 1
 PM_OK, PM_EINVAL, PM_ENOSPC, PM_ECUDA, PM_ENODEV = 0, -1, -2, -3, -4
@@ -18,6 +18,9 @@ PM_A_ANGLE90 = 0x800
 PM_NO_NOISECORRECT = 0x1000
 PM_L2_PREFETCH = 0x2000
 PM_NO_PRUNE = 0x4000
+PM_PATH_MONOLITH = 0x8000
+PM_TAIL_CTA = 0x10000
+PM_PHASE_ROWS = 8192
 PM_ST_OK, PM_ST_FAINT_CENTRE, PM_ST_NO_CANDIDATE, PM_ST_BAD_BRACKET, PM_ST_EMPTY_SEGMAP, PM_ST_WORKSPACE = range(6)
 
 ROW_FIELDS = ("apix_col", "apix_row", "rmax", "r20", "r80", "C", "A", "Abgr", "S", "As",
@@ -33,10 +36,11 @@ class Overrides(C.Structure):
 
 class Outputs(C.Structure):
     _fields_ = [("segmap_out", C.c_void_p), ("sorted_idx_out", C.c_void_p), ("n_positive_out", C.c_void_p),
-                ("apermask_out", C.c_void_p), ("cand_a_out", C.c_void_p), ("cand_cap", C.c_int32)]
+                ("apermask_out", C.c_void_p), ("cand_a_out", C.c_void_p), ("cand_cap", C.c_int32),
+                ("phase_cycles_out", C.c_void_p)]
 
 
-EXPORTS = ("pm_debug_phase_cycles", "pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
+EXPORTS = ("pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
            "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch",
            "pm_fits_decode_window_batch", "pm_sky_stats_batch")
 PM_SKY_COLS = 12
@@ -46,8 +50,6 @@ SKY_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_coun
 
 def declare(lib):
     """Attach prototypes to a loaded library and return it."""
-    lib.pm_debug_phase_cycles.restype = None
-    lib.pm_debug_phase_cycles.argtypes = [C.c_void_p]
     lib.pm_abi_version.restype = C.c_int
     lib.pm_abi_version.argtypes = []
     lib.pm_device_info.restype = C.c_int

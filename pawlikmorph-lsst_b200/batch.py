@@ -77,7 +77,7 @@ class BatchResult:
 def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segmap_in=None, apermask_in=None,
                   centroid_in=None, radius_in=None, r20_in=None, threshold_in=None, smooth_sky_in=None,
                   want_segmap=False, want_sorted=False, want_apermask=False, cand_cap=0, rows_out=None,
-                  segmap_out=None, stream=None):
+                  segmap_out=None, stream=None, phase_cycles_out=None):
     """Run the hot path of main.py:421-495 on `images` [B, n, n] (CUDA tensor, float32 or float64,
     sky still in).  Asynchronous on `stream` (default: the current torch stream).  Returns a
     BatchResult whose tensors live on the same device."""
@@ -123,7 +123,7 @@ def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segma
             if cand_cap:
                 res.cand_a = torch.empty((B, int(cand_cap)), dtype=torch.float64, device=dev)
             out = _abi.Outputs(_ptr(res.segmap), _ptr(res.sorted_idx), _ptr(res.n_positive), _ptr(res.apermask),
-                               _ptr(res.cand_a), int(cand_cap))
+                               _ptr(res.cand_a), int(cand_cap), _ptr(phase_cycles_out))
             if B == 0:
                 return res
             wsb = L.pm_workspace_bytes(B, n, dtype)

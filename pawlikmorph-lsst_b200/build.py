@@ -8,7 +8,7 @@ REPO = os.path.dirname(HERE)
 # PM_LIB_VARIANT=<threads>x<ctas> selects an experimental build (tuning runs only), e.g. 256x2
 VARIANT = os.environ.get("PM_LIB_VARIANT", "")
 SO = os.path.join(HERE, "libpawlik_b200.so" if not VARIANT else f"libpawlik_b200_{VARIANT}.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh", "pm_sky.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_tail.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_launch.cuh", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh", "pm_sky.cuh")] + \
     [os.path.join(REPO, "include", "pawlik_b200.h")]
 
 
@@ -24,18 +24,37 @@ def up_to_date():
 
 
 def build(force=False, verbose=False):
+    """The translation units (pm_capi.cu: the C ABI; pm_k_*.cu: one CTA-group kernel each; pm_tail.cu: the warp-group tail
+    kernel) are compiled side by side, then linked into one shared object."""
     if not force and up_to_date():
         return SO
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(REPO, "include"),
-           os.path.join(HERE, "csrc", "pm_capi.cu"), "-o", SO]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "csrc", "_obj" + (("_" + VARIANT) if VARIANT else ""))
+    os.makedirs(objdir, exist_ok=True)
+    common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I" + os.path.join(REPO, "include")]
     if VARIANT:
         t, k = VARIANT.split("x")
-        cmd[1:1] = [f"-DPM_THREADS={int(t)}", f"-DPM_MIN_CTAS={int(k)}"]
+        common[1:1] = [f"-DPM_THREADS={int(t)}", f"-DPM_MIN_CTAS={int(k)}"]
+    for d in os.environ.get("PM_NVCC_DEFINES", "").split():
+        common.insert(1, "-D" + d)
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.run(cmd, check=True)
+        common[1:1] = ["-Xptxas", "-v"]
+    units = ["pm_capi.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_tail.cu"]
+
+    def one(u):
+        o = os.path.join(objdir, u.replace(".cu", ".o"))
+        r = subprocess.run(common + ["-c", os.path.join(HERE, "csrc", u), "-o", o], capture_output=True, text=True)
+        return o, r
+
+    with ThreadPoolExecutor(len(units)) as ex:
+        res = list(ex.map(one, units))
+    for o, r in res:
+        if verbose or r.returncode:
+            print(r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed for {o}")
+    subprocess.run([nvcc_path(), "-shared", "-o", SO] + [o for o, _ in res], check=True)
     return SO
 
 

@@ -6,10 +6,20 @@
 #pragma once
 #include "pm_platform.cuh"
 
-namespace pmk {
+// PM_NS: the namespace of this translation unit's copy of the kernels.  The library compiles the kernel sources in
+// two units — pm_capi.cu (CTA groups, namespace pmk) and pm_tail.cu (PM_GROUP_WARP: warp groups, namespace pmk_w) —
+// and the sizes of the block-shared structures differ between them.
+#ifndef PM_NS
+#define PM_NS pmk
+#endif
+namespace PM_NS {
 
-// CTA shape: 256 threads x 2 CTAs per SM (128 registers per thread).  Two independent CTAs per SM overlap
-// each other's barrier waits and latency-bound phases; measured +12 % over one 512-thread CTA (profiles/).
+// Group shape.  CTA groups: 256 threads x 2 CTAs per SM for the front kernel (two independent CTAs per SM overlap each
+// other's barrier waits; measured +12 % over one 512-thread CTA, profiles/).  Warp groups: 32 threads.
+#if defined(PM_GROUP_WARP)
+#undef PM_THREADS
+#define PM_THREADS 32
+#endif
 #ifndef PM_THREADS
 #define PM_THREADS 256
 #endif
@@ -17,7 +27,7 @@ namespace pmk {
 #define PM_MIN_CTAS 2
 #endif
 constexpr int kThreads = PM_THREADS;
-static_assert(kThreads >= 160 && kThreads % 32 == 0, "whole warps; thread k holds walk radius k (k <= 130)");
+static_assert(kThreads % 32 == 0, "whole warps");
 constexpr int kWarps = kThreads / 32;
 constexpr int kRedSlots = 8;
 
@@ -50,6 +60,11 @@ PM_DEV unsigned red_half(Sh& sh) {
 }
 template <int K> PM_DEV void block_sum(Sh& sh, double (&v)[K]) {
     static_assert(K <= kRedSlots, "too many reduction slots");
+    if (kWarps == 1) {                       // warp group: the butterfly leaves the total in every lane
+#pragma unroll
+        for (int k = 0; k < K; k++) v[k] = pm::warp_sum(v[k]);
+        return;
+    }
     double* red = sh.red[red_half(sh)];
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = pm::warp_sum(v[k]);
@@ -166,8 +181,20 @@ struct Arena {
     unsigned char* g_base;
     size_t g_cap, g_top;
     int overflow;
+    unsigned s_floor;       // per-cutout resets return to these marks (what lies below lives as long as the kernel)
+    size_t g_floor;
     PM_DEV void init(unsigned char* sb, unsigned sc, unsigned char* gb, size_t gc) {
-        s_base = sb; s_cap = sc; s_top = 0; g_base = gb; g_cap = gc; g_top = 0; overflow = 0;
+        s_base = sb; s_cap = sc; s_top = 0; g_base = gb; g_cap = gc; g_top = 0; overflow = 0; s_floor = 0; g_floor = 0;
+    }
+    PM_DEV void set_floor() { s_floor = s_top; g_floor = g_top; }
+    PM_DEV void reset() { s_top = s_floor; g_top = g_floor; overflow = 0; }
+    // shared memory or nothing
+    PM_DEV void* alloc_smem(size_t bytes) {
+        bytes = (bytes + 15) & ~(size_t)15;
+        if (bytes > (size_t)(s_cap - s_top)) return nullptr;
+        void* p = s_base + s_top;
+        s_top += (unsigned)bytes;
+        return p;
     }
     PM_DEV void* alloc(size_t bytes) {
         bytes = (bytes + 15) & ~(size_t)15;
@@ -433,4 +460,4 @@ PM_DEV double circle_weight(int dx, int dy, double r) {
     return 0.0;
 }
 
-}  // namespace pmk
+}  // namespace PM_NS

@@ -15,16 +15,25 @@
 
 using namespace pmk;
 
-#define PM_WS_HEADER 256
-
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local char g_err[256] = "";
-static unsigned long long* g_phase_cycles = nullptr;   // tuning aid, see pm_debug_phase_cycles()
+
+// the kernels of the per-cutout path live in their own translation units (pm_k_*.cu, pm_tail.cu; pm_launch.cuh)
+#define PM_LAUNCHER_DECL(NAME)                                                                                        \
+    extern "C" int NAME##_launch(const void* params, size_t params_bytes, int dtype, unsigned grid, unsigned threads, \
+                                 unsigned smem, void* cuda_stream, char* err, size_t err_len)
+PM_LAUNCHER_DECL(pm_analyse);
+PM_LAUNCHER_DECL(pm_big);
+PM_LAUNCHER_DECL(pm_front);
+PM_LAUNCHER_DECL(pm_minapix);
+PM_LAUNCHER_DECL(pm_tail_cta);
+PM_LAUNCHER_DECL(pm_tail_warp);
+extern "C" unsigned pm_tail_warp_fixed_smem(int n);
+extern "C" int pm_tail_warp_groups_per_cta(void);
+extern "C" int pm_tail_warp_ctas_per_sm(void);
+extern "C" int pm_minapix_min_ctas(void);
 
 #ifndef PM_EMULATE
-template <typename T> __global__ void __launch_bounds__(kThreads, PM_MIN_CTAS) pm_analyse_kernel(const __grid_constant__ Params p) {
-    analyse_body<T>(p);
-}
 __global__ void __launch_bounds__(kThreads, 1)
 pm_aperpixmap_kernel(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out, unsigned smem_bytes) {
     aperpixmap_body(n, rad, B, ns, frac, mask_out, smem_bytes);
@@ -61,7 +70,7 @@ static int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// shared-memory size and CTAs per SM for (n, fs)
+// shared-memory size and CTAs per SM of the front / monolith / CTA-tail kernels for (n, fs)
 static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
     const unsigned fixed = smem_fixed_bytes(n, fs);
     const unsigned cap1 = (unsigned)(g_smem_optin ? g_smem_optin : 232448);   // 227 KB
@@ -77,11 +86,59 @@ static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
     *smem = per;
     *ctas_per_sm = ctas;
 }
+// the minapix kernel: aperture plane + window + list; as many CTAs per SM as the launch bounds allow
+static void minapix_shape(int n, unsigned* smem, int* ctas_per_sm) {
+    const unsigned fixed = smem_fixed_bytes(n, 1, SM_APER);
+    const unsigned cap1 = (unsigned)(g_smem_optin ? g_smem_optin : 232448);
+    const int built = pm_minapix_min_ctas();
+    int ctas = env_int("PM_MINAPIX_CTAS", built > 3 ? 3 : built);
+    if (ctas > built) ctas = built;
+    if (ctas < 1) ctas = 1;
+    while (ctas > 1 && fixed + 16 * 1024 > (cap1 + 1024) / (unsigned)ctas - 1024) ctas--;
+    unsigned per = ((cap1 + 1024) / (unsigned)ctas - 1024) & ~15u;
+    if (per > cap1) per = cap1;
+    *smem = per;
+    *ctas_per_sm = ctas;
+}
+
+// ---- workspace plan of the split path -------------------------------------------------------------------------------
+// [0, 256) work counters | big list (int per cutout of a chunk) | per-group scratch (the largest of the kernels') |
+// hand-over slots of one chunk.  Upper bounds on the grids are used so that the size does not depend on the device.
+#define PM_WS_HEADER 256
+#define PM_MAX_TAIL_GROUPS 5120        /* 32 warps x 160 SMs */
+#define PM_MAX_MINAPIX_GRID 640
+struct Plan {
+    long long chunk;
+    size_t off_big, off_scratch, scratch_bytes, off_state, total;
+};
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+static Plan make_plan(int64_t B, int n) {
+    Plan pl;
+    long long chunk = 49152;                                               // >= 20 waves of the tail kernel's groups
+    const unsigned long long stride = state_stride(n);
+    const long long by_mem = (long long)((4ull << 30) / stride);             // <= 4 GiB of hand-over slots
+    if (chunk > by_mem) chunk = by_mem < 1024 ? 1024 : by_mem;
+    const int forced = env_int("PM_CHUNK", 0);
+    if (forced > 0) chunk = forced;
+    if (chunk > B) chunk = B;
+    pl.chunk = chunk;
+    auto cap = [&](long long g) { return (unsigned long long)(B < g ? B : g); };
+    unsigned long long sc = cap(PM_MAX_GRID) * scratch_bytes_per_cta(n);                            // front, monolith pass, CTA tail
+    const unsigned long long sm_ = cap(PM_MAX_MINAPIX_GRID) * scratch_bytes_minapix(n);
+    const unsigned long long st_ = cap(PM_MAX_TAIL_GROUPS) * scratch_bytes_tail(n);
+    if (sm_ > sc) sc = sm_;
+    if (st_ > sc) sc = st_;
+    pl.off_big = PM_WS_HEADER;
+    pl.off_scratch = up256(pl.off_big + 4 * (size_t)chunk);
+    pl.scratch_bytes = up256((size_t)sc);
+    pl.off_state = pl.off_scratch + pl.scratch_bytes;
+    pl.total = pl.off_state + (size_t)chunk * (size_t)stride;
+    return pl;
+}
 
 extern "C" {
 
 int pm_abi_version(void) { return PM_ABI_VERSION; }
-void pm_debug_phase_cycles(void* device_u64_grid_x48) { g_phase_cycles = (unsigned long long*)device_u64_grid_x48; }
 const char* pm_last_cuda_error(void) { return g_err; }
 uint64_t pm_launch_count(void) { return g_launches.load(); }
 
@@ -98,9 +155,17 @@ int pm_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_opt
 size_t pm_workspace_bytes(int64_t B, int n, int dtype) {
     (void)dtype;
     if (B <= 0 || n <= 0 || n > PM_MAX_N) return 0;
-    const unsigned long long grid = (unsigned long long)(B < PM_MAX_GRID ? B : PM_MAX_GRID);
-    return (size_t)(PM_WS_HEADER + grid * scratch_bytes_per_cta(n));
+    return make_plan(B, n).total;
 }
+
+// one kernel launch of the per-cutout path (the first failure sticks; later launches are skipped)
+#define PM_LAUNCH(NAME, GRID, THREADS, SMEM)                                                                          \
+    do {                                                                                                              \
+        if (lrc == PM_OK) {                                                                                           \
+            lrc = NAME##_launch(&p, sizeof p, dtype, (unsigned)(GRID), (unsigned)(THREADS), (SMEM), cuda_stream, g_err, sizeof g_err); \
+            g_launches.fetch_add(1);                                                                                  \
+        }                                                                                                             \
+    } while (0)
 
 int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const double* sky, const double* sky_err,
                      int filter_size, uint32_t flags, const pm_overrides_t* ov, const pm_outputs_t* out,
@@ -116,7 +181,8 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
     }
     if (ov && ov->starmask) { snprintf(g_err, sizeof g_err, "star masks are not supported yet"); return PM_EINVAL; }
     if (B > 0x7fffffffLL) { snprintf(g_err, sizeof g_err, "batch too large"); return PM_EINVAL; }
-    if (workspace_bytes < pm_workspace_bytes(B, n, dtype)) { snprintf(g_err, sizeof g_err, "workspace too small"); return PM_ENOSPC; }
+    const Plan pl = make_plan(B, n);
+    if (workspace_bytes < pl.total) { snprintf(g_err, sizeof g_err, "workspace too small"); return PM_ENOSPC; }
     if (((uintptr_t)workspace & 15) != 0) { snprintf(g_err, sizeof g_err, "workspace must be 16-byte aligned"); return PM_EINVAL; }
     int rc = device_props();
     if (rc != PM_OK) return rc;
@@ -129,44 +195,93 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
     if (out) p.out = *out;
     p.rows = rows;
     p.counter = (unsigned long long*)workspace;
-    p.scratch = (unsigned char*)workspace + PM_WS_HEADER;
+    p.scratch = (unsigned char*)workspace + pl.off_scratch;
     p.scratch_per_cta = scratch_bytes_per_cta(n);
-    p.phase_cycles = g_phase_cycles;
+    p.phase_cycles = (unsigned long long*)p.out.phase_cycles_out;
+    p.big_list = (int*)((unsigned char*)workspace + pl.off_big);
+    p.state = (unsigned char*)workspace + pl.off_state;
+    p.state_stride = state_stride(n);
+    p.list_cap = state_list_cap(n);
+    p.cand_cap = state_cand_cap();
+    {   // test hooks: smaller hand-over slots push more cutouts through the monolith pass
+        const int lc = env_int("PM_TEST_LIST_CAP", 0), cc = env_int("PM_TEST_CAND_CAP", 0);
+        if (cc > 0 && cc < p.cand_cap) p.cand_cap = cc;
+        if (lc > 0 && lc < p.list_cap) p.list_cap = lc;
+    }
     unsigned smem = 0;
     int ctas = 1;
     launch_shape(n, filter_size, &smem, &ctas);
     if (smem < smem_fixed_bytes(n, filter_size) + 4096) { snprintf(g_err, sizeof g_err, "shared memory too small for n"); return PM_EINVAL; }
-    p.smem_bytes = smem;
-    long long grid = (long long)g_sm_count * ctas;
-    if (grid > PM_MAX_GRID) grid = PM_MAX_GRID;
-    if (grid > B) grid = B;
+    long long grid_cap = (long long)g_sm_count * ctas;
+    if (grid_cap > PM_MAX_GRID) grid_cap = PM_MAX_GRID;
     const int g_env = env_int("PM_GRID", 0);
-    if (g_env > 0 && g_env < grid) grid = g_env;
+    if (g_env > 0 && g_env < grid_cap) grid_cap = g_env;
+    const bool mono = (flags & PM_PATH_MONOLITH) != 0 || env_int("PM_PATH_MONOLITH", 0) != 0;
+    const bool tail_cta = (flags & PM_TAIL_CTA) != 0 || env_int("PM_TAIL_CTA", 0) != 0;
 
+    int lrc = PM_OK;
+    auto zero_counters = [&]() -> int {
 #ifndef PM_EMULATE
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    cudaError_t e = cudaMemsetAsync(p.counter, 0, PM_WS_HEADER, st);
-    if (e == cudaSuccess) {
-        if (dtype == PM_F32) {
-            e = cudaFuncSetAttribute(pm_analyse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) pm_analyse_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>(p);
-        } else {
-            e = cudaFuncSetAttribute(pm_analyse_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) pm_analyse_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>(p);
-        }
-        if (e == cudaSuccess) e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_analyse_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
+        cudaError_t e = cudaMemsetAsync(p.counter, 0, PM_WS_HEADER, (cudaStream_t)cuda_stream);
+        if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_analyse_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
 #else
-    (void)cuda_stream;
-    memset(p.counter, 0, PM_WS_HEADER);
-    for (long long blk = 0; blk < grid; blk++) {
-        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { analyse_body<float>(p); });
-        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { analyse_body<double>(p); });
-    }
+        memset(p.counter, 0, PM_WS_HEADER);
 #endif
-    g_launches.fetch_add(1);
-    return PM_OK;
+        return PM_OK;
+    };
+    if (mono) {
+        p.smem_bytes = smem;
+        p.b0 = 0; p.nb = B;
+        const long long grid = grid_cap < B ? grid_cap : B;
+        lrc = zero_counters();
+        PM_LAUNCH(pm_analyse, grid, kThreads, smem);
+        return lrc;
+    }
+    // ---- the split path, chunk by chunk
+    unsigned smem_m = 0;
+    int ctas_m = 1;
+    minapix_shape(n, &smem_m, &ctas_m);
+    long long grid_m_cap = (long long)g_sm_count * ctas_m;
+    if (grid_m_cap > PM_MAX_MINAPIX_GRID) grid_m_cap = PM_MAX_MINAPIX_GRID;
+    // tail, one warp per cutout: G groups per SM, each with an equal share of the shared memory
+    const int gpc = pm_tail_warp_groups_per_cta();
+    int tail_ctas = env_int("PM_TAIL_CTAS", pm_tail_warp_ctas_per_sm());
+    if (tail_ctas < 1) tail_ctas = 1;
+    if (tail_ctas > pm_tail_warp_ctas_per_sm()) tail_ctas = pm_tail_warp_ctas_per_sm();
+    const unsigned cap1 = (unsigned)(g_smem_optin ? g_smem_optin : 232448);
+    unsigned smem_g = (((cap1 + 1024) / (unsigned)tail_ctas - 1024) / (unsigned)gpc) & ~15u;
+    if (smem_g > 65536u) smem_g = 65536u;
+    if (smem_g < pm_tail_warp_fixed_smem(n) + 1024u) { snprintf(g_err, sizeof g_err, "shared memory too small for the tail kernel"); return PM_EINVAL; }
+    long long groups_cap = (long long)g_sm_count * tail_ctas * gpc;
+    if (groups_cap > PM_MAX_TAIL_GROUPS) groups_cap = PM_MAX_TAIL_GROUPS;
+    for (long long b0 = 0; b0 < B && lrc == PM_OK; b0 += pl.chunk) {
+        const long long nb = B - b0 < pl.chunk ? B - b0 : pl.chunk;
+        p.b0 = b0; p.nb = nb;
+        const long long grid = grid_cap < nb ? grid_cap : nb;
+        lrc = zero_counters();
+        // front
+        p.smem_bytes = smem; p.scratch_per_cta = scratch_bytes_per_cta(n);
+        PM_LAUNCH(pm_front, grid, kThreads, smem);
+        // minapix (skipped when the centre is supplied or the path stops before it)
+        if (!p.ov.centroid_in && !(flags & (PM_STOP_AFTER_PIXELMAP | PM_STOP_AFTER_RMAX))) {
+            const long long grid_m = grid_m_cap < nb ? grid_m_cap : nb;
+            p.smem_bytes = smem_m; p.scratch_per_cta = scratch_bytes_minapix(n);
+            PM_LAUNCH(pm_minapix, grid_m, kThreads, smem_m);
+        }
+        // tail (also writes the rows of the cutouts that ended early)
+        if (tail_cta) {
+            p.smem_bytes = smem; p.scratch_per_cta = scratch_bytes_per_cta(n);
+            PM_LAUNCH(pm_tail_cta, grid, kThreads, smem);
+        } else {
+            p.smem_bytes = smem_g; p.scratch_per_cta = scratch_bytes_tail(n);
+            const long long groups = groups_cap < nb ? groups_cap : nb;
+            PM_LAUNCH(pm_tail_warp, (groups + gpc - 1) / gpc, 32 * gpc, smem_g * (unsigned)gpc);
+        }
+        // the monolith pass over whatever the front kernel handed over (normally nothing)
+        p.smem_bytes = smem; p.scratch_per_cta = scratch_bytes_per_cta(n);
+        PM_LAUNCH(pm_big, grid, kThreads, smem);
+    }
+    return lrc;
 }
 
 int pm_aperpixmap_batch(int n, const double* rad, int64_t B, int nsubpix, double frac, uint8_t* mask_out,

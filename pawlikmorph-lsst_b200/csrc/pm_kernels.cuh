@@ -13,7 +13,7 @@
 #include "../../include/pawlik_b200.h"
 #include "pm_block.cuh"
 
-namespace pmk {
+namespace PM_NS {
 
 struct Params {
     const void* images;
@@ -27,9 +27,16 @@ struct Params {
     pm_row_t* rows;
     unsigned char* scratch;       // per-CTA global scratch, scratch_per_cta bytes each
     unsigned long long scratch_per_cta;
-    unsigned long long* counter;  // work counter (zeroed by the host before the launch)
-    unsigned smem_bytes;          // dynamic shared memory given to the kernel
-    unsigned long long* phase_cycles;   // optional [grid, 16] per-CTA cycle counters (tuning aid), or null
+    unsigned long long* counter;  // work counters (zeroed by the host before the launches): [0] monolith, [1] front,
+                                  // [2] minapix, [3] tail, [4] number of cutouts handed to the monolith pass
+    unsigned smem_bytes;          // dynamic shared memory given to each group (CTA, or warp of the tail kernel)
+    unsigned long long* phase_cycles;   // optional [PM_PHASE_ROWS, 48] per-group cycle counters (tuning aid), or null
+    // split path: the cutouts [b0, b0 + nb) of the batch are in flight, their hand-over state lives at state + i * stride
+    long long b0, nb;
+    unsigned char* state;
+    unsigned long long state_stride;
+    int* big_list;                // cutouts of the chunk that take the monolith pass (local indices), counter[4] of them
+    int list_cap, cand_cap;       // hand-over capacities (entries), see state_stride()
 };
 
 struct Geo {
@@ -48,33 +55,70 @@ PM_HOSTDEV Geo make_geo(int n, int fs) {
 struct SmemMap {
     unsigned sh, seg, dil, aper, rowoff, i0, tw, ri, rstart, arena, arena_bytes;
 };
+constexpr unsigned kNoSmem = 0xffffffffu;
+enum { SM_SEG = 1, SM_DIL = 2, SM_APER = 4, SM_ROWOFF = 8, SM_TABLES = 16, SM_ALL = 31 };
 PM_HOSTDEV unsigned align16(unsigned v) { return (v + 15u) & ~15u; }
-PM_HOSTDEV SmemMap make_smem_map(const Geo& g, unsigned total) {
+// Fixed part of a group's shared memory.  `mask`: the pieces this kernel keeps there; with `optional` a piece is
+// placed only while it leaves >= 1 KB of arena (the body then takes it from the arena / global scratch instead).
+PM_HOSTDEV SmemMap make_smem_map(const Geo& g, unsigned total, unsigned mask = SM_ALL, bool optional = false) {
     SmemMap s;
     unsigned o = 0;
     s.sh = o; o = align16(o + (unsigned)sizeof(Sh));
     unsigned plane = (unsigned)(g.n * g.nw * 4);
     unsigned zplane = (unsigned)(g.m * g.mw * 4);
     if (zplane > plane) plane = zplane;   // cannot happen (m <= n) but keep the aliasing safe
-    s.seg = o; o += plane;
-    s.dil = o; o += plane;
-    s.aper = o; o += plane;
-    s.rowoff = o; o = align16(o + (unsigned)(g.n + 1) * 4);
-    s.tw = o; o = align16(o + (unsigned)g.m * 8);
-    s.i0 = o; o = align16(o + (unsigned)g.m * 2);
-    s.ri = o; o = align16(o + (unsigned)g.n * 2);
-    s.rstart = o; o = align16(o + (unsigned)(g.m + 1) * 2);
+    auto fits = [&](unsigned bytes) { return !optional || o + bytes + 1024u <= total; };
+    s.seg = s.dil = s.aper = s.rowoff = s.tw = s.i0 = s.ri = s.rstart = kNoSmem;
+    const unsigned rowoff_bytes = align16((unsigned)(g.n + 1) * 4);
+    if ((mask & SM_ROWOFF) && fits(rowoff_bytes)) { s.rowoff = o; o += rowoff_bytes; }
+    if ((mask & SM_SEG) && fits(plane)) { s.seg = o; o += plane; }
+    if ((mask & SM_APER) && fits(plane)) { s.aper = o; o += plane; }
+    if ((mask & SM_DIL) && fits(plane)) { s.dil = o; o += plane; }
+    if (mask & SM_TABLES) {
+        s.tw = o; o = align16(o + (unsigned)g.m * 8);
+        s.i0 = o; o = align16(o + (unsigned)g.m * 2);
+        s.ri = o; o = align16(o + (unsigned)g.n * 2);
+        s.rstart = o; o = align16(o + (unsigned)(g.m + 1) * 2);
+    }
     s.arena = o;
     s.arena_bytes = total > o ? total - o : 0;
     return s;
 }
-PM_HOSTDEV unsigned smem_fixed_bytes(int n, int fs) {
+PM_HOSTDEV unsigned smem_fixed_bytes(int n, int fs, unsigned mask = SM_ALL) {
     Geo g = make_geo(n, fs);
-    return make_smem_map(g, 0).arena;
+    return make_smem_map(g, 0, mask).arena;
 }
 // per-CTA global scratch: exact-filter planes (2 x 8 n^2), or list/sort/window spill, or the folded table
 PM_HOSTDEV unsigned long long scratch_bytes_per_cta(int n) {
     return 64ull * (unsigned long long)n * (unsigned long long)n + 65536ull;
+}
+// ---- split path: hand-over state of one cutout between the front, minapix and tail kernels (HBM; one slot per cutout
+// of the chunk in flight).  256-byte header, the segmap and aperture bit planes, then list_cap entries holding the
+// raster list of map pixels followed by the centroid candidates.  Cutouts whose lists do not fit (or whose radius /
+// candidate count would break the scratch bounds of the later kernels) take the monolith pass instead.
+struct GalState {
+    pm_row_t row;                  // the result row as far as it is known
+    double sky, thr, rmax, abs_sum, gini, m20;
+    int status, done;              // done: 1 = nothing left for the later kernels, 2 = handed to the monolith pass
+    int n_g, r0, r1, c0, c1;       // map pixel count, bounding box (inclusive)
+    int n_cand, cx, cy;
+};
+static_assert(sizeof(GalState) <= 256, "hand-over header");
+PM_HOSTDEV int state_list_cap(int n) { return n * n / 4 + 2048; }
+PM_HOSTDEV int state_cand_cap() { return 1024; }
+PM_HOSTDEV unsigned long long state_stride(int n) {
+    const unsigned long long plane = (unsigned long long)n * ((n + 31) / 32) * 4;
+    const unsigned long long b = 256 + 2 * plane + 4ull * (unsigned long long)state_list_cap(n);
+    return (b + 255) & ~255ull;
+}
+// per-group global scratch of the minapix kernel (window of the image over the bounding box when it does not fit
+// shared memory + the candidate bookkeeping) and of the tail kernel (folded radial table <= 8 (n/2 + 4)^2 bytes x 2,
+// bit planes, band buffers)
+PM_HOSTDEV unsigned long long scratch_bytes_minapix(int n) {
+    return 8ull * (unsigned long long)n * (unsigned long long)n + 131072ull;
+}
+PM_HOSTDEV unsigned long long scratch_bytes_tail(int n) {
+    return 6ull * (unsigned long long)n * (unsigned long long)n + 131072ull;
 }
 
 PM_DEV int refl(int i, int L) {  // scipy "reflect" (d c b a | a b c d | d c b a), any distance
@@ -1310,8 +1354,14 @@ template <typename T_> PM_DEV void build_fold(Ctx<T_>& c, int cx, int cy, Fold& 
     auto fetch = [&](int dr, int dc, bool valid) -> double {
         const int r = cy + dr, col = cx + dc;
         const bool ok = valid && r >= c.r0 && r <= c.r1 && col >= c.c0 && col <= c.c1;    // the window lies inside the image
-        const T_ w = c.mw[ok ? (r - c.r0) * c.bw + (col - c.c0) : 0];
-        return (ok && w == w) ? (double)w - c.sky : 0.0;
+        if (c.mw) {
+            const T_ w = c.mw[ok ? (r - c.r0) * c.bw + (col - c.c0) : 0];
+            return (ok && w == w) ? (double)w - c.sky : 0.0;
+        }
+        // no masked window (split path): the map's bit plane and the image itself
+        const bool in = ok && bit_at(c.seg, c.g.nw, ok ? r : c.r0, ok ? col : c.c0);
+        const T_ x = pm::ldg(c.img + (size_t)(in ? r : c.r0) * c.g.n + (in ? col : c.c0));
+        return in ? (double)x - c.sky : 0.0;
     };
     auto entry_ab = [&](int e, int& a, int& b) {
         a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);     // invert the triangular index
@@ -1535,14 +1585,24 @@ PM_DEV void phase_r20_r80(Ctx<T_>& c, int cx, int cy, double radius, RadiiOut* o
     {
         // the reference subtracts delta repeatedly (rounding accumulates): every thread runs the short serial chain in
         // registers and thread k keeps r_k — no stores or branches on the chain
-        double r = radius, mine = 0.0;
+        if (kThreads > 130) {
+            double r = radius, mine = 0.0;
 #pragma unroll 10
-        for (int k = 1; k <= 130; k++) {
-            r -= delta;
-            K += (r > 0.0) ? 1 : 0;                   // r decreases monotonically: counts the leading positive radii
-            if (k == pm::tid()) mine = r;
+            for (int k = 1; k <= 130; k++) {
+                r -= delta;
+                K += (r > 0.0) ? 1 : 0;               // r decreases monotonically: counts the leading positive radii
+                if (k == pm::tid()) mine = r;
+            }
+            if (pm::tid() >= 1 && pm::tid() <= K) sh.rk[pm::tid()] = mine;
+        } else {                                      // small groups: thread t keeps the radii k = t (mod kThreads)
+            double r = radius;
+            for (int k = 1; k <= 130; k++) {
+                r -= delta;
+                const bool pos = r > 0.0;
+                K += pos ? 1 : 0;
+                if (pos && (k % kThreads) == pm::tid()) sh.rk[k] = r;
+            }
         }
-        if (pm::tid() >= 1 && pm::tid() <= K) sh.rk[pm::tid()] = mine;
     }
     pm::sync();
     double fv[kRedSlots];
@@ -2054,7 +2114,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
     c.sky = p.sky ? p.sky[b] : 0.0;
     c.thr = p.ov.threshold_in ? p.ov.threshold_in[b] : c.sky + (p.sky_err ? p.sky_err[b] : 0.0);
     c.flags = p.flags;
-    c.ar.s_top = 0; c.ar.g_top = 0; c.ar.overflow = 0;
+    c.ar.reset();
     c.crop = nullptr; c.crop_r0 = c.crop_c0 = 0; c.crop_h = c.crop_w = 0;
     pm_row_t row;
     row_defaults(row);
@@ -2252,7 +2312,7 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             pc.lap(7);   // r20 / r80
             // ---- the arena is free now: stage the central part of the image (what calcA and smoothness touch:
             // the aperture about the image centre, its mirror image about apix, the annulus about apix) in shared memory
-            c.ar.s_top = 0; c.ar.g_top = 0;
+            c.ar.reset();
             c.posR = nullptr; c.mw = nullptr;
             if (p.flags & (PM_DO_A | PM_DO_CAS | PM_DO_S)) {
                 // bounding box of {image centre, apix, mirror of the centre about apix} grown by rmax + margin
@@ -2306,22 +2366,41 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
     pm::sync();
 }
 
-template <typename T> PM_DEV void analyse_body(const Params& p) {
-    unsigned char* smem = pm::dyn_smem();
-    Ctx<T> c;
+// group setup shared by all kernels: the fixed shared-memory pieces named by `mask` (the others come out of
+// the arena, i.e. global scratch when shared memory is short), the arena, the tables
+template <typename T> PM_DEV void setup_ctx(Ctx<T>& c, const Params& p, unsigned mask, bool optional, unsigned long long scratch_per_group) {
+    unsigned char* smem = pm::dyn_smem(p.smem_bytes);
     c.g = make_geo(p.n, p.fs);
-    const SmemMap sm = make_smem_map(c.g, p.smem_bytes);
+    const SmemMap sm = make_smem_map(c.g, p.smem_bytes, mask, optional);
     c.sh = (Sh*)(smem + sm.sh);
-    c.seg = (unsigned*)(smem + sm.seg); c.dil = (unsigned*)(smem + sm.dil); c.aper = (unsigned*)(smem + sm.aper);
-    c.rowoff = (unsigned*)(smem + sm.rowoff);
-    c.tw = (double*)(smem + sm.tw); c.i0 = (uint16_t*)(smem + sm.i0); c.ri = (uint16_t*)(smem + sm.ri);
-    c.rstart = (uint16_t*)(smem + sm.rstart);
-    c.ar.init(smem + sm.arena, sm.arena_bytes, p.scratch + (size_t)pm::block() * p.scratch_per_cta, (size_t)p.scratch_per_cta);
+    c.ar.init(smem + sm.arena, sm.arena_bytes, p.scratch + (size_t)pm::block() * scratch_per_group, (size_t)scratch_per_group);
+    const size_t plane = (size_t)c.g.n * c.g.nw * 4;
+    auto piece = [&](unsigned off, bool wanted, size_t bytes) -> void* {
+        if (!wanted) return nullptr;
+        return off != kNoSmem ? (void*)(smem + off) : c.ar.alloc(bytes);
+    };
+    c.rowoff = (unsigned*)piece(sm.rowoff, mask & SM_ROWOFF, (size_t)(c.g.n + 1) * 4);
+    c.seg = (unsigned*)piece(sm.seg, mask & SM_SEG, plane);
+    c.aper = (unsigned*)piece(sm.aper, mask & SM_APER, plane);
+    c.dil = (unsigned*)piece(sm.dil, mask & SM_DIL, plane);
+    c.tw = (mask & SM_TABLES) ? (double*)(smem + sm.tw) : nullptr;
+    c.i0 = (mask & SM_TABLES) ? (uint16_t*)(smem + sm.i0) : nullptr;
+    c.ri = (mask & SM_TABLES) ? (uint16_t*)(smem + sm.ri) : nullptr;
+    c.rstart = (mask & SM_TABLES) ? (uint16_t*)(smem + sm.rstart) : nullptr;
+    c.ar.set_floor();
     c.n_g = 0; c.r0 = c.c0 = 0; c.r1 = c.c1 = -1; c.posR = nullptr; c.plist = nullptr; c.mw = nullptr; c.bw = 0;
+    c.crop = nullptr; c.crop_r0 = c.crop_c0 = 0; c.crop_h = c.crop_w = 0;
     c.mbar_phase[0] = c.mbar_phase[1] = 0u;
     c.sh->par[pm::tid()] = 0;
-    if (pm::tid() == 0) { pm::mbar_init(&c.sh->mbar[0], 1); pm::mbar_init(&c.sh->mbar[1], 1); pm::mbar_fence_init(); }
-    build_tables(c);
+    if (mask & SM_TABLES) {
+        if (pm::tid() == 0) { pm::mbar_init(&c.sh->mbar[0], 1); pm::mbar_init(&c.sh->mbar[1], 1); pm::mbar_fence_init(); }
+        build_tables(c);
+    }
+    pm::sync();
+}
+template <typename T> PM_DEV void analyse_body(const Params& p) {
+    Ctx<T> c;
+    setup_ctx(c, p, SM_ALL, false, p.scratch_per_cta);
     // Persistent CTA: galaxy indices come from a global work counter, fetched ONE AHEAD so that the next cutout
     // can optionally be pulled towards L2 (TMA bulk prefetch, PM_L2_PREFETCH) while the current one is analysed.
     // Off by default: with the TMA-staged pixelmap it no longer pays (measured -1 %: it competes for L2 capacity).
@@ -2346,10 +2425,390 @@ template <typename T> PM_DEV void analyse_body(const Params& p) {
     }
 }
 
+// ====================================================================================================
+// The split path: the same phases as analyse_one(), cut into three kernels by resource class so that every kernel
+// runs at the occupancy its phases allow (and fits the instruction cache):
+//   front   (one CTA per cutout)   pixelmap -> bbox -> raster list / keys -> rmax, aperture -> sort -> gini, m20, candidates
+//   minapix (one CTA per cutout, more CTAs per SM: the loop needs ~64 registers and window + list of shared memory)
+//   tail    (one WARP per cutout in pm_tail.cu, or one CTA)   r20/r80, calcA x3, smoothness -> result row
+// The hand-over goes through GalState slots in the workspace.  Cutouts that do not fit a slot take analyse_one().
+// ====================================================================================================
+PM_DEV GalState* state_of(const Params& p, long long i) { return (GalState*)(p.state + (size_t)i * p.state_stride); }
+PM_DEV unsigned* state_seg(GalState* gs) { return (unsigned*)((unsigned char*)gs + 256); }
+PM_DEV unsigned* state_aper(GalState* gs, const Geo& g) { return state_seg(gs) + g.n * g.nw; }
+PM_DEV unsigned* state_list(GalState* gs, const Geo& g) { return state_seg(gs) + 2 * g.n * g.nw; }
+
+// hand a cutout to the monolith pass
+PM_DEV void push_big(const Params& p, long long i, GalState* gs) {
+    if (pm::tid() == 0) {
+        const unsigned long long k = pm::atomic_add(p.counter + 4, 1ull);
+        p.big_list[k] = (int)i;
+        gs->done = 2;
+    }
+}
+
+template <typename T> PM_DEV void front_one(Ctx<T>& c, const Params& p, long long i) {
+    typedef typename KeyT<T>::type K;
+    const Geo& g = c.g;
+    Sh& sh = *c.sh;
+    const long long b = p.b0 + i;
+    GalState* gs = state_of(p, i);
+    const size_t plane_elems = (size_t)g.N;
+    c.img = (const T*)p.images + (size_t)b * plane_elems;
+    c.sky = p.sky ? p.sky[b] : 0.0;
+    c.thr = p.ov.threshold_in ? p.ov.threshold_in[b] : c.sky + (p.sky_err ? p.sky_err[b] : 0.0);
+    c.flags = p.flags;
+    c.ar.reset();
+    c.crop = nullptr; c.crop_r0 = c.crop_c0 = 0; c.crop_h = c.crop_w = 0;
+    c.mw = nullptr;
+    pm_row_t row;
+    row_defaults(row);
+    PhaseClock& pc = c.pc;
+    pc.start(p.phase_cycles ? p.phase_cycles + (size_t)pm::block() * kPhaseSlots : nullptr);
+    uint8_t* seg_out = p.out.segmap_out ? p.out.segmap_out + (size_t)b * plane_elems : nullptr;
+    int32_t* sidx_out = p.out.sorted_idx_out ? p.out.sorted_idx_out + (size_t)b * plane_elems : nullptr;
+
+    // ---- pixelmap (main.py:421) or supplied segmap (main.py:428-439)
+    int status = PM_ST_OK;
+    int edge = 0;
+    if (p.ov.segmap_in) {
+        load_plane_u8(g, p.ov.segmap_in + (size_t)b * plane_elems, c.seg);
+    } else {
+        status = phase_pixelmap(c);
+        if (status != PM_ST_OK) {
+            for (int k = pm::tid(); k < g.n * g.nw; k += kThreads) c.seg[k] = 0;
+            pm::sync();
+        }
+    }
+    if (seg_out) store_plane_u8(g, c.seg, seg_out);
+    pc.lap(0);   // pixelmap (+ segmap store)
+    if (status == PM_ST_OK) phase_bbox(c, &edge);
+    if (status == PM_ST_OK && !p.ov.segmap_in) row.object_edge = (double)edge;   // main.py:427 (only on the pixelmap path)
+    if (p.ov.segmap_in && (p.flags & PM_STOP_AFTER_PIXELMAP)) row.object_edge = (double)edge;
+    bool done = status != PM_ST_OK || (p.flags & PM_STOP_AFTER_PIXELMAP);
+    if (!done && c.r1 < 0) { status = PM_ST_EMPTY_SEGMAP; done = true; }
+    double rmax = 0.0, gini = -99.0, m20 = -99.0, abs_sum = 0.0;
+    int n_cand = 0;
+    if (!done) {
+        unsigned ng = 0;
+        for (int r = pm::tid(); r < g.n; r += kThreads) {   // n_g first (for the allocations)
+            const unsigned cnt = row_popcount(c.seg, g.nw, r);
+            c.rowoff[r] = cnt;            // stays there for phase_list
+            ng += cnt;
+        }
+        c.n_g = (int)block_sum_u(sh, ng);
+        const int n_g = c.n_g;
+        if (n_g + p.cand_cap > p.list_cap) { push_big(p, i, gs); return; }     // lists would not fit the slot
+        c.bw = c.c1 - c.c0 + 1;
+        c.posR = (unsigned*)c.ar.alloc((size_t)n_g * 4);
+        unsigned* spA = (unsigned*)c.ar.alloc((size_t)n_g * 4);     // sorted positions end up here
+        K* skA = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
+        Arena::Mark mk_keys = c.ar.mark();
+        K* skB = (K*)c.ar.alloc((size_t)n_g * sizeof(K));
+        unsigned* spB = (unsigned*)c.ar.alloc((size_t)n_g * 4);
+        int sort_db = kMaxDigitBits;
+        Arena::Mark mk_hist = c.ar.mark();
+        unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * kMaxDigits * 4);
+        if (!c.ar.in_smem(hist)) {
+            c.ar.release(mk_hist);
+            sort_db = 8;
+            hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+        }
+        if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
+        SegStats st;
+        st.sum = st.m10 = st.m01 = st.vmax = st.abs_sum = 0.0; st.argmax = 0; st.edge = edge;
+        SortOut so;
+        so.gini = so.m20 = -99.0; so.n_cand = 0; so.n_pos = 0;
+        if (!done) {
+            phase_list(c, skA, &st);
+            pc.lap(1);   // bbox, counts, raster list
+            int cen_flat = 0;
+            const int rmax2 = phase_rmax2(c, st, &cen_flat);
+            pc.lap(40);
+            rmax = p.ov.radius_in ? p.ov.radius_in[b] : pm::dsqrt((double)rmax2);
+            // the later kernels size their folded radial table by the radius: very large ones take the monolith pass
+            if (!(rmax <= 0.5 * (double)g.n)) { push_big(p, i, gs); return; }
+            row.rmax = rmax;
+            abs_sum = st.abs_sum;
+            if (p.ov.apermask_in) {
+                load_plane_u8(g, p.ov.apermask_in + (size_t)b * plane_elems, c.aper);
+            } else {
+                Arena::Mark mk = c.ar.mark();
+                double* sq = (double*)c.ar.alloc((size_t)(g.half + 1) * 9 * 8);
+                int* hw = (int*)c.ar.alloc((size_t)(g.half + 1) * 4);
+                build_aperture(g, rmax, 9, 0.1, c.aper, sq, hw);
+                c.ar.release(mk);
+            }
+            if (p.out.apermask_out) store_plane_u8(g, c.aper, p.out.apermask_out + (size_t)b * plane_elems);
+            pc.lap(2);   // rmax + aperture
+            if (p.flags & PM_STOP_AFTER_RMAX) done = true;
+        }
+        if (!done) {
+            unsigned* st_list = state_list(gs, g);
+            for (int k = pm::tid(); k < n_g; k += kThreads) { const unsigned q = c.posR[k]; spA[k] = q; st_list[k] = q; }
+            pm::sync();
+            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db, [&](int ph) { pc.lap(ph); });
+            if (where) {
+                for (int k = pm::tid(); k < n_g; k += kThreads) { spA[k] = spB[k]; skA[k] = skB[k]; }
+                pm::sync();
+            }
+            c.ar.release(mk_keys);    // drop skB, spB, hist
+            pc.lap(3);   // sort
+            phase_gini_m20_cands(c, skA, spA, st, &so);
+            row.n_candidates = (double)so.n_cand;
+            n_cand = so.n_cand;
+            gini = so.gini; m20 = so.m20;
+            if (n_cand > p.cand_cap) { push_big(p, i, gs); return; }
+            // the canonical DESCENDING order (value desc, flat index desc), asymmetry.py:94-95: the candidates are its head
+            for (int k = pm::tid(); k < n_cand; k += kThreads) st_list[n_g + k] = spA[n_g - 1 - k];
+            if (sidx_out) {
+                for (int k = pm::tid(); k < g.N; k += kThreads) {
+                    int v = -1;
+                    if (k < so.n_pos) { const unsigned q = spA[n_g - 1 - k]; v = (int)(q >> 16) * g.n + (int)(q & 0xffff); }
+                    sidx_out[k] = v;
+                }
+            }
+            if (p.out.n_positive_out && pm::tid() == 0) p.out.n_positive_out[b] = so.n_pos;
+            pc.lap(4);   // gini, m20, candidates
+        }
+    }
+    // ---- hand-over
+    if (!done) {
+        unsigned* ss = state_seg(gs);
+        unsigned* sa = state_aper(gs, g);
+        for (int k = pm::tid(); k < g.n * g.nw; k += kThreads) { ss[k] = c.seg[k]; sa[k] = c.aper[k]; }
+    }
+    if (pm::tid() == 0) {
+        gs->row = row;
+        gs->sky = c.sky; gs->thr = c.thr; gs->rmax = rmax; gs->abs_sum = abs_sum; gs->gini = gini; gs->m20 = m20;
+        gs->status = status; gs->done = done ? 1 : 0;
+        gs->n_g = c.n_g; gs->r0 = c.r0; gs->r1 = c.r1; gs->c0 = c.c0; gs->c1 = c.c1;
+        gs->n_cand = n_cand; gs->cx = 0; gs->cy = 0;
+    }
+    pm::sync();
+}
+
+// image over the map's bounding box with NaN outside the map (the window minapix pairs pixels through), from the image
+// and the map's bit plane `seg` (any address space)
+template <typename T> PM_DEV void build_window(const Ctx<T>& c, const unsigned* seg, T* mw) {
+    const Geo& g = c.g;
+    const int bh = c.r1 - c.r0 + 1;
+    for (int wr = pm::warp(); wr < bh; wr += kWarps) {        // one window row per warp, loads independent
+        const int r = c.r0 + wr;
+        const T* src = c.img + (size_t)r * g.n + c.c0;
+        for (int x = pm::lane(); x < c.bw; x += 32)
+            mw[wr * c.bw + x] = bit_at(seg, g.nw, r, c.c0 + x) ? pm::ldg(src + x) : nan_of(T());
+    }
+}
+
+template <typename T> PM_DEV void minapix_one(Ctx<T>& c, const Params& p, long long i) {
+    const Geo& g = c.g;
+    const long long b = p.b0 + i;
+    GalState* gs = state_of(p, i);
+    if (gs->done) return;
+    PhaseClock& pc = c.pc;
+    pc.start(p.phase_cycles ? p.phase_cycles + (size_t)pm::block() * kPhaseSlots : nullptr);
+    const int n_cand = gs->n_cand;
+    if (n_cand == 0) {                                   // np.argmin([]) upstream (asymmetry.py:127)
+        pm::sync();
+        if (pm::tid() == 0) { gs->status = PM_ST_NO_CANDIDATE; gs->done = 1; }
+        pm::sync();
+        return;
+    }
+    c.img = (const T*)p.images + (size_t)b * (size_t)g.N;
+    c.sky = gs->sky; c.flags = p.flags;
+    c.n_g = gs->n_g; c.r0 = gs->r0; c.r1 = gs->r1; c.c0 = gs->c0; c.c1 = gs->c1;
+    c.bw = c.c1 - c.c0 + 1;
+    const int bh = c.r1 - c.r0 + 1, n_g = c.n_g;
+    const double abs_sum = gs->abs_sum;
+    c.ar.reset();
+    c.crop = nullptr;
+    const unsigned* st_seg = state_seg(gs);
+    const unsigned* st_aper = state_aper(gs, g);
+    const unsigned* st_list = state_list(gs, g);
+    for (int k = pm::tid(); k < g.n * g.nw; k += kThreads) c.aper[k] = st_aper[k];
+    // the window and the list in shared memory when they fit (else the window in global scratch, the list in place)
+    T* mw = (T*)c.ar.alloc((size_t)c.bw * bh * sizeof(T));
+    unsigned* plist = (unsigned*)c.ar.alloc_smem((size_t)n_g * 4);
+    unsigned* cand = (unsigned*)c.ar.alloc((size_t)n_cand * 4);
+    int status = PM_ST_OK;
+    if (c.ar.overflow) status = PM_ST_WORKSPACE;
+    int best = 0;
+    if (status == PM_ST_OK) {
+        build_window(c, st_seg, mw);
+        if (plist) { for (int k = pm::tid(); k < n_g; k += kThreads) plist[k] = st_list[k]; }
+        for (int k = pm::tid(); k < n_cand; k += kThreads) cand[k] = st_list[n_g + k];
+        pm::sync();
+        c.mw = mw;
+        c.posR = plist ? plist : const_cast<unsigned*>(st_list);
+        c.plist = c.posR;
+        pc.lap(41);   // (minapix kernel: window + lists)
+        const int groups = (n_cand + kCandBlock - 1) / kCandBlock;
+        const bool prune = p.out.cand_a_out == nullptr && n_cand > 2 * kCandBlock && !(p.flags & PM_NO_PRUNE);
+        if (prune) {
+            double* acc = (double*)c.ar.alloc((size_t)n_cand * 16);
+            int* alive = (int*)c.ar.alloc((size_t)n_cand * 4);
+            int* alive2 = (int*)c.ar.alloc((size_t)n_cand * 4);
+            unsigned* flag = (unsigned*)c.ar.alloc((size_t)(n_cand + 1) * 4);
+            double* parts = (double*)c.ar.alloc((size_t)(kWarps + groups) * 64);
+            if (c.ar.overflow) status = PM_ST_WORKSPACE;
+            else phase_minapix_pruned(c, cand, n_cand, abs_sum, acc, alive, alive2, flag, parts, &best);
+        } else {
+            int slices = (3 * kWarps + groups - 1) / groups;       // aim at >= 3 work items per warp
+            slices = max(1, min(slices, (n_g + 63) / 64));
+            double* a_arr = (double*)c.ar.alloc((size_t)n_cand * 8);
+            double* parts = (double*)c.ar.alloc((size_t)groups * slices * kCandBlock * 16);
+            if (c.ar.overflow) status = PM_ST_WORKSPACE;
+            else {
+                phase_minapix(c, cand, n_cand, a_arr, parts, slices, &best);
+                if (p.out.cand_a_out) {
+                    for (int k = pm::tid(); k < p.out.cand_cap; k += kThreads)
+                        p.out.cand_a_out[(size_t)b * p.out.cand_cap + k] = k < n_cand ? a_arr[k] : -99.0;
+                }
+            }
+        }
+    }
+    pm::sync();
+    if (pm::tid() == 0) {
+        if (status != PM_ST_OK) { gs->status = status; gs->done = 1; }
+        else { const unsigned q = cand[best]; gs->cy = (int)(q >> 16); gs->cx = (int)(q & 0xffff); }
+    }
+    pc.lap(5);   // minapix
+    pm::sync();
+    c.mw = nullptr; c.posR = nullptr; c.plist = nullptr;
+}
+
+template <typename T> PM_DEV void tail_one(Ctx<T>& c, const Params& p, long long i) {
+    const Geo& g = c.g;
+    const long long b = p.b0 + i;
+    GalState* gs = state_of(p, i);
+    const int done_in = gs->done;
+    if (done_in == 2) return;                            // the monolith pass writes this row
+    pm_row_t row = gs->row;
+    int status = gs->status;
+    PhaseClock& pc = c.pc;
+    pc.start(p.phase_cycles ? p.phase_cycles + (size_t)pm::block() * kPhaseSlots : nullptr);
+    if (!done_in) {
+        c.img = (const T*)p.images + (size_t)b * (size_t)g.N;
+        c.sky = gs->sky; c.flags = p.flags;
+        c.n_g = gs->n_g; c.r0 = gs->r0; c.r1 = gs->r1; c.c0 = gs->c0; c.c1 = gs->c1;
+        c.bw = c.c1 - c.c0 + 1;
+        c.mw = nullptr; c.posR = nullptr; c.plist = nullptr;
+        c.crop = nullptr; c.crop_r0 = c.crop_c0 = 0; c.crop_h = c.crop_w = 0;
+        c.ar.reset();
+        const double rmax = gs->rmax;
+        int cx, cy;
+        if (p.ov.centroid_in) { cx = (int)p.ov.centroid_in[2 * b]; cy = (int)p.ov.centroid_in[2 * b + 1]; }
+        else { cx = gs->cx; cy = gs->cy; }
+        const unsigned* st_seg = state_seg(gs);
+        const unsigned* st_aper = state_aper(gs, g);
+        for (int k = pm::tid(); k < g.n * g.nw; k += kThreads) { c.seg[k] = st_seg[k]; c.aper[k] = st_aper[k]; }
+        pm::sync();
+        pc.lap(42);  // (tail kernel: planes)
+        row.apix_col = (double)cx; row.apix_row = (double)cy;
+        if (p.flags & PM_DO_CAS) { row.gini = gs->gini; row.m20 = gs->m20; }
+        // ---- r20, r80, C (main.py:491-492)
+        if (p.flags & PM_DO_CAS) {
+            RadiiOut ro;
+            phase_r20_r80(c, cx, cy, rmax, &ro);
+            if (ro.ok) {
+                row.r20 = ro.r20; row.r80 = ro.r80;
+                row.C = 5.0 * log10(ro.r80 / ro.r20);
+            } else {
+                status = PM_ST_BAD_BRACKET;
+            }
+        }
+        pc.lap(7);   // r20 / r80
+        c.ar.reset();
+        // ---- CTA groups: stage the central part of the image (what calcA and smoothness touch) in shared memory
+        if (kWarps > 1 && (p.flags & (PM_DO_A | PM_DO_CAS | PM_DO_S))) {
+            const int reach = (int)fmin(rmax, 4096.0) + 12;
+            int lo_r = max(0, min(min(g.half, cy), 2 * cy - g.half) - reach), hi_r = min(g.n - 1, max(max(g.half, cy), 2 * cy - g.half) + reach);
+            int lo_c = max(0, min(min(g.half, cx), 2 * cx - g.half) - reach), hi_c = min(g.n - 1, max(max(g.half, cx), 2 * cx - g.half) + reach);
+            const long long room = (long long)(c.ar.s_cap - c.ar.s_top) - (long long)(g.n * g.nw * 12 + 24 * 1024);
+            while ((long long)(hi_r - lo_r + 1) * (hi_c - lo_c + 1) * (long long)sizeof(T) > room && hi_r - lo_r > 16 && hi_c - lo_c > 16) {
+                lo_r++; hi_r--; lo_c++; hi_c--;
+            }
+            const int ch = hi_r - lo_r + 1, cw = hi_c - lo_c + 1;
+            if (ch > 0 && cw > 0 && (long long)ch * cw * (long long)sizeof(T) <= room) {
+                T* cb = (T*)c.ar.alloc((size_t)ch * cw * sizeof(T));
+                for (int wr = pm::warp(); wr < ch; wr += kWarps) {
+                    const T* src = c.img + (size_t)(lo_r + wr) * g.n + lo_c;
+                    int x = pm::lane();
+                    for (; x + 96 < cw; x += 128) {       // four independent loads in flight
+                        const T a0 = pm::ldg(src + x), a1 = pm::ldg(src + x + 32), a2 = pm::ldg(src + x + 64), a3 = pm::ldg(src + x + 96);
+                        cb[wr * cw + x] = a0; cb[wr * cw + x + 32] = a1; cb[wr * cw + x + 64] = a2; cb[wr * cw + x + 96] = a3;
+                    }
+                    for (; x < cw; x += 32) cb[wr * cw + x] = pm::ldg(src + x);
+                }
+                pm::sync();
+                c.crop = cb; c.crop_r0 = lo_r; c.crop_c0 = lo_c; c.crop_h = ch; c.crop_w = cw;
+            }
+        }
+        // ---- calcA x3 (main.py:470-478)
+        if (p.flags & (PM_DO_A | PM_DO_AS | PM_DO_CAS)) {
+            Arena::Mark mk = c.ar.mark();
+            unsigned* tmp = (unsigned*)c.ar.alloc((size_t)g.n * g.nw * 4);
+            AsymOut ao;
+            phase_calcA(c, cx, cy, &ao, tmp);
+            c.ar.release(mk);
+            if (p.flags & (PM_DO_A | PM_DO_CAS)) { row.A = ao.A; row.Abgr = ao.Abgr; }
+            if (p.flags & PM_DO_AS) { row.As = ao.As; row.As90 = ao.As90; }
+        }
+        pc.lap(6);   // calcA x3
+        // ---- smoothness (casgm.py:276; the call is commented out at main.py:494)
+        if (p.flags & PM_DO_S) {
+            const double r20 = p.ov.r20_in ? p.ov.r20_in[b] : row.r20;
+            const double skyt = p.ov.smooth_sky_in ? p.ov.smooth_sky_in[b] : c.sky;
+            if (status == PM_ST_OK && (p.ov.r20_in || (p.flags & PM_DO_CAS)))
+                row.S = phase_smoothness(c, cx, cy, rmax, r20, skyt);
+        }
+        c.crop = nullptr;
+    }
+    pc.lap(8);   // smoothness (or whatever ended the cutout early)
+    row.status = (double)status;
+    if (pm::tid() == 0) p.rows[b] = row;
+    pm::sync();
+}
+
+// persistent groups: cutout indices of the chunk come from a work counter
+template <typename F> PM_DEV void work_loop(Sh& sh, unsigned long long* counter, long long nb, F&& fn) {
+    for (;;) {
+        pm::sync();
+        if (pm::tid() == 0) sh.ia[0] = (int)pm::atomic_add(counter, 1ull);
+        pm::sync();
+        const long long cur = (long long)sh.ia[0];
+        if (cur >= nb) break;
+        fn(cur);
+    }
+}
+template <typename T> PM_DEV void front_body(const Params& p) {
+    Ctx<T> c;
+    setup_ctx(c, p, SM_ALL, false, p.scratch_per_cta);
+    work_loop(*c.sh, p.counter + 1, p.nb, [&](long long i) { front_one(c, p, i); });
+}
+template <typename T> PM_DEV void minapix_body(const Params& p) {
+    Ctx<T> c;
+    setup_ctx(c, p, SM_APER, false, p.scratch_per_cta);
+    work_loop(*c.sh, p.counter + 2, p.nb, [&](long long i) { minapix_one(c, p, i); });
+}
+template <typename T> PM_DEV void tail_body(const Params& p) {
+    Ctx<T> c;
+    setup_ctx(c, p, SM_ROWOFF | SM_SEG | SM_APER | SM_DIL, kWarps == 1, p.scratch_per_cta);
+    work_loop(*c.sh, p.counter + 3, p.nb, [&](long long i) { tail_one(c, p, i); });
+}
+// the monolith pass over the cutouts the front kernel handed over (rare: lists / radii beyond the slot bounds)
+template <typename T> PM_DEV void big_body(const Params& p) {
+    Ctx<T> c;
+    setup_ctx(c, p, SM_ALL, false, p.scratch_per_cta);
+    const long long nbig = (long long)p.counter[4];
+    work_loop(*c.sh, p.counter + 0, nbig, [&](long long k) { analyse_one(c, p, p.b0 + (long long)p.big_list[k]); });
+}
+
 // apertures.aperpixmap for a batch of radii (one CTA per mask)
 PM_DEV void aperpixmap_body(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out,
                             unsigned smem_bytes) {
-    unsigned char* smem = pm::dyn_smem();
+    unsigned char* smem = pm::dyn_smem(smem_bytes);
     const Geo g = make_geo(n, 1);
     unsigned* plane = (unsigned*)smem;
     double* sq = (double*)(smem + align16((unsigned)(g.n * g.nw * 4)));
@@ -2366,4 +2825,4 @@ PM_HOSTDEV unsigned aperpixmap_smem_bytes(int n, int ns) {
     return align16((unsigned)(g.n * g.nw * 4)) + align16((unsigned)((g.half + 1) * ns * 8)) + align16((unsigned)((g.half + 1) * 4));
 }
 
-}  // namespace pmk
+}  // namespace PM_NS

@@ -15,16 +15,13 @@
 #define PM_DEV_NOINLINE __device__ __noinline__
 #define PM_HOSTDEV __host__ __device__ inline
 #define PM_KERNEL __global__
-namespace pm {
-PM_DEV int tid() { return threadIdx.x; }
-PM_DEV int nthreads() { return blockDim.x; }
+// Execution groups.  The phase code is written against pm::tid() / pm::warp() / pm::sync() of a GROUP of kThreads
+// threads that analyses one cutout.  Two groups exist: the whole CTA (the default: __syncthreads barriers), and — for
+// translation units compiled with PM_GROUP_WARP — a single warp (32 threads, __syncwarp as the barrier, several
+// independent groups per CTA, each with its own slice of the dynamic shared memory).  The latency-bound tail of the
+// path (r20/r80, calcA, smoothness) runs warp-per-cutout so that many cutouts are in flight per SM.
+namespace pm_common {
 PM_DEV int lane() { return threadIdx.x & 31; }
-PM_DEV int warp() { return threadIdx.x >> 5; }
-PM_DEV int nwarps() { return blockDim.x >> 5; }
-PM_DEV int block() { return blockIdx.x; }
-PM_DEV int nblocks() { return gridDim.x; }
-PM_DEV void sync() { __syncthreads(); }
-PM_DEV int sync_or(int p) { return __syncthreads_or(p); }
 PM_DEV void syncwarp() { __syncwarp(); }
 PM_DEV unsigned ballot(int p) { return __ballot_sync(0xffffffffu, p); }
 PM_DEV unsigned match_any(unsigned v) { return __match_any_sync(0xffffffffu, v); }
@@ -132,9 +129,40 @@ PM_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_sh
 PM_DEV unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 PM_DEV float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 PM_DEV double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
-PM_DEV unsigned char* dyn_smem() {
+}  // namespace pm_common
+#if defined(PM_GROUP_WARP)
+namespace pm_grp_warp {
+using namespace pm_common;
+PM_DEV int tid() { return threadIdx.x & 31; }
+PM_DEV int nthreads() { return 32; }
+PM_DEV int warp() { return 0; }
+PM_DEV int nwarps() { return 1; }
+PM_DEV int block() { return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); }
+PM_DEV int nblocks() { return gridDim.x * (blockDim.x >> 5); }
+PM_DEV void sync() { __syncwarp(); }
+PM_DEV int sync_or(int p) { return __any_sync(0xffffffffu, p); }
+PM_DEV unsigned char* dyn_smem(unsigned group_bytes) {
+    extern __shared__ __align__(16) unsigned char pm_dyn_smem[];
+    return pm_dyn_smem + (size_t)(threadIdx.x >> 5) * group_bytes;
+}
+}  // namespace pm_grp_warp
+namespace pm = pm_grp_warp;
+#else
+namespace pm_grp_cta {
+using namespace pm_common;
+PM_DEV int tid() { return threadIdx.x; }
+PM_DEV int nthreads() { return blockDim.x; }
+PM_DEV int warp() { return threadIdx.x >> 5; }
+PM_DEV int nwarps() { return blockDim.x >> 5; }
+PM_DEV int block() { return blockIdx.x; }
+PM_DEV int nblocks() { return gridDim.x; }
+PM_DEV void sync() { __syncthreads(); }
+PM_DEV int sync_or(int p) { return __syncthreads_or(p); }
+PM_DEV unsigned char* dyn_smem(unsigned) {
     extern __shared__ __align__(16) unsigned char pm_dyn_smem[];
     return pm_dyn_smem;
 }
-}  // namespace pm
+}  // namespace pm_grp_cta
+namespace pm = pm_grp_cta;
+#endif
 #endif

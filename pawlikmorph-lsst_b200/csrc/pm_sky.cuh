@@ -188,7 +188,7 @@ template <typename T> PM_DEV SkyStats sky_stats(Sh& sh, SkyScratch& sc, const Sk
 
 template <typename T>
 PM_DEV void sky_body(const T* images, long long B, int n, const double* ellipse, double* out) {
-    unsigned char* smem = pm::dyn_smem();
+    unsigned char* smem = pm::dyn_smem(0);
     Sh& sh = *(Sh*)smem;
     SkyScratch& sc = *(SkyScratch*)(smem + align16((unsigned)sizeof(Sh)));
     unsigned* mask = (unsigned*)(smem + align16((unsigned)sizeof(Sh)) + align16((unsigned)sizeof(SkyScratch)));

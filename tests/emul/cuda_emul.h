@@ -59,17 +59,12 @@ inline void yield_() {
 void run_block(int block_id, int nblocks, int nthreads, size_t smem_bytes, const std::function<void()>& body);
 }  // namespace pm_emul
 
-namespace pm {
+namespace pm_common {
 using pm_emul::g_blk;
-PM_DEV int tid() { return g_blk->cur; }
-PM_DEV int nthreads() { return g_blk->nthreads; }
 PM_DEV int lane() { return g_blk->cur & 31; }
-PM_DEV int warp() { return g_blk->cur >> 5; }
-PM_DEV int nwarps() { return g_blk->nthreads >> 5; }
-PM_DEV int block() { return g_blk->block_id; }
-PM_DEV int nblocks() { return g_blk->nblocks; }
 
-PM_DEV int sync_or(int p) {
+// block barrier (all fibres of the emulated CTA)
+PM_DEV int block_sync_or_(int p) {
     pm_emul::Block* b = g_blk;
     int me = b->cur;
     unsigned long long my_gen = b->tgen[me]++;
@@ -85,7 +80,6 @@ PM_DEV int sync_or(int p) {
     while (b->bar_gen <= my_gen) pm_emul::yield_();
     return b->bar_or_result;
 }
-PM_DEV void sync() { (void)sync_or(0); }
 
 // generic warp rendez-vous: publish a 64-bit value, return all 32 once everyone arrived
 PM_DEV void warp_exchange_(uint64_t mine, uint64_t out[32]) {
@@ -212,8 +206,37 @@ PM_DEV unsigned smem_addr(const void* p) {
 PM_DEV unsigned lds_u32(unsigned a) { unsigned v; memcpy(&v, g_blk->smem + a, 4); return v; }
 PM_DEV float lds_f32(unsigned a) { float v; memcpy(&v, g_blk->smem + a, 4); return v; }
 PM_DEV double lds_f64(unsigned a) { double v; memcpy(&v, g_blk->smem + a, 8); return v; }
-PM_DEV unsigned char* dyn_smem() { return g_blk->smem; }
-}  // namespace pm
+}  // namespace pm_common
+// execution groups, see pm_platform.cuh: the whole emulated CTA, or (PM_GROUP_WARP) one warp of it
+#if defined(PM_GROUP_WARP)
+namespace pm_grp_warp {
+using namespace pm_common;
+PM_DEV int tid() { return g_blk->cur & 31; }
+PM_DEV int nthreads() { return 32; }
+PM_DEV int warp() { return 0; }
+PM_DEV int nwarps() { return 1; }
+PM_DEV int block() { return g_blk->block_id * (g_blk->nthreads >> 5) + (g_blk->cur >> 5); }
+PM_DEV int nblocks() { return g_blk->nblocks * (g_blk->nthreads >> 5); }
+PM_DEV void sync() { syncwarp(); }
+PM_DEV int sync_or(int p) { return ballot(p) != 0u; }
+PM_DEV unsigned char* dyn_smem(unsigned group_bytes) { return g_blk->smem + (size_t)(g_blk->cur >> 5) * group_bytes; }
+}  // namespace pm_grp_warp
+namespace pm = pm_grp_warp;
+#else
+namespace pm_grp_cta {
+using namespace pm_common;
+PM_DEV int tid() { return g_blk->cur; }
+PM_DEV int nthreads() { return g_blk->nthreads; }
+PM_DEV int warp() { return g_blk->cur >> 5; }
+PM_DEV int nwarps() { return g_blk->nthreads >> 5; }
+PM_DEV int block() { return g_blk->block_id; }
+PM_DEV int nblocks() { return g_blk->nblocks; }
+PM_DEV int sync_or(int p) { return block_sync_or_(p); }
+PM_DEV void sync() { (void)block_sync_or_(0); }
+PM_DEV unsigned char* dyn_smem(unsigned) { return g_blk->smem; }
+}  // namespace pm_grp_cta
+namespace pm = pm_grp_cta;
+#endif
 
 // what kernels use from the CUDA headers
 #ifndef __CUDACC__

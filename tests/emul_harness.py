@@ -21,7 +21,7 @@ _spec.loader.exec_module(abi)
 
 def _sources():
     cs = os.path.join(PKG, "csrc")
-    return [os.path.join(cs, f) for f in os.listdir(cs)] + [os.path.join(REPO, "tests", "emul", f)
+    return [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith((".cu", ".cuh"))] + [os.path.join(REPO, "tests", "emul", f)
                                                               for f in ("cuda_emul.h", "cuda_emul.cpp")] + \
         [os.path.join(REPO, "include", "pawlik_b200.h")]
 
@@ -32,7 +32,9 @@ def build(force=False):
         return SO
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DPM_EMULATE",
            "-I" + os.path.join(REPO, "tests", "emul"), "-I" + os.path.join(REPO, "include"),
-           "-x", "c++", os.path.join(PKG, "csrc", "pm_capi.cu"), os.path.join(REPO, "tests", "emul", "cuda_emul.cpp"),
+           "-x", "c++"] + [os.path.join(PKG, "csrc", u) for u in ("pm_capi.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu",
+                                                                   "pm_k_tailcta.cu", "pm_tail.cu")] + [
+           os.path.join(REPO, "tests", "emul", "cuda_emul.cpp"),
            "-o", SO]
     subprocess.run(cmd, check=True)
     return SO
@@ -82,7 +84,7 @@ def analyse(images, sky, sky_err, filter_size=3, flags=abi.PM_DO_ALL, segmap_in=
     if "cand" in want:
         res["cand_a"] = np.full((B, cap), -7.0, np.float64)
     out = abi.Outputs(_p(res.get("segmap")), _p(res.get("sorted_idx")), _p(res.get("n_positive")),
-                      _p(res.get("apermask")), _p(res.get("cand_a")), cap)
+                      _p(res.get("apermask")), _p(res.get("cand_a")), cap, None)
     rows = np.full((B, abi.ROW_DOUBLES), np.nan, np.float64)
     wsb = L.pm_workspace_bytes(B, n, dtype)
     ws = np.zeros(wsb // 8 + 2, np.float64)

@@ -27,10 +27,17 @@ def test_library_builds_loads_and_exports_every_symbol():
     for name in _header_functions():
         assert hasattr(L, name), name
     L = pm._lib.lib()
-    assert L.pm_abi_version() == 1
+    assert L.pm_abi_version() == 2
     assert L.pm_workspace_bytes(0, 256, 0) == 0
-    assert L.pm_workspace_bytes(1, 256, 0) == 256 + 64 * 256 * 256 + 65536
-    assert L.pm_workspace_bytes(10 ** 6, 256, 0) == 256 + 592 * (64 * 256 * 256 + 65536)
+
+    def want(B, n):          # pm_capi.cu make_plan(): counters | big list | per-group scratch | hand-over slots of a chunk
+        up = lambda v: (v + 255) // 256 * 256
+        stride = up(256 + 2 * n * ((n + 31) // 32) * 4 + 4 * (n * n // 4 + 2048))
+        chunk = min(B, 49152, max(1024, (4 << 30) // stride))
+        scratch = max(min(B, 592) * (64 * n * n + 65536), min(B, 640) * (8 * n * n + 131072), min(B, 5120) * (6 * n * n + 131072))
+        return up(256 + 4 * chunk) + up(scratch) + chunk * stride
+    for B, n in ((1, 256), (10 ** 6, 256), (5000, 140), (3, 512), (10 ** 5, 640)):
+        assert L.pm_workspace_bytes(B, n, 0) == want(B, n), (B, n)
     assert L.pm_workspace_bytes(1, 10 ** 4, 0) == 0          # n > PM_MAX_N
 
 
