@@ -220,7 +220,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         cyc = buf.sum(dim=0).cpu().numpy().astype(float)
         tot = cyc.sum()
-        print("phase cycles per galaxy: " + ", ".join(f"{nm} {c / B:.0f} ({100 * c / tot:.1f}%)" for nm, c in zip(names, cyc) if c > 0)
+        print("phase cycles per galaxy: " + ", ".join((f"{nm} {c / B:.3f}" if nm.startswith("#") else f"{nm} {c / B:.0f} ({100 * c / tot:.1f}%)") for nm, c in zip(names, cyc) if c > 0)
               + f"; total {tot / B:.0f}", file=sys.stderr, flush=True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -245,6 +245,15 @@ def run_ours(args):
     status = rows[:, 14]
     n_ok = int((status == 0).sum().item())
     mean_cands = float(rows[:, 15].mean().item())
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"value": value, "unit": UNIT, "ms_per_step": total_ms / args.steps, "galaxies": B, "n": n,
+                              "ok_fraction": n_ok / B, "mean_candidates": mean_cands, "launches": int(launches),
+                              "flags": FLAGS_ALL, "clocks": clocks}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public host API: pinned host images -> rows on the host
     E = min(args.e2e_batch, B)
@@ -401,6 +410,7 @@ def main():
     ap.add_argument("--e2e-payload-chunk", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning: stop after the resident timed steps (short JSON line)")
     ap.add_argument("--phases", action="store_true", help="print per-phase cycle shares to stderr (tuning aid)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -63,10 +63,11 @@ extern "C" {
 #define PM_NO_NOISECORRECT 0x1000u    /* calcA(..., noisecorrect=False): Abgr = 0, A not corrected */
 #define PM_NO_PRUNE 0x4000u           /* tuning/test: evaluate every minapix candidate completely (no exact pruning) */
 #define PM_L2_PREFETCH 0x2000u        /* tuning: TMA-prefetch the next cutout into L2 while the current one runs (off) */
-#define PM_PATH_MONOLITH 0x8000u      /* tuning/test: one fused kernel per batch (one CTA per cutout through every phase)
-                                         instead of the three kernels split by resource class */
-#define PM_TAIL_CTA 0x10000u          /* tuning/test: the tail kernel (r20/r80, calcA, S) with one CTA per cutout instead of
-                                         one warp per cutout */
+#define PM_RADIX_SORT 0x20000u        /* tuning/test: always the LSD radix sort (the fallback of the bucket sort) */
+#define PM_PATH_SPLIT 0x8000u         /* three kernels per chunk split by resource class (front / minapix / tail)
+                                         instead of the one fused kernel (the default: measured faster, profiles/) */
+#define PM_TAIL_WARP 0x10000u         /* with PM_PATH_SPLIT: the tail kernel (r20/r80, calcA, S) with one warp per cutout
+                                         instead of one CTA per cutout */
 
 /* pm_row_t.status */
 #define PM_ST_OK 0
@@ -129,9 +130,9 @@ size_t pm_workspace_bytes(int64_t B, int n, int dtype);
  *   asymmetry.minapix                     (asymmetry.py:50-129)               main.py:467
  *   asymmetry.calcA x3                    (asymmetry.py:132-257)              main.py:470-478
  *   casgm.calcR20_R80, concentration, gini, m20, smoothness (casgm.py)        main.py:490-495
- * Three kernels per chunk of the batch, split by resource class: front (one CTA per cutout: pixelmap ..
- * candidates; the only pass that streams the image from HBM), minapix (one CTA per cutout at higher occupancy), tail
- * (one warp per cutout: r20/r80, calcA x3, smoothness).  The hand-over state lives in `workspace`.
+ * One fused kernel, one CTA per cutout, the image streamed from HBM once (default); with PM_PATH_SPLIT three kernels per
+ * chunk of the batch, split by resource class: front (pixelmap .. candidates), minapix, tail (r20/r80,
+ * calcA x3, smoothness), their hand-over state in `workspace`.
  * images  [B,n,n] dtype;  sky, sky_err [B] float64;  filter_size odd in 1..15;
  * ov / out may be NULL;  rows [B];  workspace >= pm_workspace_bytes(B,n,dtype). */
 int pm_analyse_batch(const void *images, int dtype, int64_t B, int n, const double *sky,

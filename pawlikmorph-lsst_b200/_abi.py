@@ -18,8 +18,9 @@ PM_A_ANGLE90 = 0x800
 PM_NO_NOISECORRECT = 0x1000
 PM_L2_PREFETCH = 0x2000
 PM_NO_PRUNE = 0x4000
-PM_PATH_MONOLITH = 0x8000
-PM_TAIL_CTA = 0x10000
+PM_PATH_SPLIT = 0x8000
+PM_TAIL_WARP = 0x10000
+PM_RADIX_SORT = 0x20000
 PM_PHASE_ROWS = 8192
 PM_ST_OK, PM_ST_FAINT_CENTRE, PM_ST_NO_CANDIDATE, PM_ST_BAD_BRACKET, PM_ST_EMPTY_SEGMAP, PM_ST_WORKSPACE = range(6)
 

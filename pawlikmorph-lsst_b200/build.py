@@ -5,7 +5,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-# PM_LIB_VARIANT=<threads>x<ctas> selects an experimental build (tuning runs only), e.g. 256x2
+# PM_LIB_VARIANT=<name> selects an experimental build (tuning runs only) compiled with the extra defines of
+# PM_NVCC_DEFINES (e.g. "PM_FRONT_MIN_CTAS=3 PM_TAILCTA_MIN_CTAS=3"); the library is then libpawlik_b200_<name>.so
 VARIANT = os.environ.get("PM_LIB_VARIANT", "")
 SO = os.path.join(HERE, "libpawlik_b200.so" if not VARIANT else f"libpawlik_b200_{VARIANT}.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_tail.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_launch.cuh", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh", "pm_sky.cuh")] + \
@@ -33,9 +34,6 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(REPO, "include")]
-    if VARIANT:
-        t, k = VARIANT.split("x")
-        common[1:1] = [f"-DPM_THREADS={int(t)}", f"-DPM_MIN_CTAS={int(k)}"]
     for d in os.environ.get("PM_NVCC_DEFINES", "").split():
         common.insert(1, "-D" + d)
     if verbose:

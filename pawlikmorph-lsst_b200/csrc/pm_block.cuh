@@ -185,9 +185,23 @@ struct Arena {
     size_t g_floor;
     PM_DEV void init(unsigned char* sb, unsigned sc, unsigned char* gb, size_t gc) {
         s_base = sb; s_cap = sc; s_top = 0; g_base = gb; g_cap = gc; g_top = 0; overflow = 0; s_floor = 0; g_floor = 0;
+#if defined(PM_EMULATE)
+        if (((uintptr_t)sb & 15) || ((uintptr_t)gb & 15)) { fprintf(stderr, "pm_emul: misaligned arena base\n"); abort(); }   // x86 would not notice
+#endif
     }
     PM_DEV void set_floor() { s_floor = s_top; g_floor = g_top; }
     PM_DEV void reset() { s_top = s_floor; g_top = g_floor; overflow = 0; }
+    // global scratch even when shared memory has room (streamed data that should not crowd out random-access data)
+    PM_DEV void* alloc_global(size_t bytes) {
+        bytes = (bytes + 15) & ~(size_t)15;
+        if (bytes <= g_cap - g_top) {
+            void* p = g_base + g_top;
+            g_top += bytes;
+            return p;
+        }
+        overflow = 1;
+        return g_base;
+    }
     // shared memory or nothing
     PM_DEV void* alloc_smem(size_t bytes) {
         bytes = (bytes + 15) & ~(size_t)15;
@@ -365,6 +379,111 @@ PM_DEV int radix_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* 
         where ^= 1;
     }
     return where;
+}
+
+// ---- bucket sort of (key, value) pairs, ascending by (key, value) ---------------------------------------------
+// The values are unique and ascending in the input (raster positions), so ordering by (key, value) IS the stable
+// ascending order of np.argsort(kind="stable") that the canonical tie rule needs.  One counting pass
+// over up to 4096 buckets that are linear in the key bits (order-preserving float bits: logarithmic in the pixel
+// value, which matches the skewed brightness distribution of a galaxy), one scatter in arbitrary order inside a
+// bucket (shared-memory atomics only: no warp votes, no MATCH), then every element finds its rank inside its
+// bucket by comparing itself with the bucket's other elements and moves to its final place.  Two data movements
+// instead of the 2 x 3 of the LSD radix sort; the compare step costs sum(bucket size^2) — typically < 20 per
+// element.  Returns 0 (sorted data in keyA / valA) or -1 when a bucket holds more than kMaxBucket elements (many
+// equal keys: integer-valued frames, flat maps): the caller then falls back to radix_sort_pairs.
+constexpr int kBucketBits = 12;
+constexpr int kBuckets = 1 << kBucketBits;
+constexpr int kMaxBucket = 192;
+template <typename K> PM_DEV K block_min_max_key(Sh& sh, K kmin, K kmax, K* out_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = pm::shfl_xor((unsigned long long)kmin, o), b = pm::shfl_xor((unsigned long long)kmax, o);
+        kmin = (K)a < kmin ? (K)a : kmin;
+        kmax = (K)b > kmax ? (K)b : kmax;
+    }
+    unsigned long long* red = (unsigned long long*)sh.red[red_half(sh)];
+    if (pm::lane() == 0) { red[2 * pm::warp()] = (unsigned long long)kmin; red[2 * pm::warp() + 1] = (unsigned long long)kmax; }
+    pm::sync();
+    K lo = (K)red[0], hi = (K)red[1];
+    for (int w = 1; w < kWarps; w++) {
+        const K a = (K)red[2 * w], b = (K)red[2 * w + 1];
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    *out_max = hi;
+    return lo;
+}
+template <typename K, typename Lap = NoLap>
+PM_DEV int bucket_sort_pairs(Sh& sh, K* keyA, unsigned* valA, K* keyB, unsigned* valB, unsigned* hist /* kBuckets + 2 */, int n,
+                             Lap lap = Lap()) {
+    const int t = pm::tid();
+    if (n <= 1) return 0;
+    K kmin = ~(K)0, kmax = 0;
+    for (int i = t; i < n; i += kThreads) {
+        const K k = keyA[i];
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+    }
+    kmin = block_min_max_key<K>(sh, kmin, kmax, &kmax);
+    lap(16);
+    if (kmax == kmin) return 0;                          // all keys equal: the input order is the answer
+    const unsigned long long range = (unsigned long long)(kmax - kmin);
+    const int hb = high_bit(range) + 1;                   // range < 2^hb
+    const int shift = hb > kBucketBits ? hb - kBucketBits : 0;
+    const int nb = (int)(range >> shift) + 1;             // <= kBuckets
+    for (int i = t; i <= nb; i += kThreads) hist[i] = 0;
+    pm::sync();
+    for (int i = t; i < n; i += kThreads) pm::atomic_add(&hist[(unsigned)((keyA[i] - kmin) >> shift)], 1u);
+    pm::sync();
+    lap(17);
+    int cmax = 0;
+    for (int i = t; i < nb; i += kThreads) cmax = max(cmax, (int)hist[i]);
+    cmax = block_max_i(sh, cmax);
+    if (cmax > kMaxBucket) return -1;
+    block_scan_excl_array(sh, hist, nb);                  // hist[b] = first slot of bucket b
+    lap(18);
+    // scatter (arbitrary order inside a bucket); afterwards hist[b] = END of bucket b
+    for (int i0 = t; i0 < n; i0 += 4 * kThreads) {
+        K k[4];
+        unsigned v[4], slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * kThreads;
+            k[u] = keyA[i < n ? i : 0];
+            v[u] = valA[i < n ? i : 0];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            slot[u] = (i0 + u * kThreads < n) ? pm::atomic_add(&hist[(unsigned)((k[u] - kmin) >> shift)], 1u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * kThreads < n) { keyB[slot[u]] = k[u]; valB[slot[u]] = v[u]; }
+    }
+    pm::sync();
+    // rank inside the bucket, final placement
+    for (int i = t; i < n; i += kThreads) {
+        const K k = keyB[i];
+        const unsigned v = valB[i];
+        const unsigned b = (unsigned)((k - kmin) >> shift);
+        const int lo = b ? (int)hist[b - 1] : 0, hi = (int)hist[b];
+        int r = 0, j = lo;
+        for (; j + 3 < hi; j += 4) {                          // four independent compares in flight
+            const K k0 = keyB[j], k1 = keyB[j + 1], k2 = keyB[j + 2], k3 = keyB[j + 3];
+            const unsigned v0 = valB[j], v1 = valB[j + 1], v2 = valB[j + 2], v3 = valB[j + 3];
+            r += ((k0 < k || (k0 == k && v0 < v)) ? 1 : 0) + ((k1 < k || (k1 == k && v1 < v)) ? 1 : 0) +
+                 ((k2 < k || (k2 == k && v2 < v)) ? 1 : 0) + ((k3 < k || (k3 == k && v3 < v)) ? 1 : 0);
+        }
+        for (; j < hi; j++) {
+            const K kj = keyB[j];
+            const unsigned vj = valB[j];
+            r += (kj < k || (kj == k && vj < v)) ? 1 : 0;
+        }
+        keyA[lo + r] = k;
+        valA[lo + r] = v;
+    }
+    pm::sync();
+    lap(19);
+    return 0;
 }
 
 // ---- exact area of circle(0, r) ∩ rectangle — photutils geometry -------------------

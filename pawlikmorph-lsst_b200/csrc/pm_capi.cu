@@ -32,6 +32,11 @@ extern "C" unsigned pm_tail_warp_fixed_smem(int n);
 extern "C" int pm_tail_warp_groups_per_cta(void);
 extern "C" int pm_tail_warp_ctas_per_sm(void);
 extern "C" int pm_minapix_min_ctas(void);
+extern "C" int pm_front_min_ctas(void);
+extern "C" int pm_tail_cta_min_ctas(void);
+extern "C" int pm_tail_cta_threads(void);
+extern "C" int pm_front_threads(void);
+extern "C" int pm_minapix_threads(void);
 
 #ifndef PM_EMULATE
 __global__ void __launch_bounds__(kThreads, 1)
@@ -70,14 +75,16 @@ static int env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// shared-memory size and CTAs per SM of the front / monolith / CTA-tail kernels for (n, fs)
-static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm) {
+// shared-memory size and CTAs per SM of a kernel that keeps every fixed piece in shared memory (monolith, front, CTA
+// tail) for (n, fs); `built`: the CTAs per SM its launch bounds were compiled for
+static void launch_shape(int n, int fs, unsigned* smem, int* ctas_per_sm, int built = PM_MIN_CTAS, const char* env = "PM_CTAS_PER_SM") {
     const unsigned fixed = smem_fixed_bytes(n, fs);
     const unsigned cap1 = (unsigned)(g_smem_optin ? g_smem_optin : 232448);   // 227 KB
-    int ctas = PM_MIN_CTAS;                                                    // what the launch bounds were compiled for
+    int ctas = built;
     while (ctas > 1 && fixed + 24 * 1024 > (cap1 + 1024) / (unsigned)ctas - 1024) ctas--;   // large n: fewer, fatter CTAs
-    ctas = env_int("PM_CTAS_PER_SM", ctas);
+    ctas = env_int(env, ctas);
     if (ctas < 1) ctas = 1;
+    if (ctas > built) ctas = built;
     unsigned per = (cap1 + 1024) / (unsigned)ctas - 1024;
     per &= ~15u;
     const int forced = env_int("PM_SMEM_BYTES", 0);
@@ -216,8 +223,8 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
     if (grid_cap > PM_MAX_GRID) grid_cap = PM_MAX_GRID;
     const int g_env = env_int("PM_GRID", 0);
     if (g_env > 0 && g_env < grid_cap) grid_cap = g_env;
-    const bool mono = (flags & PM_PATH_MONOLITH) != 0 || env_int("PM_PATH_MONOLITH", 0) != 0;
-    const bool tail_cta = (flags & PM_TAIL_CTA) != 0 || env_int("PM_TAIL_CTA", 0) != 0;
+    const bool mono = (flags & PM_PATH_SPLIT) == 0 && env_int("PM_PATH_SPLIT", 0) == 0;
+    const bool tail_cta = (flags & PM_TAIL_WARP) == 0;
 
     int lrc = PM_OK;
     auto zero_counters = [&]() -> int {
@@ -238,6 +245,13 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
         return lrc;
     }
     // ---- the split path, chunk by chunk
+    unsigned smem_f = 0, smem_t = 0;
+    int ctas_f = 1, ctas_t = 1;
+    launch_shape(n, filter_size, &smem_f, &ctas_f, pm_front_min_ctas(), "PM_FRONT_CTAS");
+    launch_shape(n, filter_size, &smem_t, &ctas_t, pm_tail_cta_min_ctas(), "PM_TAILCTA_CTAS");
+    long long grid_f_cap = (long long)g_sm_count * ctas_f, grid_t_cap = (long long)g_sm_count * ctas_t;
+    if (grid_f_cap > PM_MAX_GRID) grid_f_cap = PM_MAX_GRID;
+    if (grid_t_cap > PM_MAX_GRID) grid_t_cap = PM_MAX_GRID;
     unsigned smem_m = 0;
     int ctas_m = 1;
     minapix_shape(n, &smem_m, &ctas_m);
@@ -260,18 +274,18 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
         const long long grid = grid_cap < nb ? grid_cap : nb;
         lrc = zero_counters();
         // front
-        p.smem_bytes = smem; p.scratch_per_cta = scratch_bytes_per_cta(n);
-        PM_LAUNCH(pm_front, grid, kThreads, smem);
+        p.smem_bytes = smem_f; p.scratch_per_cta = scratch_bytes_per_cta(n);
+        PM_LAUNCH(pm_front, grid_f_cap < nb ? grid_f_cap : nb, pm_front_threads(), smem_f);
         // minapix (skipped when the centre is supplied or the path stops before it)
         if (!p.ov.centroid_in && !(flags & (PM_STOP_AFTER_PIXELMAP | PM_STOP_AFTER_RMAX))) {
             const long long grid_m = grid_m_cap < nb ? grid_m_cap : nb;
             p.smem_bytes = smem_m; p.scratch_per_cta = scratch_bytes_minapix(n);
-            PM_LAUNCH(pm_minapix, grid_m, kThreads, smem_m);
+            PM_LAUNCH(pm_minapix, grid_m, pm_minapix_threads(), smem_m);
         }
         // tail (also writes the rows of the cutouts that ended early)
         if (tail_cta) {
-            p.smem_bytes = smem; p.scratch_per_cta = scratch_bytes_per_cta(n);
-            PM_LAUNCH(pm_tail_cta, grid, kThreads, smem);
+            p.smem_bytes = smem_t; p.scratch_per_cta = scratch_bytes_per_cta(n);
+            PM_LAUNCH(pm_tail_cta, grid_t_cap < nb ? grid_t_cap : nb, pm_tail_cta_threads(), smem_t);
         } else {
             p.smem_bytes = smem_g; p.scratch_per_cta = scratch_bytes_tail(n);
             const long long groups = groups_cap < nb ? groups_cap : nb;

@@ -67,6 +67,7 @@ PM_HOSTDEV SmemMap make_smem_map(const Geo& g, unsigned total, unsigned mask = S
     unsigned plane = (unsigned)(g.n * g.nw * 4);
     unsigned zplane = (unsigned)(g.m * g.mw * 4);
     if (zplane > plane) plane = zplane;   // cannot happen (m <= n) but keep the aliasing safe
+    plane = align16(plane);               // every piece (and the arena behind them) starts 16-byte aligned
     auto fits = [&](unsigned bytes) { return !optional || o + bytes + 1024u <= total; };
     s.seg = s.dil = s.aper = s.rowoff = s.tw = s.i0 = s.ri = s.rstart = kNoSmem;
     const unsigned rowoff_bytes = align16((unsigned)(g.n + 1) * 4);
@@ -104,7 +105,7 @@ struct GalState {
     int n_cand, cx, cy;
 };
 static_assert(sizeof(GalState) <= 256, "hand-over header");
-PM_HOSTDEV int state_list_cap(int n) { return n * n / 4 + 2048; }
+PM_HOSTDEV int state_list_cap(int n) { return n * n / 2 + 2048; }
 PM_HOSTDEV int state_cand_cap() { return 1024; }
 PM_HOSTDEV unsigned long long state_stride(int n) {
     const unsigned long long plane = (unsigned long long)n * ((n + 31) / 32) * 4;
@@ -115,10 +116,10 @@ PM_HOSTDEV unsigned long long state_stride(int n) {
 // shared memory + the candidate bookkeeping) and of the tail kernel (folded radial table <= 8 (n/2 + 4)^2 bytes x 2,
 // bit planes, band buffers)
 PM_HOSTDEV unsigned long long scratch_bytes_minapix(int n) {
-    return 8ull * (unsigned long long)n * (unsigned long long)n + 131072ull;
+    return ((8ull * (unsigned long long)n * (unsigned long long)n + 255ull) & ~255ull) + 131072ull;
 }
 PM_HOSTDEV unsigned long long scratch_bytes_tail(int n) {
-    return 6ull * (unsigned long long)n * (unsigned long long)n + 131072ull;
+    return ((6ull * (unsigned long long)n * (unsigned long long)n + 255ull) & ~255ull) + 131072ull;
 }
 
 PM_DEV int refl(int i, int L) {  // scipy "reflect" (d c b a | a b c d | d c b a), any distance
@@ -2169,11 +2170,11 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
         // 9-bit digits (3 passes for typical float keys) when their histogram fits shared memory, else 8-bit digits
         int sort_db = kMaxDigitBits;
         Arena::Mark mk_hist = c.ar.mark();
-        unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * kMaxDigits * 4);
+        unsigned* hist = (unsigned*)c.ar.alloc((size_t)max(kWarps * kMaxDigits, kBuckets + 2) * 4);
         if (!c.ar.in_smem(hist)) {
             c.ar.release(mk_hist);
             sort_db = 8;
-            hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+            hist = (unsigned*)c.ar.alloc((size_t)max(kWarps * 256, kBuckets + 2) * 4);
         }
         const unsigned* cand = spA;
         if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }   // workspace contract violated
@@ -2208,7 +2209,8 @@ template <typename T> PM_DEV void analyse_one(Ctx<T>& c, const Params& p, long l
             // ---- sort ascending by (value, flat index); the reverse is the canonical descending order
             for (int i = pm::tid(); i < n_g; i += kThreads) spA[i] = c.posR[i];
             pm::sync();
-            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db, [&](int ph) { pc.lap(ph); });
+            int where = (p.flags & PM_RADIX_SORT) ? -1 : bucket_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, [&](int ph) { pc.lap(ph); });
+            if (where < 0) where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db, [&](int ph) { pc.lap(ph); });
             if (where) {
                 for (int i = pm::tid(); i < n_g; i += kThreads) { spA[i] = spB[i]; skA[i] = skB[i]; }
                 pm::sync();
@@ -2508,11 +2510,11 @@ template <typename T> PM_DEV void front_one(Ctx<T>& c, const Params& p, long lon
         unsigned* spB = (unsigned*)c.ar.alloc((size_t)n_g * 4);
         int sort_db = kMaxDigitBits;
         Arena::Mark mk_hist = c.ar.mark();
-        unsigned* hist = (unsigned*)c.ar.alloc((size_t)kWarps * kMaxDigits * 4);
+        unsigned* hist = (unsigned*)c.ar.alloc((size_t)max(kWarps * kMaxDigits, kBuckets + 2) * 4);
         if (!c.ar.in_smem(hist)) {
             c.ar.release(mk_hist);
             sort_db = 8;
-            hist = (unsigned*)c.ar.alloc((size_t)kWarps * 256 * 4);
+            hist = (unsigned*)c.ar.alloc((size_t)max(kWarps * 256, kBuckets + 2) * 4);
         }
         if (c.ar.overflow) { status = PM_ST_WORKSPACE; done = true; }
         SegStats st;
@@ -2526,8 +2528,8 @@ template <typename T> PM_DEV void front_one(Ctx<T>& c, const Params& p, long lon
             const int rmax2 = phase_rmax2(c, st, &cen_flat);
             pc.lap(40);
             rmax = p.ov.radius_in ? p.ov.radius_in[b] : pm::dsqrt((double)rmax2);
-            // the later kernels size their folded radial table by the radius: very large ones take the monolith pass
-            if (!(rmax <= 0.5 * (double)g.n)) { push_big(p, i, gs); return; }
+            // the warp-group tail sizes its folded radial table by the radius: very large ones take the monolith pass
+            if ((p.flags & PM_TAIL_WARP) && !(rmax <= 0.5 * (double)g.n)) { push_big(p, i, gs); return; }
             row.rmax = rmax;
             abs_sum = st.abs_sum;
             if (p.ov.apermask_in) {
@@ -2547,7 +2549,8 @@ template <typename T> PM_DEV void front_one(Ctx<T>& c, const Params& p, long lon
             unsigned* st_list = state_list(gs, g);
             for (int k = pm::tid(); k < n_g; k += kThreads) { const unsigned q = c.posR[k]; spA[k] = q; st_list[k] = q; }
             pm::sync();
-            const int where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db, [&](int ph) { pc.lap(ph); });
+            int where = (p.flags & PM_RADIX_SORT) ? -1 : bucket_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, [&](int ph) { pc.lap(ph); });
+            if (where < 0) where = radix_sort_pairs<K>(sh, skA, spA, skB, spB, hist, n_g, sort_db, [&](int ph) { pc.lap(ph); });
             if (where) {
                 for (int k = pm::tid(); k < n_g; k += kThreads) { spA[k] = spB[k]; skA[k] = skB[k]; }
                 pm::sync();

@@ -54,3 +54,50 @@ def make_batch(B, n, seed, device="cpu", dtype=torch.float32, chunk=4096):
         noise = torch.randn((k, n, n), generator=g, device=device) * SKY_ERR
         out[s:s + k] = (img + comp + SKY + noise).to(dtype)
     return out
+
+
+def make_exact(B, n, seed):
+    """float32 [B, n, n] numpy cutouts that are BIT-IDENTICAL on every machine: integer random numbers (PCG64 raw
+    integers) and IEEE-exact operations only (+, -, *, /, sqrt; no exp / pow / sin whose last bit depends on the
+    maths library).  Used where oracle rows are committed and the images are re-made from the seed on the GPU box
+    (tests/golden/seeded_*.npz).  Per galaxy: a Moffat profile I0 / (1 + (r/a)^2)^beta, beta in {1, 1.5, 2, 2.5},
+    elliptical (axis ratio 0.4..1, rational rotation), centre (n/2, n/2) + U(-1, 1)^2, with p = 0.3 a round companion;
+    sky 100 + noise of sigma 5 (sum of four uniforms)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(int(seed)))
+
+    def U(k, lo, hi):               # exact: 24 random bits scaled
+        return lo + (hi - lo) * (rng.integers(0, 1 << 24, size=k).astype(np.float64) / float(1 << 24))
+
+    yy, xx = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
+    out = np.empty((B, n, n), dtype=np.float32)
+    for b in range(B):
+        beta2 = int(rng.integers(2, 6))                       # 2 beta
+        a = float(U(1, 0.02, 0.07)[0]) * n
+        q = float(U(1, 0.4, 1.0)[0])
+        t = float(U(1, -1.0, 1.0)[0])
+        c, s = (1.0 - t * t) / (1.0 + t * t), 2.0 * t / (1.0 + t * t)
+        i0 = float(U(1, 60.0, 1500.0)[0])
+        cx, cy = n / 2 + float(U(1, -1.0, 1.0)[0]), n / 2 + float(U(1, -1.0, 1.0)[0])
+        dx, dy = xx - cx, yy - cy
+        xr = dx * c + dy * s
+        yr = (dy * c - dx * s) / q
+        u = 1.0 + (xr * xr + yr * yr) / (a * a)
+
+        def powm(v, twice_beta):      # v ** (-twice_beta / 2) with exact operations
+            w = np.ones_like(v)
+            for _ in range(twice_beta // 2):
+                w = w * v
+            if twice_beta & 1:
+                w = w * np.sqrt(v)
+            return 1.0 / w
+
+        img = i0 * powm(u, beta2)
+        if int(rng.integers(0, 10)) < 3:
+            off, t2 = float(U(1, 0.05, 0.15)[0]) * n, float(U(1, -1.0, 1.0)[0])
+            ox, oy = off * (1.0 - t2 * t2) / (1.0 + t2 * t2), off * 2.0 * t2 / (1.0 + t2 * t2)
+            uc = 1.0 + ((dx - ox) ** 2 + (dy - oy) ** 2) / ((0.02 * n) ** 2)
+            img = img + float(U(1, 0.05, 0.5)[0]) * i0 * powm(uc, 4)
+        noise = rng.integers(0, 1 << 16, size=(4, n, n)).astype(np.float64).sum(axis=0) / float(1 << 16) - 2.0   # var 1/3
+        out[b] = (img + SKY + noise * (SKY_ERR * 1.7320508075688772)).astype(np.float32)
+    return out

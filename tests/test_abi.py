@@ -32,9 +32,9 @@ def test_library_builds_loads_and_exports_every_symbol():
 
     def want(B, n):          # pm_capi.cu make_plan(): counters | big list | per-group scratch | hand-over slots of a chunk
         up = lambda v: (v + 255) // 256 * 256
-        stride = up(256 + 2 * n * ((n + 31) // 32) * 4 + 4 * (n * n // 4 + 2048))
+        stride = up(256 + 2 * n * ((n + 31) // 32) * 4 + 4 * (n * n // 2 + 2048))
         chunk = min(B, 49152, max(1024, (4 << 30) // stride))
-        scratch = max(min(B, 592) * (64 * n * n + 65536), min(B, 640) * (8 * n * n + 131072), min(B, 5120) * (6 * n * n + 131072))
+        scratch = max(min(B, 592) * (64 * n * n + 65536), min(B, 640) * (up(8 * n * n) + 131072), min(B, 5120) * (up(6 * n * n) + 131072))
         return up(256 + 4 * chunk) + up(scratch) + chunk * stride
     for B, n in ((1, 256), (10 ** 6, 256), (5000, 140), (3, 512), (10 ** 5, 640)):
         assert L.pm_workspace_bytes(B, n, 0) == want(B, n), (B, n)
