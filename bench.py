@@ -48,34 +48,59 @@ def _cpu_init():
 
 
 def _cpu_one(img):
+    """One cutout through the oracle port: (row vector over ROW_FIELDS, packed pixelmap)."""
     import numpy as np
 
     import synth
     from oracle import pm_oracle as O
-    row, _, _ = O.analyse(img.astype(np.float64), synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL)
-    return row["status"]
+    row, seg, _ = O.analyse(img.astype(np.float64), synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL & 15)
+    return np.array([row[k] for k in ROW_FIELDS]), np.packbits(seg)
 
 
-def cpu_pool_rate(images, procs):
-    """galaxies/s of the oracle port over `images` with a pool of `procs` workers (warm)."""
+ROW_FIELDS = ("apix_col", "apix_row", "rmax", "r20", "r80", "C", "A", "Abgr", "S", "As", "As90", "gini", "m20", "object_edge",
+              "status", "n_candidates")
+
+
+def cpu_pool_run(images, procs):
+    """The oracle port over `images` with a pool of `procs` workers (warm): galaxies/s, seconds, rows, packed pixelmaps."""
     import multiprocessing as mp
+
+    import numpy as np
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs, initializer=_cpu_init) as pool:
         pool.map(_cpu_one, [images[0]] * procs)                           # every worker warm
         t0 = time.perf_counter()
-        pool.map(_cpu_one, list(images), chunksize=1)
+        res = pool.map(_cpu_one, list(images), chunksize=1)
         dt = time.perf_counter() - t0
-    return len(images) / dt, dt
+    return len(images) / dt, dt, np.stack([r for r, _ in res]), [s for _, s in res]
+
+
+def sample_size(procs, requested=0):
+    """Cutouts of the CPU sample: the first 512 of the resident batch when the box has the cores to do them in
+    ~20 s, fewer on small hosts."""
+    return requested or (512 if procs >= 12 else 32 * procs)
+
+
+def first_galaxies(S, n, device_index=0):
+    """The first S cutouts of rank 0's resident batch (same generator, seed and chunking as run_ours), on the host."""
+    import torch
+
+    import synth
+    seed = 20261019 + 1000 * 2 + 0
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", device_index)
+        x = synth.make_batch(max(S, 2048), n, seed, device=dev, chunk=2048)[:S].cpu().numpy()     # data generation only
+        return x, "first %d cutouts of the resident batch of the GPU arm (seed 20261019+2000, generated on the device)" % S, True
+    return synth.make_batch(S, n, seed).numpy(), "%d cutouts of the same generator on the host (no CUDA device: other random stream)" % S, False
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import synth
     procs = os.cpu_count() or 1
-    S = args.cpu_sample or 8 * procs
-    images = synth.make_batch(S, args.n, 20261019 + 3000).numpy()
+    S = sample_size(procs, args.cpu_sample)
+    images, sample_desc, same = first_galaxies(S, args.n)
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     times = []
@@ -89,16 +114,26 @@ def run_reference(args):
                 times.append(dt)
     total = sum(times)
     value = S * len(times) / total
-    sample = f"{S} synthetic {args.n}x{args.n} cutouts per step (seed 20261019+3000), multiprocessing.Pool({procs})"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    sample = f"{sample_desc}, every step, multiprocessing.Pool({procs})"
+    line = {"impl": "reference", "metric": metric_name(args.n), "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic Sersic+noise {args.n}x{args.n} float32 cutouts, -Aall -cas +S +Gini/M20 "
-                                   f"(BASELINE.json configs[2]), bounded sample", "filter_size": 3, "flags": FLAGS_ALL},
+            "config": {"workload": workload_name(args.n) + "; bounded sample per step", "n": args.n, "filter_size": 3, "flags": FLAGS_ALL & 15,
+                       "same_galaxies_as_gpu_arm": same},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def metric_name(n):
+    return METRIC if n == 256 else METRIC.replace("256^2", f"{n}^2")
+
+
+def workload_name(n):
+    cfg = {256: "BASELINE.json configs[2]", 140: "the 140^2 size of BASELINE.json configs[1] with every statistic", 512: "the 512^2 size of BASELINE.json configs[4]"}
+    return (f"synthetic Sersic+noise {n}x{n} float32 cutouts, -Aall -cas +S +Gini/M20 (flags 15)"
+            + (f" = {cfg[n]}" if n in cfg else ""))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -190,15 +225,16 @@ def run_ours(args):
     gen_s = time.perf_counter() - t0
     sky = torch.full((B,), synth.SKY, dtype=torch.float64, device=dev)
     err = torch.full((B,), synth.SKY_ERR, dtype=torch.float64, device=dev)
-    rows = torch.empty((B, 16), dtype=torch.float64, device=dev)
+    # the kernel writes its rows straight into this rank's slot of the gather buffer: in-place all-gather
+    table = torch.empty((B * world, 16), dtype=torch.float64, device=dev)
+    rows = table[rank * B:(rank + 1) * B]
     segmap = torch.empty((B, n, n), dtype=torch.uint8, device=dev)      # the pixelmap is an output of the path
-    table = torch.empty((B * world, 16), dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream(dev)
 
     def step():
         pm.batch.analyse_batch(x, sky, err, 3, FLAGS_ALL, rows_out=rows, segmap_out=segmap, stream=stream)
         if world > 1:
-            dist.all_gather_into_tensor(table, rows)
+            dist.all_gather_into_tensor(table, rows)           # in place: `rows` is this rank's slot of `table`
 
     def fence():
         if world > 1:
@@ -254,6 +290,84 @@ def run_ours(args):
             dist.barrier()
             dist.destroy_process_group()
         return
+
+    # ---- multi-GPU: the gathered table holds every rank's rows in rank order, bit for bit, and a fixed global batch
+    # sharded over the ranks gives the same table whatever the world size (no cross-galaxy term: main.py:161-174)
+    dist_info = None
+    if world > 1:
+        mine = rows.clone()
+        table.zero_()
+        rows.copy_(mine)
+        dist.all_gather_into_tensor(table, rows)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(table[rank * B:(rank + 1) * B], mine), "gathered table: own slot differs"
+        chk = torch.stack([table[r * B:(r + 1) * B].nan_to_num(nan=-7.0).sum(dim=0) for r in range(world)])   # [W, 16] per-slot checksums
+        ref = chk.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(chk, ref), "gathered table differs between ranks"
+    G = 8192                                             # fixed global batch: identical table for N = 1, 2, 4, 8
+    if G % world == 0:
+        import hashlib
+        xg = synth.make_batch(G, n, 20261019 + 7777, device=dev, chunk=2048)
+        lo, hi = pm.batch.shard_bounds(G, world, rank)
+        tg = torch.empty((G, 16), dtype=torch.float64, device=dev)
+        pm.batch.analyse_batch(xg[lo:hi].contiguous(), synth.SKY, synth.SKY_ERR, 3, FLAGS_ALL, rows_out=tg[lo:hi], stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(tg, tg[lo:hi])
+        torch.cuda.synchronize(dev)
+        dist_info = {"fixed_batch": G, "seed": "20261019+7777", "table_sha256": hashlib.sha256(tg.cpu().numpy().tobytes()).hexdigest(),
+                     "note": "rows of the same 8192 cutouts sharded over the ranks and all-gathered: the hash must not depend on --gpus"}
+        del xg, tg
+    # ---- BASELINE.json configs[3]: 4 194 304 cutouts of 256^2 strong-scaled over the ranks, generated on the device in
+    # chunks (never materialised: SURVEY 8d); only the analysis of each chunk is timed (CUDA events), generation is not
+    strong = None
+    if world > 1 and n == 256 and not args.no_strong:
+        total_g = 4194304
+        per_rank = total_g // world
+        done_g, ms = 0, 0.0
+        k = 0
+        while done_g < per_rank:
+            nb = min(B, per_rank - done_g)
+            if k > 0:
+                x[:nb] = synth.make_batch(nb, n, 20261019 + 4000 + 64 * rank + k, device=dev, chunk=2048)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            pm.batch.analyse_batch(x[:nb], sky[:nb], err[:nb], 3, FLAGS_ALL, rows_out=rows[:nb], segmap_out=segmap[:nb], stream=stream)
+            b_.record(stream)
+            torch.cuda.synchronize(dev)
+            ms += a.elapsed_time(b_)
+            done_g += nb
+            k += 1
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"galaxies_total": per_rank * world, "galaxies_per_gpu": per_rank, "chunks_per_gpu": k, "value": per_rank * world / (float(t.item()) * 1e-3),
+                  "unit": UNIT, "seconds": float(t.item()) * 1e-3, "scaling": "strong",
+                  "note": "BASELINE.json configs[3]; chunks regenerated on the device between timed launches, rows stay on the device"}
+        x = synth.make_batch(B, n, 20261019 + 1000 * 2 + rank, device=dev, chunk=2048)      # the resident batch again
+        pm.batch.analyse_batch(x, sky, err, 3, FLAGS_ALL, rows_out=rows, segmap_out=segmap, stream=stream)
+        torch.cuda.synchronize(dev)
+
+    # ---- pinned host -> device bandwidth of this rank (what bounds the end-to-end numbers below)
+    probe_h = [torch.empty(512 * 2 ** 20, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    probe_d = [torch.empty_like(t, device=dev) for t in probe_h]
+    pstreams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]          # two copy streams, like analyse_host
+    for k in range(2):
+        with torch.cuda.stream(pstreams[k]):
+            probe_d[k].copy_(probe_h[k], non_blocking=True)
+    fence()
+    t0p = time.perf_counter()
+    for it in range(4):
+        for k in range(2):
+            with torch.cuda.stream(pstreams[k]):
+                probe_d[k].copy_(probe_h[k], non_blocking=True)
+    for st_ in pstreams:
+        st_.synchronize()
+    h2d_gbs = 8 * probe_h[0].numel() / (time.perf_counter() - t0p) / 1e9
+    h2d_all = torch.tensor([h2d_gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_all, op=dist.ReduceOp.SUM)      # all ranks copy at the same time: the aggregate the host sustains
+    h2d_sum = float(h2d_all.item())
+    del probe_h, probe_d
 
     # ---- end to end through the public host API: pinned host images -> rows on the host
     E = min(args.e2e_batch, B)
@@ -351,25 +465,83 @@ def run_ours(args):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_galaxy") and tj["dram_bytes_per_galaxy"] * B
+            per_n = tj.get("dram_bytes_per_galaxy_by_n", {}).get(str(n))          # ncu --set full captures, per cutout size
+            traffic = per_n * B if per_n else None
             dec_traffic = tj.get("decode16_f32_dram_bytes_per_pixel") and tj["decode16_f32_dram_bytes_per_pixel"] * D * n * n
         except Exception:
             traffic = None
-    # ---- CPU baseline (bounded sample, N = 1 only)
-    cpu = None
+    # ---- CPU baseline + parity sample (N = 1 only): the oracle port over the FIRST S cutouts of the resident batch, timed
+    # on the host cores, and its rows / pixelmaps compared with what the kernel wrote for the same cutouts
+    cpu = parity = None
     if world == 1 and not args.no_cpu:
+        from tests.golden_util import FLOATS, compare_row
         procs = os.cpu_count() or 1
-        S = args.cpu_sample or 8 * procs
+        S = min(B, sample_size(procs, args.cpu_sample))
         sample_imgs = x[:S].cpu().numpy()
-        rate, dt = cpu_pool_rate(sample_imgs, procs)
+        rate, dt, want_rows, want_segs = cpu_pool_run(sample_imgs, procs)
         cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": f"first {S} cutouts of the same synthetic batch, oracle port, multiprocessing.Pool({procs}), {dt:.1f} s"}
-    line = {"metric": METRIC if args.n == 256 else METRIC.replace("256^2", f"{args.n}^2"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "sample": f"first {S} cutouts of the resident batch, oracle port, multiprocessing.Pool({procs}), {dt:.1f} s"}
+        got_rows, got_segs = rows[:S].cpu().numpy(), segmap[:S].cpu().numpy()
+        seg_equal = all(np.array_equal(np.packbits(got_segs[i]), want_segs[i]) for i in range(S))
+        errs, max_rel = [], 0.0
+        for i in range(S):
+            g_, w_ = dict(zip(ROW_FIELDS, got_rows[i])), dict(zip(ROW_FIELDS, want_rows[i]))
+            errs += compare_row(g_, w_, 1e-9, f"[{i}] ")
+            if g_["n_candidates"] != w_["n_candidates"]:
+                errs.append(f"[{i}] n_candidates")
+            for k_ in FLOATS:
+                if w_[k_] != -99.0 and np.isfinite(w_[k_]) and np.isfinite(g_[k_]) and w_[k_] != 0.0:
+                    max_rel = max(max_rel, abs(g_[k_] - w_[k_]) / abs(w_[k_]))
+        parity = {"n": S, "segmap_equal": bool(seg_equal), "rows_within_1e-9": not errs, "max_rel": max_rel,
+                  "mismatches": errs[:5], "checker": "oracle/pm_oracle.py (pinned by the goldens of the unmodified reference)"}
+    # ---- the other BASELINE.json configurations that fit one GPU (info keys; N = 1 only, after the headline run)
+    other = {}
+    if world == 1 and not args.no_configs and n == 256:
+        del x, segmap, table, rows
+        torch.cuda.empty_cache()
+
+        def run_cfg(nn, Bc, flags, seed, with_segmaps):
+            xc = synth.make_batch(Bc, nn, seed, device=dev, chunk=1024)
+            rc_ = torch.empty((Bc, 16), dtype=torch.float64, device=dev)
+            sc_ = torch.empty((Bc, nn, nn), dtype=torch.uint8, device=dev)
+            kw = {}
+            if with_segmaps:        # configs[4]: precomputed segmaps are an INPUT (main.py:428-439); made here by the pixelmap pass
+                pm.batch.analyse_batch(xc, synth.SKY, synth.SKY_ERR, 3, flags | pm._abi.PM_STOP_AFTER_PIXELMAP, rows_out=rc_, segmap_out=sc_, stream=stream)
+                kw = dict(segmap_in=sc_)
+            else:
+                kw = dict(segmap_out=sc_)
+            for _ in range(3):
+                pm.batch.analyse_batch(xc, synth.SKY, synth.SKY_ERR, 3, flags, rows_out=rc_, stream=stream, **kw)
+            c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            c0_.record(stream)
+            for _ in range(3):
+                pm.batch.analyse_batch(xc, synth.SKY, synth.SKY_ERR, 3, flags, rows_out=rc_, stream=stream, **kw)
+            c1_.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = c0_.elapsed_time(c1_) / 3
+            ab = algorithmic_bytes(nn)
+            ach = Bc * ab / (ms * 1e-3) / 1e9
+            tn = None
+            try:
+                tn = json.load(open(tpath)).get("dram_bytes_per_galaxy_by_n", {}).get(str(nn))
+            except Exception:
+                pass
+            ok = float((rc_[:, 14] == 0).double().mean().item())
+            return {"value": Bc / (ms * 1e-3), "unit": UNIT, "galaxies": Bc, "n": nn, "flags": flags, "ms_per_step": ms, "status_ok_fraction": ok,
+                    "segmap": "supplied (u8 input)" if with_segmaps else "computed (u8 output)",
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "algorithmic_bytes_per_galaxy": ab, "traffic": tn * Bc if tn else None}}
+        other["config2_140"] = dict(run_cfg(140, 65536, 3, 20261019 + 1000 * 1, False),
+                                    workload="BASELINE.json configs[1]: 65536 cutouts of 140^2, -A -As (flags 3)")
+        other["config5_512"] = dict(run_cfg(512, 8192, 15, 20261019 + 1000 * 4, True),
+                                    workload="BASELINE.json configs[4]: 512^2 cutouts with precomputed segmaps, every statistic (flags 15), "
+                                             "8192 resident cutouts (8 GiB); one CTA per cutout, the same kernel (no tiled variant)")
+    line = {"metric": metric_name(n), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{B} synthetic Sersic+noise {n}x{n} float32 cutouts per GPU resident in HBM "
-                                   f"({B * per / 2 ** 30:.1f} GiB > L2, no flush needed), -Aall -cas +S +Gini/M20 "
-                                   f"(BASELINE.json configs[2]); one CTA per galaxy, one launch per step",
+            "config": {"workload": f"{B} per GPU resident in HBM ({B * per / 2 ** 30:.1f} GiB > L2, no flush needed): " + workload_name(n)
+                                   + "; one CTA per galaxy, one launch per step",
                        "galaxies_per_gpu": B, "n": n, "filter_size": 3, "flags": FLAGS_ALL,
                        "parallelism": f"galaxy-sharded x{world}" + (" + all-gather of rows" if world > 1 else ""),
                        "status_ok_fraction": n_ok / B, "mean_candidates": mean_cands, "gen_seconds": gen_s,
@@ -377,11 +549,16 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_galaxy": abytes,
                          "kernel": "pm_analyse_kernel<float>", "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity_sample": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * per + 16 * E, "d2h_bytes_per_step": E * 128,
-                    "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host"},
+                    "galaxies_per_step": E, "chunk": args.e2e_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host",
+                    "h2d_gbs_per_rank": h2d_gbs, "h2d_gbs_all_ranks": h2d_sum,
+                    "fraction_of_h2d_bound": e2e_value * (per + 16) / 1e9 / h2d_sum if h2d_sum > 0 else None,
+                    "note": "pinned host -> device copy bandwidth measured in this run with every rank copying at once; the float32 "
+                            "payload call is bound by it"},
             "e2e_fits16": {"value": f16_value, "unit": UNIT, "h2d_bytes_per_step": E * n * n * 2 + 16 * E, "d2h_bytes_per_step": E * 128,
                            "galaxies_per_step": E, "chunk": args.e2e_payload_chunk, "api": "pawlikmorph_lsst_b200.batch.analyse_host_payload",
+                           "fraction_of_h2d_bound": f16_value * (n * n * 2 + 16) / 1e9 / h2d_sum if h2d_sum > 0 else None,
                            "note": "same cutouts as integer counts in the FITS BITPIX 16 / BZERO 32768 wire format, decoded on the device"},
             "roofline_decode": {"bound": "hbm", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / peak, "kernel": "pm_fits_decode_kernel<16, float>",
@@ -390,6 +567,11 @@ def run_ours(args):
                           "cutouts": S_, "mean_clip_iterations": sky_iters, "per_gpu": True,
                           "note": "sky-region statistics of skyBackground._calcSkybgr with random fitted ellipses; L2/issue bound, see profiles/r1i_sky_ncu_summary.txt"},
             "gpu_launches": int(launches), "clocks": clocks}
+    if dist_info:
+        line["distributed_check"] = dist_info
+    if strong:
+        line["config4_strong_4M"] = strong
+    line.update(other)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -410,6 +592,8 @@ def main():
     ap.add_argument("--e2e-payload-chunk", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaled 4 M stream of --gpus N > 1")
+    ap.add_argument("--no-configs", action="store_true", help="skip the 140^2 / 512^2 configuration runs")
     ap.add_argument("--kernel-only", action="store_true", help="tuning: stop after the resident timed steps (short JSON line)")
     ap.add_argument("--phases", action="store_true", help="print per-phase cycle shares to stderr (tuning aid)")
     args = ap.parse_args()
