@@ -171,6 +171,41 @@ int pm_fits_decode_window_batch(const void *payload, int bitpix, double bzero, d
 #define PM_SKY_COLS 12
 int pm_sky_stats_batch(const void *images, int dtype, int64_t B, int n, const double *ellipse, double *out, void *cuda_stream);
 
+/* astropy.stats.sigma_clipped_stats(image, sigma=sigma, maxiters=maxiters, cenfunc=median, stdfunc=std) over every pixel of
+ * each cutout (imageutils.py:62; photutils.detect_threshold, skyBackground.py:109 / imageutils.py:67, is mean + nsigma * std
+ * of the call with maxiters = None, passed here as maxiters <= 0), plus the unclipped statistics and the maximum
+ * (gaussfitter.moments needs the median and the maximum, gaussfitter.py:71-72).
+ * out: DEVICE double [B, PM_CLIP_COLS] = count, mean, median, std, clip iterations, clipped count, mean, median, std, max. */
+#define PM_CLIP_COLS 10
+int pm_clipped_stats_batch(const void *images, int dtype, int64_t B, int n, double sigma, int maxiters, double *out, void *cuda_stream);
+
+/* skyBackground._gauss2dfit (skyBackground.py:306-331): the least-squares fit of gaussfitter.twodgaussian (gaussfitter.py:87-148)
+ * to each cutout that scipy.optimize.curve_fit performs from the start values of gaussfitter.moments (:40-84) — here a
+ * Levenberg-Marquardt iteration with the analytic Jacobian run to the optimum (curve_fit stops at ftol = xtol = 1.5e-8, so the
+ * two agree to that tolerance, not bit for bit).  median, vmax: DEVICE double [B] (columns 2 and 9 of pm_clipped_stats_batch),
+ * used for the start values unless p0 (DEVICE double [B, 7], nullable) supplies them.
+ * out: DEVICE double [B, PM_GAUSS_COLS] = height, amplitude, xo, yo, sigma_x, sigma_y, theta (raw optimum, before the np.abs of
+ * skyBackground.py:331), cost, iterations, status (0 converged; 1 iteration limit: curve_fit's RuntimeError, the caller falls
+ * back like skyBackground.py:117-118; 2 NaN start values: gaussfitter.py:76-77; 3 singular system). */
+#define PM_GAUSS_COLS 10
+int pm_gaussfit_batch(const void *images, int dtype, int64_t B, int n, const double *median, const double *vmax, const double *p0,
+                      double *out, void *cuda_stream);
+
+/* photutils.detect_sources(image, threshold, npixels, kernel = 3 x 3 Gaussian of FWHM 3) as skyBackground.py:104-110 and
+ * imageutils.py:66-71 call it — smooth, `> threshold[b]`, 8-connected labels, segments of fewer than npixels pixels dropped —
+ * and, when clean_out is given, the cleaning of imageutils.maskstarsSEG (imageutils.py:73-89): every kept segment whose bounding
+ * box does not contain (n/2 + 1, n/2 + 1) is a "star", and inside a star's bounding box the pixels of kept segments are
+ * replaced by mean[b] + std[b] * N(0, 1).  The reference draws from the unseeded np.random.normal; here the normal deviate of
+ * (seed, cutout index, pixel index) comes from Philox4x32-10 + Box-Muller, so that runs are reproducible and checkable.
+ * labels_out: DEVICE int32 [B, n, n] (nullable; 0 background, 1.. in raster order of the first pixel); clean_out: DEVICE
+ * [B, n, n] of dtype (nullable); out: DEVICE double [B, PM_STAR_COLS] = segments kept, segments cleaned, pixels replaced, status;
+ * workspace >= pm_maskstars_workspace_bytes(B, n), 16-byte aligned. */
+#define PM_STAR_COLS 4
+size_t pm_maskstars_workspace_bytes(int64_t B, int n);
+int pm_maskstars_batch(const void *images, int dtype, int64_t B, int n, const double *threshold, int npixels, const double *mean,
+                       const double *std_, uint64_t seed, int32_t *labels_out, void *clean_out, double *out, void *workspace,
+                       size_t workspace_bytes, void *cuda_stream);
+
 /* Library / device introspection (HOST). */
 int pm_abi_version(void);
 int pm_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);

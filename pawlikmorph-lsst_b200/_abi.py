@@ -43,7 +43,11 @@ class Outputs(C.Structure):
 
 EXPORTS = ("pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
            "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch",
-           "pm_fits_decode_window_batch", "pm_sky_stats_batch")
+           "pm_fits_decode_window_batch", "pm_sky_stats_batch", "pm_clipped_stats_batch", "pm_gaussfit_batch",
+           "pm_maskstars_workspace_bytes", "pm_maskstars_batch")
+PM_CLIP_COLS, PM_GAUSS_COLS, PM_STAR_COLS = 10, 10, 4
+CLIP_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_count", "clipped_mean", "clipped_median", "clipped_std", "max")
+GAUSS_FIELDS = ("height", "amplitude", "xo", "yo", "sigma_x", "sigma_y", "theta", "cost", "iterations", "status")
 PM_SKY_COLS = 12
 SKY_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_count", "clipped_mean", "clipped_median", "clipped_std",
               "sky", "sky_err", "status")
@@ -74,6 +78,15 @@ def declare(lib):
     lib.pm_fits_decode_window_batch.restype = C.c_int
     lib.pm_fits_decode_window_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.pm_clipped_stats_batch.restype = C.c_int
+    lib.pm_clipped_stats_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    lib.pm_gaussfit_batch.restype = C.c_int
+    lib.pm_gaussfit_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pm_maskstars_workspace_bytes.restype = C.c_size_t
+    lib.pm_maskstars_workspace_bytes.argtypes = [C.c_int64, C.c_int]
+    lib.pm_maskstars_batch.restype = C.c_int
+    lib.pm_maskstars_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     return lib
 
 

@@ -147,6 +147,8 @@ extern "C" {
 
 int pm_abi_version(void) { return PM_ABI_VERSION; }
 const char* pm_last_cuda_error(void) { return g_err; }
+void pm_set_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); }     // for the other translation units
+void pm_count_launch(void) { g_launches.fetch_add(1); }
 uint64_t pm_launch_count(void) { return g_launches.load(); }
 
 int pm_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {

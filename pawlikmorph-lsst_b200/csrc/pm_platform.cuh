@@ -84,6 +84,10 @@ template <typename T> PM_DEV T ldg(const T* p) { return __ldg(p); }
 PM_DEV unsigned atomic_add(unsigned* p, unsigned v) { return atomicAdd(p, v); }
 PM_DEV unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
 PM_DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+PM_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+PM_DEV int atomic_min(int* p, int v) { return atomicMin(p, v); }
+PM_DEV int atomic_max(int* p, int v) { return atomicMax(p, v); }
+PM_DEV int atomic_cas(int* p, int expected, int desired) { return atomicCAS(p, expected, desired); }
 // IEEE-exact, never contracted into FMA (bit-parity with numpy/scipy where it matters)
 PM_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
 PM_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }

@@ -1,0 +1,500 @@
+// pm_prep.cuh — the pre-processing around the morphology path, one CTA per cutout:
+//   * clipstats_body   astropy.stats.sigma_clipped_stats(image, sigma, maxiters) over a whole cutout, plus the plain
+//                      statistics and the maximum: imageutils.py:62, photutils.detect_threshold (skyBackground.py:109,
+//                      imageutils.py:67) and gaussfitter.moments' median / max (gaussfitter.py:71-72)
+//   * gaussfit_body    skyBackground._gauss2dfit (skyBackground.py:306-331): gaussfitter.moments start values and the
+//                      least-squares fit of gaussfitter.twodgaussian that scipy.optimize.curve_fit performs, as a
+//                      Levenberg-Marquardt iteration with the analytic Jacobian
+//   * maskstars_body   photutils.detect_sources as skyBackground.py:110 / imageutils.py:71 call it (3x3 Gaussian smooth,
+//                      strict threshold, 8-connected labels of >= npixels pixels) and the cleaning step of
+//                      imageutils.maskstarsSEG (:42-91) with a counter-based (Philox) normal generator in place of the
+//                      reference's unseeded np.random.normal
+#pragma once
+#include "pm_sky.cuh"
+
+namespace pmk {
+
+// ----------------------------------------------------------------------------------------------------
+// clipped statistics
+// ----------------------------------------------------------------------------------------------------
+constexpr int kClipCols = 10;   // count, mean, median, std (all pixels), iterations, clipped count, mean, median, std, max
+
+template <typename T>
+PM_DEV void clipstats_body(const T* images, long long B, int n, double sigma, int maxiters, double* out) {
+    unsigned char* smem = pm::dyn_smem(0);
+    Sh& sh = *(Sh*)smem;
+    SkyScratch& sc = *(SkyScratch*)(smem + align16((unsigned)sizeof(Sh)));
+    unsigned* mask = (unsigned*)(smem + align16((unsigned)sizeof(Sh)) + align16((unsigned)sizeof(SkyScratch)));
+    sh.par[pm::tid()] = 0;
+    const int nw = (n + 31) / 32;
+    for (int i = pm::tid(); i < n * nw; i += kThreads) {
+        const int w = i % nw;
+        mask[i] = (w == nw - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;     // every pixel belongs to the set
+    }
+    pm::sync();
+    const double inf = 1.7976931348623157e308 * 2.0;
+    for (long long b = pm::block(); b < B; b += pm::nblocks()) {
+        SkySet<T> s;
+        s.img = images + (size_t)b * n * n;
+        s.mask = mask;
+        s.n = n;
+        s.nw = nw;
+        s.set_bounds(-inf, inf);
+        SkyStats cur = sky_stats(sh, sc, s, (double)pm::ldg(s.img));
+        const SkyStats all = cur;
+        double vmax = -inf;
+        sky_for_each(s, [&](T x, decltype(sky_key(T()))) { vmax = fmax(vmax, (double)x); });
+        vmax = block_max(sh, vmax);
+        // astropy SigmaClip: bounds median -/+ sigma * std (inclusive) from the surviving values, until a round removes
+        // nothing or maxiters rounds are done (maxiters <= 0: until convergence)
+        double iters = 0.0, changed = 1.0;
+        while (changed != 0.0 && (maxiters <= 0 || iters < (double)maxiters) && cur.cnt > 0.0) {
+            iters += 1.0;
+            s.set_bounds(fmax(s.lo, cur.median - cur.std * sigma), fmin(s.hi, cur.median + cur.std * sigma));
+            const SkyStats nxt = sky_stats(sh, sc, s, cur.median);
+            changed = cur.cnt - nxt.cnt;
+            cur = nxt;
+        }
+        if (pm::tid() == 0) {
+            double* o = out + (size_t)b * kClipCols;
+            o[0] = all.cnt; o[1] = all.mean; o[2] = all.median; o[3] = all.std; o[4] = iters;
+            o[5] = cur.cnt; o[6] = cur.mean; o[7] = cur.median; o[8] = cur.std; o[9] = vmax;
+        }
+        pm::sync();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Gaussian fit
+// ----------------------------------------------------------------------------------------------------
+// out: height, amplitude, xo, yo, sigma_x, sigma_y, theta (the raw optimum, before the np.abs of skyBackground.py:331),
+//      final cost (sum of squared residuals), iterations, status (0 converged, 1 iteration limit — curve_fit's
+//      RuntimeError —, 2 NaN in the start values — gaussfitter.py:76-77 —, 3 singular normal equations)
+constexpr int kGaussCols = 10;
+constexpr int kGaussMaxIter = 200;
+
+// Cholesky solve of the 7x7 system (A + par * diag(dg)^2) d = g; returns false when it is not positive definite
+PM_DEV bool lm_solve7(const double* A /* packed lower triangle, 28 */, const double* g, double par, const double* dg, double* d) {
+    double L[28];
+    for (int i = 0; i < 7; i++) {
+        for (int j = 0; j <= i; j++) {
+            double sum = A[i * (i + 1) / 2 + j];
+            if (i == j) sum += par * dg[i] * dg[i];
+            for (int k = 0; k < j; k++) sum -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+            if (i == j) {
+                if (!(sum > 0.0) || !(sum < 1.7e308)) return false;
+                L[i * (i + 1) / 2 + i] = sqrt(sum);
+            } else {
+                L[i * (i + 1) / 2 + j] = sum / L[j * (j + 1) / 2 + j];
+            }
+        }
+    }
+    double y[7];
+    for (int i = 0; i < 7; i++) {
+        double sum = g[i];
+        for (int k = 0; k < i; k++) sum -= L[i * (i + 1) / 2 + k] * y[k];
+        y[i] = sum / L[i * (i + 1) / 2 + i];
+    }
+    for (int i = 6; i >= 0; i--) {
+        double sum = y[i];
+        for (int k = i + 1; k < 7; k++) sum -= L[k * (k + 1) / 2 + i] * d[k];
+        d[i] = sum / L[i * (i + 1) / 2 + i];
+    }
+    return true;
+}
+
+struct GaussShared {
+    double p[7], trial[7], jtj[28], jtr[7];
+    double cost;
+    int flag;
+};
+
+// one pass over the cutout at parameters q: cost = sum r^2, and (with_jac) J^T J, J^T r for r = model - data
+template <typename T>
+PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const double* q, bool with_jac, double* cost, double* jtj, double* jtr) {
+    const double h = q[0], A = q[1], xo = q[2], yo = q[3], sx = q[4], sy = q[5], th = q[6];
+    const double c = cos(th), s = sin(th);
+    const double isx = 1.0 / sx, isy = 1.0 / sy;
+    double acc[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] = 0.0;
+    for (int i = pm::tid(); i < n * n; i += kThreads) {
+        const int row = i / n, col = i - row * n;
+        // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
+        const double dx = yo - (double)col, dy = xo - (double)row;
+        const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
+        const double E = exp(-0.5 * (u * u + v * v));
+        const double r = h + A * E - (double)pm::ldg(img + i);
+        acc[35] += r * r;
+        if (with_jac) {
+            const double AE = A * E;
+            double J[7];
+            J[0] = 1.0;
+            J[1] = E;
+            J[2] = AE * (u * s * isx - v * c * isy);
+            J[3] = -AE * (u * c * isx + v * s * isy);
+            J[4] = AE * u * u * isx;
+            J[5] = AE * v * v * isy;
+            J[6] = AE * u * v * (sy * isx - sx * isy);
+#pragma unroll
+            for (int a = 0; a < 7; a++) {
+                acc[28 + a] += J[a] * r;
+#pragma unroll
+                for (int b2 = 0; b2 <= a; b2++) acc[a * (a + 1) / 2 + b2] += J[a] * J[b2];
+            }
+        }
+    }
+    // 36 block sums, eight per barrier
+    for (int base = 0; base < 36; base += 8) {
+        if (!with_jac && base < 32) continue;
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = base + k < 36 ? acc[base + k] : 0.0;
+        block_sum<8>(sh, t);
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (base + k < 36) acc[base + k] = t[k];
+    }
+    *cost = acc[35];
+    if (with_jac) {
+        for (int k = 0; k < 28; k++) jtj[k] = acc[k];
+        for (int k = 0; k < 7; k++) jtr[k] = acc[28 + k];
+    }
+}
+
+template <typename T>
+PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0_in, double* out) {
+    unsigned char* smem = pm::dyn_smem(0);
+    Sh& sh = *(Sh*)smem;
+    sh.par[pm::tid()] = 0;
+    pm::sync();
+    for (long long b = pm::block(); b < B; b += pm::nblocks()) {
+        const T* img = images + (size_t)b * n * n;
+        double p[7];
+        int status = 0;
+        if (p0_in) {
+            for (int k = 0; k < 7; k++) p[k] = p0_in[7 * b + k];
+        } else {
+            // gaussfitter.moments (gaussfitter.py:61-84): widths from the central row / column, height = median, amplitude = max - median
+            const int y0 = n / 2, x0 = n / 2;
+            double a4[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = pm::tid(); i < n; i += kThreads) {
+                const double cv = (double)pm::ldg(img + (size_t)y0 * n + i), rv = (double)pm::ldg(img + (size_t)i * n + x0);
+                const double dc = (double)(i - y0), dr = (double)(i - x0);
+                a4[0] += fabs(dc * dc * cv); a4[1] += fabs(cv); a4[2] += fabs(dr * dr * rv); a4[3] += fabs(rv);
+            }
+            block_sum<4>(sh, a4);
+            p[0] = median[b]; p[1] = vmax[b] - median[b]; p[2] = (double)x0; p[3] = (double)y0;
+            p[4] = sqrt(a4[0] / a4[1]); p[5] = sqrt(a4[2] / a4[3]); p[6] = 90.0 * 3.141592653589793 / 180.0;
+            if (p[4] != p[4] || p[5] != p[5] || p[0] != p[0] || p[1] != p[1]) status = 2;
+        }
+        double cost = 0.0, jtj[28], jtr[7];
+        int iter = 0;
+        if (status == 0) {
+            // Levenberg-Marquardt with MINPACK's trust-region logic (lmder: scaling by the running maximum of the column
+            // norms, step bound delta, ratio of actual to predicted reduction steering delta and the damping parameter) —
+            // curve_fit's algorithm with the analytic Jacobian, stopped at 1e-13 instead of 1.5e-8.  An undamped or merely
+            // Marquardt-damped iteration walks off to needle-shaped Gaussians from the start values of gaussfitter.moments.
+            gauss_pass(sh, img, n, p, true, &cost, jtj, jtr);
+            status = 1;
+            if (!(cost == cost) || !(cost < 1.7e308)) status = 2;
+            double dg[7], xnorm = 0.0, par = 0.0;
+            for (int k = 0; k < 7; k++) {
+                const double a = jtj[k * (k + 1) / 2 + k];
+                dg[k] = a > 0.0 ? sqrt(a) : 1.0;
+                xnorm += dg[k] * p[k] * dg[k] * p[k];
+            }
+            xnorm = sqrt(xnorm);
+            double delta = xnorm > 0.0 ? 100.0 * xnorm : 100.0;
+            const double tol = 1e-13;
+            if (status == 1 && cost == 0.0) status = 0;
+            for (; status == 1 && iter < kGaussMaxIter; iter++) {
+                double maxratio = 0.0;
+                for (int k = 0; k < 7; k++) {
+                    const double a = jtj[k * (k + 1) / 2 + k];
+                    if (a > 0.0) dg[k] = fmax(dg[k], sqrt(a));
+                    maxratio = fmax(maxratio, a / (dg[k] * dg[k]));
+                }
+                double d[7], g[7], pnorm = 0.0;
+                for (int k = 0; k < 7; k++) g[k] = -jtr[k];
+                bool solved = false;
+                for (int inner = 0; inner < 80; inner++) {
+                    if (!lm_solve7(jtj, g, par, dg, d)) { par = fmax(par * 4.0, 1e-12 * fmax(maxratio, 1e-300)); continue; }
+                    pnorm = 0.0;
+                    for (int k = 0; k < 7; k++) pnorm += dg[k] * d[k] * dg[k] * d[k];
+                    pnorm = sqrt(pnorm);
+                    solved = true;
+                    if (pnorm <= 1.1 * delta) break;
+                    par = fmax(par * 4.0, 1e-8 * fmax(maxratio, 1e-300));
+                }
+                if (!solved) { status = 3; break; }
+                double q[7], cost_q, jtj_q[28], jtr_q[7];
+                for (int k = 0; k < 7; k++) q[k] = p[k] + d[k];
+                gauss_pass(sh, img, n, q, true, &cost_q, jtj_q, jtr_q);
+                if (iter == 0) delta = fmin(delta, pnorm);
+                const bool finite_q = cost_q == cost_q && cost_q < 1.7e308;
+                const double actred = finite_q ? 1.0 - cost_q / cost : -1.0;
+                double jd2 = 0.0;                             // |J d|^2 = d^T (J^T J) d
+                for (int a = 0; a < 7; a++)
+                    for (int b2 = 0; b2 < 7; b2++) jd2 += d[a] * d[b2] * jtj[a >= b2 ? a * (a + 1) / 2 + b2 : b2 * (b2 + 1) / 2 + a];
+                const double t1 = jd2 / cost, t2 = par * pnorm * pnorm / cost;
+                const double prered = t1 + 2.0 * t2, dirder = -(t1 + t2);
+                const double ratio = prered != 0.0 ? actred / prered : 0.0;
+                if (ratio <= 0.25) {
+                    double temp = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+                    if (!finite_q || 0.1 * cost_q >= cost || temp < 0.1) temp = 0.1;
+                    delta = temp * fmin(delta, pnorm / 0.1);
+                    par /= temp;
+                } else if (par == 0.0 || ratio >= 0.75) {
+                    delta = pnorm / 0.5;
+                    par *= 0.5;
+                }
+                if (ratio >= 1e-4) {
+                    for (int k = 0; k < 7; k++) p[k] = q[k];
+                    cost = cost_q;
+                    for (int k = 0; k < 28; k++) jtj[k] = jtj_q[k];
+                    for (int k = 0; k < 7; k++) jtr[k] = jtr_q[k];
+                    xnorm = 0.0;
+                    for (int k = 0; k < 7; k++) xnorm += dg[k] * p[k] * dg[k] * p[k];
+                    xnorm = sqrt(xnorm);
+                }
+                if ((fabs(actred) <= tol && prered <= tol && 0.5 * ratio <= 1.0) || delta <= tol * xnorm || cost == 0.0) status = 0;
+            }
+        }
+        if (pm::tid() == 0) {
+            double* o = out + (size_t)b * kGaussCols;
+            for (int k = 0; k < 7; k++) o[k] = p[k];
+            o[7] = cost; o[8] = (double)iter; o[9] = (double)status;
+        }
+        pm::sync();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// source detection + cleaning
+// ----------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0, k1) -> four 32-bit words
+PM_HOSTDEV void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// standard normal of (seed, cutout, pixel): Box-Muller on two 32-bit uniforms in (0, 1]
+PM_DEV double philox_normal(unsigned long long seed, unsigned long long cutout, unsigned pixel) {
+    unsigned w[4];
+    philox4x32(pixel, (unsigned)cutout, (unsigned)(cutout >> 32), 0x504d4253u, (unsigned)seed, (unsigned)(seed >> 32), w);
+    const double u1 = ((double)w[0] + 1.0) * (1.0 / 4294967296.0), u2 = ((double)w[1] + 1.0) * (1.0 / 4294967296.0);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+
+// find with path halving on the parent array of the run forest
+PM_DEV int uf_find(int* parent, int i) {
+    for (;;) {
+        const int p = parent[i];
+        if (p == i) return i;
+        const int gp = parent[p];
+        if (gp != p) parent[i] = gp;
+        i = gp;
+    }
+}
+PM_DEV void uf_union(int* parent, int a, int b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }       // link the larger root under the smaller: roots only decrease
+        const int old = pm::atomic_cas(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+
+constexpr int kStarCols = 4;   // number of segments kept, number of segments cleaned, pixels replaced, status (1: run table overflow)
+
+// det: threshold[B]; fill: mean[B], std[B] of the replacement noise (imageutils.py:62, :86), seed.
+// labels_out [B, n, n] int32 (nullable): 0 background, 1.. segments in raster order of their first pixel (scipy.ndimage.label
+// order kept by photutils after the small ones are dropped); clean_out [B, n, n] of T (nullable): the cleaned image.
+// scratch (per CTA): runs as (row << 20 | c0 << 10 | c1) — n <= 640 fits 10 bits —, parents, sizes, boxes.
+template <typename T>
+PM_DEV void maskstars_body(const T* images, long long B, int n, const double* threshold, int npixels, const double* mean, const double* std_,
+                           unsigned long long seed, int* labels_out, T* clean_out, double* out, unsigned char* scratch_all,
+                           unsigned long long scratch_per_cta, int max_runs) {
+    unsigned char* smem = pm::dyn_smem(0);
+    Sh& sh = *(Sh*)smem;
+    const int nw = (n + 31) / 32;
+    unsigned* plane = (unsigned*)(smem + align16((unsigned)sizeof(Sh)));
+    unsigned* rowoff = plane + n * nw;                       // [n + 1] runs before each row
+    sh.par[pm::tid()] = 0;
+    pm::sync();
+    unsigned char* scratch = scratch_all + (size_t)pm::block() * scratch_per_cta;
+    unsigned* runs = (unsigned*)scratch;                     // [max_runs]
+    int* parent = (int*)(runs + max_runs);                   // [max_runs]
+    int* size = parent + max_runs;                           // [max_runs] pixel count per root
+    int* newlab = size + max_runs;                           // [max_runs] final label per root (0: dropped)
+    int* box = newlab + max_runs;                            // [max_runs][4] rmin, rmax, cmin, cmax per root
+    // astropy Gaussian2DKernel(sigma = 3 * gaussian_fwhm_to_sigma, x_size = 3, y_size = 3), normalised (imageutils.py:68-70)
+    const double sig = 3.0 * 0.42466090014400953, e1 = exp(-1.0 / (2.0 * sig * sig)), e2 = exp(-2.0 / (2.0 * sig * sig));
+    const double ksum = 1.0 + 4.0 * e1 + 4.0 * e2, k0 = 1.0 / ksum, k1 = e1 / ksum, k2 = e2 / ksum;
+    for (long long b = pm::block(); b < B; b += pm::nblocks()) {
+        const T* img = images + (size_t)b * n * n;
+        const double thr = threshold[b];
+        // ---- smoothed image > threshold -> bit plane (convolution with zero fill beyond the frame)
+        for (int task = pm::warp(); task < n * nw; task += kWarps) {
+            const int r = task / nw, w = task - r * nw, col = w * 32 + pm::lane();
+            bool above = false;
+            if (col < n) {
+                auto at = [&](int rr, int cc) -> double {
+                    return (rr >= 0 && rr < n && cc >= 0 && cc < n) ? (double)pm::ldg(img + (size_t)rr * n + cc) : 0.0;
+                };
+                // scipy.ndimage.convolve accumulation order is not reproduced: the decision `> threshold` is robust to it except
+                // at exact ties, which real data do not produce (threshold = mean + 1.5 std of the clipped pixels)
+                const double corner = at(r - 1, col - 1) + at(r - 1, col + 1) + at(r + 1, col - 1) + at(r + 1, col + 1);
+                const double edge = at(r - 1, col) + at(r + 1, col) + at(r, col - 1) + at(r, col + 1);
+                above = k0 * at(r, col) + k1 * edge + k2 * corner > thr;
+            }
+            const unsigned bits = pm::ballot(above);
+            if (pm::lane() == 0) plane[task] = bits;
+        }
+        pm::sync();
+        // ---- runs per row
+        for (int r = pm::tid(); r < n; r += kThreads) {
+            unsigned cnt = 0, carry = 0;
+            for (int w = 0; w < nw; w++) {
+                const unsigned v = plane[r * nw + w];
+                cnt += (unsigned)pm::popc(v & ~((v << 1) | carry));      // run starts: set bits whose left neighbour is clear
+                carry = v >> 31;
+            }
+            rowoff[r] = cnt;
+        }
+        pm::sync();
+        const int nruns = (int)block_scan_excl_array(sh, rowoff, n);
+        int status = 0;
+        if (nruns > max_runs) status = 1;
+        if (status == 0) {
+            for (int r = pm::tid(); r < n; r += kThreads) {
+                unsigned o = rowoff[r];
+                int start = -1;
+                for (int col = 0; col <= n; col++) {
+                    const bool on = col < n && ((plane[r * nw + (col >> 5)] >> (col & 31)) & 1u);
+                    if (on && start < 0) start = col;
+                    if (!on && start >= 0) { runs[o] = ((unsigned)r << 20) | ((unsigned)start << 10) | (unsigned)(col - 1); parent[o] = (int)o; o++; start = -1; }
+                }
+            }
+            pm::sync();
+            // ---- union runs of adjacent rows that touch (8-connectivity: column ranges overlap after widening by one)
+            for (int i = pm::tid(); i < nruns; i += kThreads) {
+                const unsigned ru = runs[i];
+                const int r = (int)(ru >> 20), c0 = (int)((ru >> 10) & 1023u), c1 = (int)(ru & 1023u);
+                if (r == 0) continue;
+                for (int j = (int)rowoff[r - 1]; j < (int)rowoff[r]; j++) {
+                    const unsigned rj = runs[j];
+                    const int d0 = (int)((rj >> 10) & 1023u), d1 = (int)(rj & 1023u);
+                    if (d0 > c1 + 1) break;
+                    if (d1 >= c0 - 1) uf_union(parent, i, j);
+                }
+            }
+            pm::sync();
+            // ---- roots, sizes, boxes
+            for (int i = pm::tid(); i < nruns; i += kThreads) { size[i] = 0; box[4 * i] = 0x7fffffff; box[4 * i + 1] = -1; box[4 * i + 2] = 0x7fffffff; box[4 * i + 3] = -1; }
+            pm::sync();
+            for (int i = pm::tid(); i < nruns; i += kThreads) {
+                const int root = uf_find(parent, i);
+                parent[i] = root;
+            }
+            pm::sync();
+            for (int i = pm::tid(); i < nruns; i += kThreads) {
+                const unsigned ru = runs[i];
+                const int r = (int)(ru >> 20), c0 = (int)((ru >> 10) & 1023u), c1 = (int)(ru & 1023u), root = parent[i];
+                pm::atomic_add(&size[root], c1 - c0 + 1);
+                pm::atomic_min(&box[4 * root], r); pm::atomic_max(&box[4 * root + 1], r);
+                pm::atomic_min(&box[4 * root + 2], c0); pm::atomic_max(&box[4 * root + 3], c1);
+            }
+            pm::sync();
+            // ---- labels of the kept roots in raster order of their first pixel (= order of the root run index)
+            for (int i = pm::tid(); i < nruns; i += kThreads) newlab[i] = (parent[i] == i && size[i] >= npixels) ? 1 : 0;
+            pm::sync();
+        }
+        int nkept = 0;
+        if (status == 0 && nruns > 0) nkept = (int)block_scan_excl_array(sh, (unsigned*)newlab, nruns);
+        // newlab[i] = number of kept roots before run i (the table has room for the total at [nruns]): a kept root i gets
+        // label newlab[i] + 1
+        if (labels_out) {
+            int* lab = labels_out + (size_t)b * n * n;
+            for (int i = pm::tid(); i < n * n; i += kThreads) lab[i] = 0;
+            pm::sync();
+            if (status == 0) {
+                for (int i = pm::warp(); i < nruns; i += kWarps) {
+                    const unsigned ru = runs[i];
+                    const int r = (int)(ru >> 20), c0 = (int)((ru >> 10) & 1023u), c1 = (int)(ru & 1023u), root = parent[i];
+                    if (size[root] < npixels) continue;
+                    const int l = newlab[root] + 1;
+                    for (int col = c0 + pm::lane(); col <= c1; col += 32) lab[r * n + col] = l;
+                }
+            }
+        }
+        // ---- cleaning (imageutils.py:73-89): a kept segment whose bounding box does not contain cenpix is a "star"; inside
+        // the bounding box of every star every pixel that belongs to ANY kept segment is replaced by N(mean, std) noise
+        // (np.where(data_ma > 0, 1, 0) reads the label cutout, masked or not), the others keep the image value
+        int ncleaned = 0, nrepl = 0;
+        if (clean_out) {
+            T* dst = clean_out + (size_t)b * n * n;
+            for (int i = pm::tid(); i < n * n; i += kThreads) dst[i] = pm::ldg(img + i);
+            pm::sync();
+            if (status == 0 && mean && std_) {
+                const double cen = (double)(n / 2 + 1);
+                const double mu = mean[b], sd = std_[b];
+                // star flag per root: _inBbox(extent = (cmin - 0.5, cmax + 0.5, rmin - 0.5, rmax + 0.5), cenpix), strict
+                for (int i = pm::tid(); i < nruns; i += kThreads) {
+                    if (parent[i] == i && size[i] >= npixels) {
+                        const bool inbox = cen > (double)box[4 * i + 2] - 0.5 && cen > (double)box[4 * i] - 0.5 &&
+                                           cen < (double)box[4 * i + 3] + 0.5 && cen < (double)box[4 * i + 1] + 0.5;
+                        size[i] = inbox ? size[i] : -size[i];          // negative size marks a star
+                        if (!inbox) ncleaned++;
+                    }
+                }
+                pm::sync();
+                // the stars' boxes as a compact list (newlab is free again once the labels are written)
+                if (pm::tid() == 0) sh.ia[1] = 0;
+                pm::sync();
+                for (int i = pm::tid(); i < nruns; i += kThreads)
+                    if (parent[i] == i && size[i] < 0 && -size[i] >= npixels) newlab[pm::atomic_add(&sh.ia[1], 1)] = i;
+                pm::sync();
+                const int nstars = sh.ia[1];
+                // a pixel of a kept segment is replaced when it lies inside the bounding box of at least one star
+                for (int i = pm::warp(); i < nruns; i += kWarps) {
+                    const unsigned ru = runs[i];
+                    const int r = (int)(ru >> 20), c0 = (int)((ru >> 10) & 1023u), c1 = (int)(ru & 1023u), root = parent[i];
+                    if ((size[root] < 0 ? -size[root] : size[root]) < npixels) continue;
+                    for (int col = c0 + pm::lane(); col <= c1; col += 32) {
+                        bool hit = size[root] < 0;                      // its own segment is a star
+                        for (int k = 0; k < nstars && !hit; k++) {
+                            const int j = newlab[k];
+                            hit = r >= box[4 * j] && r <= box[4 * j + 1] && col >= box[4 * j + 2] && col <= box[4 * j + 3];
+                        }
+                        if (hit) {
+                            double v = mu + sd * philox_normal(seed, (unsigned long long)b, (unsigned)(r * n + col));
+                            if (v == 0.0) v = (double)pm::ldg(img + (size_t)r * n + col);    // imageutils.py:89
+                            dst[r * n + col] = (T)v;
+                            nrepl++;
+                        }
+                    }
+                }
+            }
+        }
+        ncleaned = (int)block_sum_u(sh, (unsigned)ncleaned);
+        nrepl = (int)block_sum_u(sh, (unsigned)nrepl);
+        if (pm::tid() == 0) {
+            double* o = out + (size_t)b * kStarCols;
+            o[0] = (double)nkept; o[1] = (double)ncleaned; o[2] = (double)nrepl; o[3] = (double)status;
+        }
+        pm::sync();
+    }
+}
+PM_HOSTDEV unsigned maskstars_smem_bytes(int n) {
+    return align16((unsigned)sizeof(Sh)) + align16((unsigned)(n * ((n + 31) / 32) * 4)) + align16((unsigned)(n + 2) * 4);
+}
+PM_HOSTDEV int maskstars_max_runs(int n) { return n * ((n + 1) / 2) + 2; }                 // a run needs a gap: at most ceil(n / 2) per row
+PM_HOSTDEV unsigned long long maskstars_scratch_bytes(int n) { return ((unsigned long long)maskstars_max_runs(n) * 8 * 4 + 255) & ~255ull; }
+
+}  // namespace pmk

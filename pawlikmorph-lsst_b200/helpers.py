@@ -1,7 +1,8 @@
 """File-list helpers of the reference's driver (`pawlikMorphLSST/helpers.py`), without astropy."""
 import csv
+from pathlib import Path
 
-__all__ = ["getFiles"]
+__all__ = ["getFiles", "getLocation"]
 
 
 def getFiles(file: str):
@@ -16,3 +17,11 @@ def getFiles(file: str):
             if not row or not "".join(row).strip():
                 continue
             yield row[col["filename"]].strip(), float(row[col["ra"]]), float(row[col["dec"]])
+
+
+def getLocation(folder):
+    """Output folder as a Path, created when missing: `folder`, or ./output (helpers.py:70-94)."""
+    outfolder = Path(folder) if folder else Path().cwd() / "output"
+    if not outfolder.exists():
+        outfolder.mkdir()
+    return outfolder

@@ -9,9 +9,9 @@ default Result for a frame whose centre is too faint (main.py:420-424), the CSV 
 The cut-out of Image.py:135-138, :175-186 is kept too: with `npix` not larger than the frame and truthy ra / dec the
 npix x npix window around the catalogue position is analysed (sky -> pixel on the host, the copy fused with the decode
 on the device); otherwise the whole frame, like the reference.
-What is not here: `skybgr` (sky / sky_err are inputs, or the clipped border estimate below,
-which is also what the committed goldens used), `maskstarsSEG` cleaning (unseeded noise, imageutils.py:86), star
-catalogues, Sersic fits, diagnostic plots.  Options that would need them raise NotImplementedError.
+`skybgr` (skyBackground.py) and the `maskstarsSEG` cleaning (imageutils.py:42-91, with a seeded generator in place of the
+reference's unseeded one) run on the device too.  What is not here: star catalogues, Sersic
+fits, segmap / clean-image FITS output, diagnostic plots.  Options that would need them raise NotImplementedError.
 """
 import csv
 import os
@@ -62,32 +62,86 @@ def path_flags(asymmetry=False, shapeAsymmetry=False, allAsymmetry=True, CAS=Tru
     return f
 
 
+def _decode_dtype(bitpix, bzero, bscale):
+    """float32 holds BITPIX 8 / 16 pixels with integer scaling and BITPIX -32 exactly; everything else (BITPIX 32, -64,
+    fractional BSCALE / BZERO) is decoded to float64, which is what the reference analyses (Image.py:148)."""
+    import torch
+    exact = bitpix == -32 or (bitpix in (8, 16) and float(bzero).is_integer() and float(bscale).is_integer() and abs(bscale) * 65536 + abs(bzero) < 2 ** 24)
+    return torch.float32 if exact else torch.float64
+
+
+def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed):
+    """One group of equally sized cutouts that already live on the GPU through main.py:349-495: skybgr (unless sky is given),
+    pixelmap on the image with the sky in (:421), `img -= sky`, maskstarsSEG (:442-445), the rest on the cleaned image.
+    Returns rows [B, 16], sky, sky_err [B], fwhms [B, 2], theta [B] as numpy arrays."""
+    import torch
+
+    from .batch import analyse_batch
+    from .imageutils import maskstars_batch
+    from .skyBackground import skybgr_batch
+    B = int(images.shape[0])
+    fwhms, theta = np.full((B, 2), -99.0), np.full(B, -99.0)
+    sky_fail = np.zeros(B, dtype=bool)
+    if sky is None:
+        r = skybgr_batch(images, large, seed=seed)
+        sky, sky_err, fwhms, theta = r["sky"], r["sky_err"], r["fwhms"], r["theta"]
+        sky_fail = r["status"] != 0                                       # _SkyError / ValueError: default Result (main.py:350-368)
+        sky, sky_err = np.where(sky_fail, 0.0, sky), np.where(sky_fail, 0.0, sky_err)
+    dev = images.device
+    sky_d = torch.as_tensor(np.asarray(sky, dtype=np.float64), device=dev)
+    err_d = torch.as_tensor(np.asarray(sky_err, dtype=np.float64), device=dev)
+    if not clean:
+        rows = analyse_batch(images, sky_d, err_d, filterSize, flags).rows.cpu().numpy()
+    else:
+        first = analyse_batch(images, sky_d, err_d, filterSize, flags | _abi.PM_STOP_AFTER_PIXELMAP, want_segmap=True)
+        sub = images.to(torch.float64) - sky_d[:, None, None]                                   # main.py:442
+        cleaned = maskstars_batch(sub, seed=seed)["clean"]                                       # main.py:445
+        rows1 = first.rows.cpu().numpy()
+        rows = analyse_batch(cleaned, torch.zeros_like(sky_d), err_d, filterSize, flags, segmap_in=first.segmap,
+                             smooth_sky_in=sky_d).rows.cpu().numpy()
+        col = _abi.ROW_FIELDS.index
+        rows[:, col("object_edge")] = rows1[:, col("object_edge")]                               # main.py:427 (pixelmap path)
+        faint = rows1[:, col("status")] == 1
+        rows[faint] = rows1[faint]                                                               # main.py:420-424
+    rows[sky_fail] = -99.0
+    rows[sky_fail, _abi.ROW_FIELDS.index("status")] = 1.0
+    return rows, np.where(sky_fail, -99.0, sky), np.where(sky_fail, 99.0, sky_err), fwhms, theta
+
+
 def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filterSize=3, parallelLibrary="none", cores=1,
                    numberSigmas=5., asymmetry=False, shapeAsymmetry=False, allAsymmetry=True, calculateSersic=False,
                    saveSegMap=False, saveCleanImage=False, imageSource=None, catalogue=None, largeImage=False,
                    paramsaveFile="parameters.csv", occludedSaveFile="occluded-object-locations.csv", segmap=False,
-                   starMask=False, CAS=True, *, sky=None, gauss=None, smoothness=False, root=None, device="cuda:0", chunk=8192):
+                   starMask=False, CAS=True, *, sky=None, gauss=None, smoothness=False, clean=True, seed=0, root=None,
+                   device="cuda:0", chunk=8192):
     """Analyse the frames of `imageInfos` (iterable of (filename, ra, dec), e.g. helpers.getFiles) and write
-    `outfolder/paramsaveFile`; returns the list of Result in input order.
+    `outfolder/paramsaveFile`; returns the list of Result in input order.  The steps of main.py:349-495 per frame: sky
+    background, pixelmap, `img -= sky`, cleaning of external sources, the morphology statistics — batched per frame format.
 
-    sky: None (border_sky of every frame), a callable image -> (sky, sky_err), or a sequence of (sky, sky_err) pairs.
-    gauss: a sequence of (fwhms, theta) per image — the Gaussian fit of skyBackground.py:167-262, which is the caller's —
-    makes sky / sky_err the reference's own estimate: the statistics of the pixels outside the ellipse of semi-axes
-    2 min(fwhms), 2 max(fwhms) (skyBackground.py:134-164), measured on the device from the decoded cutout
-    (pm_sky_stats_batch); a sky region of fewer than 100 pixels raises skyBackground._SkyError like upstream.
+    sky: None — `skyBackground.skybgr` on the device, like upstream (main.py:349; with largeImage=True and largeImgFactor the
+    `-li` mode: source check and sky region on the cleaned cutout of npix * largeImgFactor pixels, skyBackground.py:71-76) —,
+    "border" / a callable image -> (sky, sky_err) (host; `border_sky` is the stand-in the goldens were made with), or a
+    sequence of (sky, sky_err) pairs.  gauss: a sequence of (fwhms, theta) per image: the sky-region statistics for a
+    caller-supplied Gaussian fit.
+    clean: the maskstarsSEG step between pixelmap and the statistics (main.py:445), seeded by `seed` (the reference's generator
+    is unseeded: imageutils.py:86); clean=False analyses the sky-subtracted image as it is.
     root: folder the file names are relative to.  parallelLibrary / cores are accepted and ignored: the batch is the
     parallelism.  npix: None analyses whole frames; a number takes the npix x npix window around (ra, dec) whenever the
     frame has at least npix rows and ra and dec are truthy (Image.py:135 — a declination of exactly 0 gives the whole
     frame, as upstream); a frame that cannot be read, or whose window leaves it (image.PartialOverlapError, the
-    `Cutout2D(mode="strict")` error), gets the default Result and the run carries on (main.py:331-339)."""
+    `Cutout2D(mode="strict")` error), gets the default Result and the run carries on (main.py:331-339); so does a frame
+    whose sky estimate fails (main.py:350-368)."""
     for name, val in (("calculateSersic", calculateSersic), ("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
-                      ("catalogue", catalogue), ("largeImage", largeImage), ("segmap", segmap), ("starMask", starMask)):
+                      ("catalogue", catalogue), ("segmap", segmap), ("starMask", starMask)):
         if val:
             raise NotImplementedError(f"{name}: outside the morphology path this package covers")
-    from .batch import analyse_host_payload      # needs torch + the CUDA library; fails loudly without them
+    if isinstance(sky, str) and sky == "border":
+        sky = border_sky
+    from . import batch as _batch                    # needs torch + the CUDA library; fails loudly without them
     infos = [(str(f), ra, dec) for f, ra, dec in imageInfos]
     t0 = time.time()
     frames, groups, failed = [], {}, set()
+    device_path = (sky is None and gauss is None) or clean
     for i, (f, _, _) in enumerate(infos):
         path = f if root is None or os.path.isabs(f) else os.path.join(str(root), f)
         # main.py:331-339: an image that cannot be read or cut (IOError, AttributeError, PartialOverlapError) gets the
@@ -99,6 +153,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                 raise ValueError(f"{f}: not a 2-D image")
             H, W = hdr["NAXIS2"], hdr["NAXIS1"]
             ra, dec = infos[i][1], infos[i][2]
+            origin_large, n_large = None, None
             if npix is not None and H >= npix and ra and dec:                      # Image.py:135-136
                 n = int(npix)
                 # sky_to_pixel returns the true (x = column, y = row) for RA-first and DEC-first headers alike; the
@@ -109,50 +164,88 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                 if H != W:
                     raise ValueError(f"{f}: whole frames must be square, got {H} x {W}")
                 n, origin = H, None
+            if largeImage and sky is None:                                          # main.py:323-328
+                nl = int(npix * largeImgFactor) if (npix is not None and largeImgFactor) else H
+                if H >= nl and ra and dec and nl < H:
+                    x, y = sky_to_pixel(hdr, ra, dec)
+                    origin_large, n_large = cutout_origin(x, y, nl, (H, W)), nl
+                else:
+                    if H != W:
+                        raise ValueError(f"{f}: whole frames must be square, got {H} x {W}")
+                    n_large = H                                                     # the whole frame
         except (OSError, AttributeError, PartialOverlapError, KeyError, ValueError) as e:
             print(f"{f}: {type(e).__name__}: {e} -- default Result")
-            frames.append([None, -99., 99., None])
+            frames.append([None, -99., 99., None, None])
             failed.add(i)
             continue
         pixels = None
-        if gauss is not None:
+        if gauss is not None or sky is None:
             s = (float("nan"), float("nan"))                                  # measured on the device below
-        elif sky is None or callable(sky):
+        elif callable(sky):
             pixels = _host_pixels(payload, hdr)
             if origin is not None:
                 pixels = pixels[origin[0]:origin[0] + n, origin[1]:origin[1] + n]
-            s = (sky or border_sky)(pixels)
+            s = sky(pixels)
         else:
             s = sky[i]
-        frames.append([payload, float(s[0]), float(s[1]), origin])
-        key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)))
+        frames.append([payload, float(s[0]), float(s[1]), origin, origin_large])
+        key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)), n_large, origin_large is not None)
         groups.setdefault(key, []).append(i)
     flags = path_flags(asymmetry, shapeAsymmetry, allAsymmetry, CAS, smoothness)
     rows = np.full((len(infos), _abi.ROW_DOUBLES), -99.0)
     for i in failed:
         rows[i, _abi.ROW_FIELDS.index("status")] = 1.0                         # -> the default Result (main.py:331-339)
-    for (n, H, W, windowed, bitpix, bzero, bscale), idx in groups.items():
+    fw_all, th_all = np.full((len(infos), 2), -99.0), np.full(len(infos), -99.0)
+    for (n, H, W, windowed, bitpix, bzero, bscale, n_large, large_windowed), idx in groups.items():
         pay = np.empty((len(idx), H * W * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
         for k, i in enumerate(idx):
             pay[k] = np.frombuffer(frames[i][0], dtype=np.uint8)
         win = dict(frame=(H, W), origins=np.array([frames[i][3] for i in idx], dtype=np.int32)) if windowed else {}
+        if device_path and gauss is None:
+            import torch
+
+            from .image import decode_payload, decode_window
+            dt = _decode_dtype(bitpix, bzero, bscale)
+            pd = torch.from_numpy(pay).to(device)
+            if windowed:
+                images = decode_window(pd, bitpix, (H, W), win["origins"], n, bzero, bscale, dt)
+            else:
+                images = decode_payload(pd, bitpix, (len(idx), n, n), bzero, bscale, dt)
+            large = None
+            if n_large is not None:
+                if large_windowed:
+                    large = decode_window(pd, bitpix, (H, W), np.array([frames[i][4] for i in idx], dtype=np.int32), n_large, bzero, bscale, dt)
+                else:
+                    large = decode_payload(pd, bitpix, (len(idx), H, W), bzero, bscale, dt)
+            have_sky = sky is not None
+            r, sk, er, fw, th = _device_group(images, large, np.array([frames[i][1] for i in idx]) if have_sky else None,
+                                              np.array([frames[i][2] for i in idx]) if have_sky else None, flags, filterSize, clean,
+                                              seed)
+            rows[idx] = r
+            fw_all[idx], th_all[idx] = fw, th
+            for k, i in enumerate(idx):
+                frames[i][1], frames[i][2] = float(sk[k]), float(er[k])
+            continue
         if gauss is not None:
             sky_rows = np.empty((len(idx), _abi.PM_SKY_COLS))
             win.update(gauss=(np.array([gauss[i][0] for i in idx], dtype=np.float64), np.array([gauss[i][1] for i in idx], dtype=np.float64)),
                        sky_rows_out=sky_rows)
-        rows[idx] = analyse_host_payload(pay, bitpix, n, np.array([frames[i][1] for i in idx]), np.array([frames[i][2] for i in idx]),
-                                         bzero=bzero, bscale=bscale, filter_size=filterSize, flags=flags, device=device, chunk=chunk,
-                                         **win)
+        rows[idx] = _batch.analyse_host_payload(pay, bitpix, n, np.array([frames[i][1] for i in idx]), np.array([frames[i][2] for i in idx]),
+                                                bzero=bzero, bscale=bscale, filter_size=filterSize, flags=flags, device=device, chunk=chunk,
+                                                **win)
         if gauss is not None:
             for k, i in enumerate(idx):
                 if sky_rows[k, 11] != 0:
                     from .skyBackground import _SkyError
                     raise _SkyError(f"Error! Sky region too small {int(sky_rows[k, 0])} ({infos[i][0]})")      # skyBackground.py:147-148
                 frames[i][1], frames[i][2] = float(sky_rows[k, 9]), float(sky_rows[k, 10])
+                fw_all[i], th_all[i] = np.asarray(gauss[i][0], dtype=np.float64), float(gauss[i][1])
     per_image = (time.time() - t0) / max(1, len(infos))
     results = []
     for i, (f, _, _) in enumerate(infos):
         r = Result.from_row(rows[i], file=os.path.basename(f), sky=frames[i][1], sky_err=frames[i][2])      # main.py:341: file.name
+        if r.status != 1 and fw_all[i, 0] != -99.0:
+            r.fwhms, r.theta = [float(fw_all[i, 0]), float(fw_all[i, 1])], float(th_all[i])                # main.py:349
         r.outfolder = str(outfolder)
         r.time = per_image
         results.append(r)

@@ -170,6 +170,10 @@ template <typename T> PM_DEV T ldg(const T* p) { return *p; }
 PM_DEV unsigned atomic_add(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 PM_DEV unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 PM_DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+PM_DEV int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+PM_DEV int atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+PM_DEV int atomic_max(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+PM_DEV int atomic_cas(int* p, int expected, int desired) { int o = *p; if (o == expected) *p = desired; return o; }
 // built with -ffp-contract=off: plain IEEE operations
 PM_DEV double dadd(double a, double b) { return a + b; }
 PM_DEV double dsub(double a, double b) { return a - b; }

@@ -33,7 +33,7 @@ def build(force=False):
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DPM_EMULATE",
            "-I" + os.path.join(REPO, "tests", "emul"), "-I" + os.path.join(REPO, "include"),
            "-x", "c++"] + [os.path.join(PKG, "csrc", u) for u in ("pm_capi.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu",
-                                                                   "pm_k_tailcta.cu", "pm_tail.cu")] + [
+                                                                   "pm_k_tailcta.cu", "pm_tail.cu", "pm_k_prep.cu")] + [
            os.path.join(REPO, "tests", "emul", "cuda_emul.cpp"),
            "-o", SO]
     subprocess.run(cmd, check=True)
@@ -144,3 +144,52 @@ def sky_stats(images, fwhms, theta):
                               out.ctypes.data, None)
     abi.check(L, rc, "pm_sky_stats_batch")
     return out
+
+
+def clipped_stats(images, sigma=3.0, maxiters=5):
+    """images [B,n,n] float32/float64 -> [B, 10] (CLIP_FIELDS); maxiters=None: until convergence."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    B, n, _ = images.shape
+    out = np.full((B, abi.PM_CLIP_COLS), np.nan)
+    rc = L.pm_clipped_stats_batch(images.ctypes.data, abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64, B, n, float(sigma),
+                                  0 if maxiters is None else int(maxiters), out.ctypes.data, None)
+    abi.check(L, rc, "pm_clipped_stats_batch")
+    return out
+
+
+def gaussfit(images, p0=None):
+    """-> [B, 10] (GAUSS_FIELDS); start values from gaussfitter.moments unless p0 [B, 7] is given."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    B, n, _ = images.shape
+    out = np.full((B, abi.PM_GAUSS_COLS), np.nan)
+    med = mx = None
+    if p0 is None:
+        cs = clipped_stats(images, 3.0, 1)
+        med, mx = np.ascontiguousarray(cs[:, 2]), np.ascontiguousarray(cs[:, 9])
+    else:
+        p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(B, 7))
+    rc = L.pm_gaussfit_batch(images.ctypes.data, abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64, B, n, _p(med), _p(mx), _p(p0),
+                             out.ctypes.data, None)
+    abi.check(L, rc, "pm_gaussfit_batch")
+    return out
+
+
+def maskstars(images, seed=0, nsigma=1.5, npixels=8, clean=True):
+    """imageutils.maskstarsSEG through the emulator build: dict(clean, labels, info)."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    B, n, _ = images.shape
+    c5, cn = clipped_stats(images, 3.0, 5), clipped_stats(images, 3.0, None)
+    thr = np.ascontiguousarray(cn[:, 6] + nsigma * cn[:, 8])
+    mean, std = np.ascontiguousarray(c5[:, 6]), np.ascontiguousarray(c5[:, 8])
+    labels = np.full((B, n, n), -1, np.int32)
+    out_img = np.full_like(images, np.nan) if clean else None
+    info = np.full((B, abi.PM_STAR_COLS), np.nan)
+    wsb = L.pm_maskstars_workspace_bytes(B, n)
+    ws = np.zeros(wsb // 8 + 2, np.float64)
+    rc = L.pm_maskstars_batch(images.ctypes.data, abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64, B, n, thr.ctypes.data, npixels,
+                              mean.ctypes.data, std.ctypes.data, seed, labels.ctypes.data, _p(out_img), info.ctypes.data, ws.ctypes.data, wsb, None)
+    abi.check(L, rc, "pm_maskstars_batch")
+    return dict(clean=out_img, labels=labels, info=info, threshold=thr, mean=mean, std=std)

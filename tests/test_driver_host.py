@@ -73,7 +73,7 @@ def test_driver_dataflow_on_the_emulator_build(tmp_path, monkeypatch):
         fn = f"f{k}.fits"
         (tmp_path / fn).write_bytes(fits_bytes(g.image(i), -32 if k == 1 else 16))
         infos.append((fn, 1.0, 2.0))
-    res = pm.main.calcMorphology(infos, tmp_path / "out", smoothness=True, root=tmp_path)
+    res = pm.main.calcMorphology(infos, tmp_path / "out", smoothness=True, root=tmp_path, sky="border", clean=False)
     table = list(_csv.reader(open(tmp_path / "out" / "parameters.csv")))
     assert table[0] == pm.result.CSV_HEADER and [r[0] for r in table[1:]] == [f for f, _, _ in infos]
     for k, i in enumerate(pick):
@@ -85,7 +85,7 @@ def test_driver_dataflow_on_the_emulator_build(tmp_path, monkeypatch):
         assert not errs, "\n".join(errs)
     import pytest
     with pytest.raises(NotImplementedError):
-        pm.main.calcMorphology(infos, tmp_path / "out", calculateSersic=True, root=tmp_path)
+        pm.main.calcMorphology(infos, tmp_path / "out", calculateSersic=True, root=tmp_path, sky="border", clean=False)
 
 
 def _wcs_by_name():
@@ -119,7 +119,7 @@ def test_driver_cutout_on_the_emulator_build(tmp_path, monkeypatch):
         name = str(g.z["names"][i])
         (tmp_path / name).write_bytes(fits_bytes(g.image(i), 16, extra=wcs[name]["header"]))
         infos.append((name, wcs[name]["ra"], wcs[name]["dec"]))
-    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, smoothness=True, root=tmp_path)
+    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, smoothness=True, root=tmp_path, sky="border", clean=False)
     for k, i in enumerate(pick):
         h = wcs[infos[k][0]]["header"]
         r0, c0 = pm.image.cutout_origin(*pm.image.sky_to_pixel(h, infos[k][1], infos[k][2]), 128, g.image(i).shape)
@@ -136,7 +136,7 @@ def test_driver_cutout_on_the_emulator_build(tmp_path, monkeypatch):
     seen.clear()
     monkeypatch.setattr(batch, "analyse_host_payload", lambda payload, bitpix, n, *a, frame=None, **kw: (
         seen.setdefault("n", n), np.full((len(payload), 16), -99.0))[1])
-    pm.main.calcMorphology([(infos[0][0], infos[0][1], 0.0)], tmp_path / "out", npix=128, root=tmp_path)
+    pm.main.calcMorphology([(infos[0][0], infos[0][1], 0.0)], tmp_path / "out", npix=128, root=tmp_path, sky="border", clean=False)
     assert seen["n"] == 177
 
 
@@ -169,7 +169,7 @@ def test_driver_dec_first_header_and_bad_frames(tmp_path, monkeypatch):
     monkeypatch.setattr(batch, "analyse_host_payload", fake)
     ra, dec = wcs[name]["ra"], wcs[name]["dec"]
     infos = [("sub/ra_first.fits", ra, dec), ("sub/missing.fits", ra, dec), ("sub/dec_first.fits", ra, dec), ("sub/edge.fits", ra, dec)]
-    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, root=tmp_path)
+    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, root=tmp_path, sky="border", clean=False)
     assert len(seen) == 1 and seen[0].shape == (2, 2) and np.array_equal(seen[0][0], seen[0][1])
     assert [r.file for r in res] == ["ra_first.fits", "missing.fits", "dec_first.fits", "edge.fits"]
     assert [r.status for r in res] == [0, 1, 0, 1] and res[1].rmax == -99 and res[3].rmax == -99 and res[0].rmax == 7.0

@@ -26,7 +26,7 @@ def test_calcMorphology_on_the_sdss_frames(name, tmp_path):
     (tmp_path / "images.csv").write_text("\n".join(lines) + "\n")
     out = tmp_path / "output"
     res = pm.main.calcMorphology(pm.helpers.getFiles(str(tmp_path / "images.csv")), out, filterSize=3, allAsymmetry=True, CAS=True,
-                                 smoothness=True, root=tmp_path)
+                                 smoothness=True, root=tmp_path, sky="border", clean=False)
     assert len(res) == g.n
     table = list(csv.reader(open(out / "parameters.csv")))
     assert table[0] == pm.result.CSV_HEADER and len(table) == g.n + 1
@@ -45,7 +45,7 @@ def test_calcMorphology_on_the_sdss_frames(name, tmp_path):
         assert d["Object on image edge?"] == str(r.objectEdge)
     # -A only (main.py:469-476): the CAS and shape columns keep their sentinels
     res_a = pm.main.calcMorphology(list(pm.helpers.getFiles(str(tmp_path / "images.csv")))[:5], out, asymmetry=True, allAsymmetry=False,
-                                   CAS=False, paramsaveFile="a.csv", root=tmp_path)
+                                   CAS=False, paramsaveFile="a.csv", root=tmp_path, sky="border", clean=False)
     for i, r in enumerate(res_a):
         assert r.A == res[i].A and r.As == [-99., -99.] and r.C == -99. and r.gini == -99. and r.S == -99.
 
@@ -71,7 +71,7 @@ def test_calcMorphology_cutouts_of_the_catalogue_positions(tmp_path):
         infos.append((e["file"], e["ra"], e["dec"]))
         r0, c0 = pm.image.cutout_origin(*pm.image.sky_to_pixel(e["header"], e["ra"], e["dec"]), 128, img.shape)
         wins.append(img[r0:r0 + 128, c0:c0 + 128].astype(np.float32))
-    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, smoothness=True, root=tmp_path)
+    res = pm.main.calcMorphology(infos, tmp_path / "out", npix=128, smoothness=True, root=tmp_path, sky="border", clean=False)
     sky = np.array([r.sky for r in res]), np.array([r.sky_err for r in res])
     for k, r in enumerate(res):
         assert (r.sky, r.sky_err) == pm.main.border_sky(wins[k])
