@@ -39,9 +39,12 @@ def subdistarr(npix, nsubpix, cenpix):
     (the y vector reuses the x one, :200).  Folded into the aperture kernel; device tensor ops here."""
     dev = _single.device()
     half = (int(npix) // 2) * int(nsubpix)
-    neg = torch.arange(half, device=dev, dtype=torch.float64) / float(nsubpix) - float(cenpix[0])
-    v = torch.cat((neg, torch.zeros(int(nsubpix), device=dev, dtype=torch.float64), -neg.flip(0)))
-    return torch.sqrt(v[:, None] ** 2 + v[None, :] ** 2).cpu().numpy()
+    # the coordinate vector on the host (a few thousand correctly rounded divisions: torch divides by a scalar through its
+    # reciprocal), the (npix * nsubpix)^2 distance grid on the device
+    neg = np.arange(half, dtype=np.float64) / float(nsubpix) - float(cenpix[0])
+    v = torch.from_numpy(np.concatenate((neg, np.zeros(int(nsubpix)), -neg[::-1]))).to(dev)
+    v2 = v * v
+    return torch.sqrt(v2[:, None] + v2[None, :]).cpu().numpy()
 
 
 def apercentre(apermask, pix):

@@ -142,35 +142,58 @@ def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segma
 _host_cache = {}
 
 
-def _host_staging(dev, chunk, n, dtype, B):
-    """Reusable buffers of analyse_host: two device staging tensors and two streams (chunks alternate), device rows
-    and a pinned host copy of them.  Kept per (device, chunk, n, dtype) so that a steady stream of calls allocates
-    nothing (device allocations and pinning synchronise the device)."""
-    key = (dev.type, dev.index, int(chunk), int(n), dtype)
+def clear_cache():
+    """Release the workspaces, staging buffers, streams and pinned rows kept between calls."""
+    _ws_cache.clear()
+    _host_cache.clear()
+    torch.cuda.empty_cache()
+
+
+def _staging(dev, row_bytes_key, chunk, row_shape, dtype, B):
+    """Reusable buffers of the host calls: two device staging tensors and two streams (chunks alternate), device rows and a
+    pinned host copy of them.  One entry per (device, row shape, dtype); the buffers GROW to the largest chunk / batch seen
+    (a caller looping over groups of varying size does not leak), `clear_cache()` releases them."""
+    key = (dev.type, dev.index, row_bytes_key, dtype)
     h = _host_cache.get(key)
     if h is None:
-        h = dict(bufs=[torch.empty((chunk, n, n), dtype=dtype, device=dev) for _ in range(2)],
-                 streams=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)], rows_d=None, rows_h=None)
+        h = dict(bufs=None, streams=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)], rows_d=None, rows_h=None, pin=None)
         _host_cache[key] = h
+    if h["bufs"] is None or h["bufs"][0].shape[0] < chunk:
+        h["bufs"] = [torch.empty((chunk,) + tuple(row_shape), dtype=dtype, device=dev) for _ in range(2)]
     if h["rows_d"] is None or h["rows_d"].shape[0] < B:
         h["rows_d"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev)
         h["rows_h"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
     return h
 
 
+def _pinned_chunks(h, x, s, e):
+    """x[s:e] as a pinned tensor: itself when the input is pinned, else staged through a pinned buffer (two, alternating)
+    so that the copy to the device stays asynchronous."""
+    if x.is_pinned():
+        return x[s:e], None
+    n = e - s
+    if h["pin"] is None or h["pin"][0].shape[0] < n or h["pin"][0].shape[1:] != x.shape[1:] or h["pin"][0].dtype != x.dtype:
+        h["pin"] = [torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype).pin_memory() for _ in range(2)]
+        h["pin_ev"] = [None, None]
+    return None, n
+
+
 def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="cuda:0", chunk=8192, **kw):
     """The call a user of the reference's driver makes: HOST arrays in, HOST rows out.
 
-    `images` is a numpy array / CPU tensor [B, n, n] (pinned memory makes the copies asynchronous); chunks
-    alternate between two streams, each with its own device staging buffer, so that the host->device copy of
-    chunk i+1 overlaps the kernel of chunk i.  Returns a [B, 16] float64 numpy array (columns = ROW_FIELDS)."""
+    `images` is a numpy array / CPU tensor [B, n, n]; chunks alternate between two streams, each with its own device staging
+    buffer, so that the host->device copy of chunk i+1 overlaps the kernel of chunk i.  Pinned input is copied straight
+    from where it is; pageable input is staged through two pinned buffers.  Returns a [B, 16] float64 numpy array
+    (columns = ROW_FIELDS) that the caller owns."""
     dev = torch.device(device)
     x = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
     if x.dtype not in (torch.float32, torch.float64):
         x = x.to(torch.float64) if x.dtype in (torch.int64, torch.uint64) else x.to(torch.float32)
     B, n = int(x.shape[0]), int(x.shape[1])
+    if B == 0:
+        return np.empty((0, ROW_DOUBLES))
     chunk = max(1, min(int(chunk), B))
-    h = _host_staging(dev, chunk, n, x.dtype, B)
+    h = _staging(dev, ("img", n), chunk, (n, n), x.dtype, B)
     cur = torch.cuda.current_stream(dev)
     sky_d = _per_galaxy(sky, B, dev, "sky")
     err_d = _per_galaxy(sky_err, B, dev, "sky_err")
@@ -182,23 +205,44 @@ def analyse_host(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, device="c
         st = h["streams"][i & 1]
         if i < 2:
             st.wait_event(ready)           # the sky vectors (and whatever the caller queued before)
+        src, m = _pinned_chunks(h, x, s, e)
+        if src is None:                    # pageable input: through the pinned buffer of this stream
+            if h["pin_ev"][i & 1] is not None:
+                h["pin_ev"][i & 1].synchronize()
+            src = h["pin"][i & 1][:m]
+            src.copy_(x[s:e])
         with torch.cuda.stream(st):
             d = h["bufs"][i & 1][:e - s]
-            d.copy_(x[s:e], non_blocking=True)
+            d.copy_(src, non_blocking=True)
+            if not x.is_pinned():
+                ev = torch.cuda.Event()
+                ev.record(st)
+                h["pin_ev"][i & 1] = ev
             analyse_batch(d, sky_d[s:e], err_d[s:e], filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
     for st in h["streams"]:
         cur.wait_stream(st)
+    out = torch.empty((B, ROW_DOUBLES), dtype=torch.float64)
     rows_h = h["rows_h"][:B]
     rows_h.copy_(rows_d[:B], non_blocking=True)
     cur.synchronize()
-    return rows_h.numpy().copy()
+    out.copy_(rows_h)
+    return out.numpy()
+
+
+def payload_dtype(bitpix, bzero=0.0, bscale=1.0):
+    """Decode type that loses nothing: float32 holds BITPIX 8 / 16 pixels with integer scaling and BITPIX -32 exactly;
+    BITPIX 32 / -64 and fractional BSCALE / BZERO need float64 (what the reference analyses, Image.py:148)."""
+    exact = bitpix == -32 or (bitpix in (8, 16) and float(bzero).is_integer() and float(bscale).is_integer()
+                              and abs(bscale) * 65536 + abs(bzero) < 2 ** 24)
+    return torch.float32 if exact else torch.float64
 
 
 def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0, filter_size=3, flags=PM_DO_ALL,
-                         device="cuda:0", chunk=8192, frame=None, origins=None, gauss=None, sky_rows_out=None, **kw):
+                         device="cuda:0", chunk=8192, frame=None, origins=None, gauss=None, sky_rows_out=None, dtype=None, **kw):
     """Like analyse_host, but from the big-endian FITS pixel blocks of B cutouts of n x n pixels (`payload`: uint8
     numpy array / CPU tensor [B, n * n * bytes_per_pixel], pinned memory makes the copies asynchronous).  The bytes are
     copied as they are and decoded on the device (image.decode_payload): 2 bytes per pixel on the wire for BITPIX 16.
+    `dtype`: the decoded type, by default the smallest that is exact for (bitpix, bzero, bscale) (`payload_dtype`).
     With `frame=(H, W)` and `origins` (int32 [B, 2]: first row, first column) every payload row is a whole H x W frame
     and the n x n window at its origin is analysed (image.decode_window: the cut-out of Image.py:175-186 on the device).
     With `gauss=(fwhms [B, 2], theta [B])` — the Gaussian fit of skyBackground.py:167-262 — `sky` / `sky_err` are not
@@ -215,16 +259,11 @@ def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0
         if origins.shape[0] != x.shape[0]:
             raise ValueError("one window origin per frame")
     B = int(x.shape[0])
+    if B == 0:
+        return np.empty((0, ROW_DOUBLES))
+    dt = dtype if dtype is not None else payload_dtype(bitpix, bzero, bscale)
     chunk = max(1, min(int(chunk), B))
-    key = (dev.type, dev.index, int(chunk), int(x.shape[1]), "payload")
-    h = _host_cache.get(key)
-    if h is None:
-        h = dict(bufs=[torch.empty((chunk, x.shape[1]), dtype=torch.uint8, device=dev) for _ in range(2)],
-                 streams=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)], rows_d=None, rows_h=None)
-        _host_cache[key] = h
-    if h["rows_d"] is None or h["rows_d"].shape[0] < B:
-        h["rows_d"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64, device=dev)
-        h["rows_h"] = torch.empty((B, ROW_DOUBLES), dtype=torch.float64).pin_memory()
+    h = _staging(dev, ("payload", int(x.shape[1])), chunk, (int(x.shape[1]),), torch.uint8, B)
     cur = torch.cuda.current_stream(dev)
     if gauss is None:
         sky_d = _per_galaxy(sky, B, dev, "sky")
@@ -247,9 +286,9 @@ def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0
             d = h["bufs"][i & 1][:e - s]
             d.copy_(x[s:e], non_blocking=True)
             if frame is None:
-                img = decode_payload(d, bitpix, (e - s, n, n), bzero, bscale, torch.float32, stream=st)
+                img = decode_payload(d, bitpix, (e - s, n, n), bzero, bscale, dt, stream=st)
             else:
-                img = decode_window(d, bitpix, (H, W), origins[s:e], n, bzero, bscale, torch.float32, stream=st)
+                img = decode_window(d, bitpix, (H, W), origins[s:e], n, bzero, bscale, dt, stream=st)
             if gauss is None:
                 sk, er = sky_d[s:e], err_d[s:e]
             else:
@@ -259,12 +298,14 @@ def analyse_host_payload(payload, bitpix, n, sky, sky_err, bzero=0.0, bscale=1.0
             analyse_batch(img, sk, er, filter_size, flags, rows_out=rows_d[s:e], stream=st, **kw)
     for st in h["streams"]:
         cur.wait_stream(st)
+    out = torch.empty((B, ROW_DOUBLES), dtype=torch.float64)
     rows_h = h["rows_h"][:B]
     rows_h.copy_(rows_d[:B], non_blocking=True)
     cur.synchronize()
+    out.copy_(rows_h)
     if skyrows_d is not None and sky_rows_out is not None:
         sky_rows_out[...] = skyrows_d.cpu().numpy()
-    return rows_h.numpy().copy()
+    return out.numpy()
 
 
 # ---- multi-GPU: galaxies are independent, so the batch shards by galaxy (main.py:136-148 did the

@@ -63,11 +63,8 @@ def path_flags(asymmetry=False, shapeAsymmetry=False, allAsymmetry=True, CAS=Tru
 
 
 def _decode_dtype(bitpix, bzero, bscale):
-    """float32 holds BITPIX 8 / 16 pixels with integer scaling and BITPIX -32 exactly; everything else (BITPIX 32, -64,
-    fractional BSCALE / BZERO) is decoded to float64, which is what the reference analyses (Image.py:148)."""
-    import torch
-    exact = bitpix == -32 or (bitpix in (8, 16) and float(bzero).is_integer() and float(bscale).is_integer() and abs(bscale) * 65536 + abs(bzero) < 2 ** 24)
-    return torch.float32 if exact else torch.float64
+    from .batch import payload_dtype
+    return payload_dtype(bitpix, bzero, bscale)
 
 
 def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed):

@@ -156,6 +156,9 @@ def test_per_cutout_api_matches_oracle_functions():
         np.testing.assert_allclose(pm.casgm.smoothness(img, seg, apix, rmax, w20, 100.0),
                                    O.smoothness(img, seg, apix, rmax, w20, 100.0), rtol=1e-8)
         np.testing.assert_array_equal(pm.apertures.distarr(n, n, np.array([3, 5])), O.distarr(n, n, np.array([3, 5])))
+        for npix_, ns_ in ((n, 9), (15, 9), (16, 3)):          # odd and even sizes (apertures.py:96-114 reads the first n blocks)
+            c_ = np.array([npix_ // 2 + 1, npix_ // 2 + 1])
+            np.testing.assert_array_equal(pm.apertures.subdistarr(npix_, ns_, c_), O.subdistarr(npix_, ns_, c_))
         np.testing.assert_array_equal(pm.apertures.apercentre(ap, np.array(apix)), O.apercentre(ap, np.array(apix)))
     with pytest.raises(AttributeError):
         pm.pixmap.pixelmap(img_sky, 1e9, 3)          # "Central pixel too faint" (pixmap.py:178-179)

@@ -36,3 +36,22 @@ def test_golden_sets_are_complete():
     # canonical (stable) and native argsort tie order gave identical results everywhere
     for name in ("sdss_s", "sdss_l", "synth"):
         assert not _gs(name).z["native_differs"].any()
+
+
+def test_oracle_aperture_helpers_against_the_reference_numba_functions():
+    """distarr / subdistarr / aperpixmap / apercentre of the oracle against the reference's own numba functions, executed
+    unmodified (oracle/ref_import.py).  Runs where /root/reference exists (the build container); skipped elsewhere."""
+    import pytest
+
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present")
+    R = ref_import.load().apertures
+    for npix, ns in ((15, 9), (16, 9), (31, 3), (64, 9)):
+        cen = np.array([npix // 2 + 1, npix // 2 + 1], dtype=np.int64)
+        assert np.array_equal(O.subdistarr(npix, ns, cen), R.subdistarr(npix, ns, cen))
+        assert np.array_equal(O.distarr(npix, npix, cen), R.distarr(npix, npix, cen))
+        for rad in (2.0, np.sqrt(37.0), npix / 3.0):
+            ap = R.aperpixmap(npix, rad, 9, 0.1)
+            assert np.array_equal(O.aperpixmap(npix, rad, 9, 0.1), ap)
+            assert np.array_equal(O.apercentre(ap, np.array([npix // 2 + 3, npix // 2 - 2])), R.apercentre(ap, np.array([npix // 2 + 3, npix // 2 - 2])))
