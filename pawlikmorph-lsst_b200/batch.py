@@ -139,6 +139,96 @@ def analyse_batch(images, sky, sky_err, filter_size=3, flags=PM_DO_ALL, *, segma
     return res
 
 
+def _rotated_masks(star, angle, cx, cy):
+    """Batched starMask * rotate(starMask, angle, center=(cx, cy), cval=1) (asymmetry.py:186-191) for integer centres and
+    the angles of the path: an index permutation with 1 where the source falls outside the frame.  star: [B, n, n] bool / u8;
+    cx, cy: int64 [B].  Device tensor ops (0/1 arithmetic, exact)."""
+    B, n = star.shape[0], star.shape[1]
+    dev = star.device
+    r = torch.arange(n, device=dev)[None, :, None]
+    c = torch.arange(n, device=dev)[None, None, :]
+    cxv, cyv = cx[:, None, None], cy[:, None, None]
+    if angle == 180:
+        sr, sc = 2 * cyv - r, 2 * cxv - c
+    else:
+        sr, sc = cyv + (c - cxv), cxv - (r - cyv)
+    sr, sc = sr.expand(B, n, n), sc.expand(B, n, n)
+    ok = (sr >= 0) & (sr < n) & (sc >= 0) & (sc < n)
+    flat = star.reshape(B, -1).to(torch.uint8)
+    idx = (sr.clamp(0, n - 1) * n + sc.clamp(0, n - 1)).reshape(B, -1)
+    rot = torch.where(ok.reshape(B, -1), torch.gather(flat, 1, idx), torch.ones_like(flat)).reshape(B, n, n)
+    return (star.to(torch.uint8) * rot)
+
+
+def analyse_batch_starmask(images, sky, sky_err, starmask, filter_size=3, flags=PM_DO_ALL, stream=None):
+    """The path with a star mask per cutout (1 = keep) — the `-starmask` flow of main.py:395-413 and what follows it:
+    pixelmap(img, thr, fs, starMask) (pixmap.py:156-158), calcRmax without the mask, minapix on image * segmap * starMask
+    (asymmetry.py:82-86), calcA with S = starMask * rotate(starMask) about apix, the segmap multiplied by S in place
+    (:186-196, :219) and used like that by As, As90 (with the 90 degree S), r20 / r80, Gini and M20 (main.py:470-495).
+    A composition of launches of the fused kernel with its overrides (the mask changes between the steps once apix is
+    known), for the rare catalogue / star-mask runs; `pm_analyse_batch` itself rejects `starmask`.  With noisecorrect the
+    reference's result depends on ~1e-14 leakage of skimage's bilinear rotation of the mask; the exact 0/1 mask is used.
+    Returns a BatchResult (rows + the pixelmap)."""
+    if not torch.is_tensor(images) or not images.is_cuda:
+        raise TypeError("analyse_batch_starmask needs a CUDA tensor (there is no CPU path)")
+    dev = images.device
+    B, n = int(images.shape[0]), int(images.shape[1])
+    star = _mask(starmask, B, n, dev, "starmask")
+    sky_t = _per_galaxy(sky, B, dev, "sky")
+    err_t = _per_galaxy(sky_err, B, dev, "sky_err")
+    col = ROW_FIELDS.index
+    kw = dict(stream=stream)
+    # 1. pixelmap of image * starMask (sky still in)
+    p1 = analyse_batch(images * star.to(images.dtype), sky_t, err_t, filter_size, flags | _abi.PM_STOP_AFTER_PIXELMAP, want_segmap=True, **kw)
+    rows = p1.rows.clone()
+    seg = p1.segmap
+    ok = rows[:, col("status")] == 0
+    # 2. rmax from the unmasked image and the map (pixmap.calcRmax, main.py:463)
+    p2 = analyse_batch(images, sky_t, err_t, filter_size, _abi.PM_STOP_AFTER_RMAX, segmap_in=seg, **kw)
+    rmax = p2.rows[:, col("rmax")].contiguous()
+    rows[:, col("rmax")] = torch.where(ok, rmax, rows[:, col("rmax")])
+    status2 = p2.rows[:, col("status")]
+    # 3. minapix: image * segmap * starMask == the map with the masked pixels taken out
+    p3 = analyse_batch(images, sky_t, err_t, filter_size, 0, segmap_in=seg * star, radius_in=torch.where(rmax > 0, rmax, torch.ones_like(rmax)), **kw)
+    for name in ("apix_col", "apix_row", "n_candidates"):
+        rows[:, col(name)] = torch.where(ok, p3.rows[:, col(name)], rows[:, col(name)])
+    status3 = p3.rows[:, col("status")]
+    cx = p3.rows[:, col("apix_col")].clamp(min=0).to(torch.int64)
+    cy = p3.rows[:, col("apix_row")].clamp(min=0).to(torch.int64)
+    cen = torch.stack([cx, cy], dim=1).to(torch.float64)
+    good = ok & (status2 == 0) & (status3 == 0)
+    # 4. A, Abgr, As, r20, r80, C, Gini, M20 on I = (img - sky) * S180 with the map * S180
+    s180 = _rotated_masks(star, 180, cx, cy)
+    sub = images.to(torch.float64) - sky_t[:, None, None]
+    zero = torch.zeros_like(sky_t)
+    seg180 = seg * s180
+    f4 = flags & (_abi.PM_DO_A | _abi.PM_DO_AS | _abi.PM_DO_CAS)
+    if f4:
+        p4 = analyse_batch(sub * s180.to(torch.float64), zero, err_t, filter_size, f4, segmap_in=seg180, centroid_in=cen, radius_in=rmax, **kw)
+        for name in ("A", "Abgr", "As", "r20", "r80", "C", "gini", "m20"):
+            rows[:, col(name)] = torch.where(good, p4.rows[:, col(name)], rows[:, col(name)])
+        status4 = p4.rows[:, col("status")]
+    else:
+        status4 = torch.zeros_like(status3)
+    # 5. As90 with S90 = starMask * rotate(starMask, 90) on the (already multiplied) map
+    if flags & _abi.PM_DO_AS:
+        s90 = _rotated_masks(star, 90, cx, cy)
+        p5 = analyse_batch(sub, zero, err_t, filter_size, _abi.PM_DO_AS, segmap_in=seg180 * s90, centroid_in=cen, radius_in=rmax, **kw)
+        rows[:, col("As90")] = torch.where(good, p5.rows[:, col("As90")], rows[:, col("As90")])
+    # 6. smoothness on the unmasked image with the multiplied map (casgm.smoothness takes img, segmap: main.py:494)
+    if (flags & _abi.PM_DO_S) and (flags & _abi.PM_DO_CAS):
+        r20 = rows[:, col("r20")].contiguous()
+        p6 = analyse_batch(sub, zero, err_t, filter_size, _abi.PM_DO_S, segmap_in=seg180, centroid_in=cen, radius_in=rmax,
+                           r20_in=torch.where(r20 > 0, r20, torch.ones_like(r20)), smooth_sky_in=sky_t, **kw)
+        rows[:, col("S")] = torch.where(good & (status4 == 0) & (r20 > 0), p6.rows[:, col("S")], rows[:, col("S")])
+    st = rows[:, col("status")]
+    st = torch.where(ok & (status2 != 0), status2, st)
+    st = torch.where(ok & (status2 == 0) & (status3 != 0), status3, st)
+    st = torch.where(good & (status4 != 0), status4, st)
+    rows[:, col("status")] = st
+    return BatchResult(rows=rows, segmap=seg)
+
+
 _host_cache = {}
 
 

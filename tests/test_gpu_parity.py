@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from tests import parity_checks as P
+from tests.golden_util import compare_row
 from tests.runners import gpu_runner as run
 
 pytestmark = pytest.mark.gpu
@@ -255,3 +256,50 @@ def test_maximum_size_and_supplied_segmaps():
 
 def test_small_radius_growth_curves():
     P.check_small_radius_growth_curves(run)
+
+
+def test_star_masks_in_the_batch_api():
+    """batch.analyse_batch_starmask: the -starmask flow (main.py:395-413, :463-495) for a batch, against the same chain of
+    oracle calls (exact 0/1 rotated masks, like test_star_masks_in_the_per_cutout_api)."""
+    import torch
+
+    import pawlikmorph_lsst_b200 as pm
+    from oracle import pm_oracle as O
+    from pawlikmorph_lsst_b200 import _single
+    n, B = 96, 4
+    x = P.synth_batch(B, n, 83)
+    rng = np.random.default_rng(83)
+    star = np.ones((B, n, n), np.uint8)
+    for b in range(B):
+        for _ in range(3):
+            r0, c0 = rng.integers(5, n - 20, 2)
+            star[b, r0:r0 + rng.integers(4, 14), c0:c0 + rng.integers(4, 14)] = 0
+        star[b, n // 2 - 3:n // 2 + 4, n // 2 - 3:n // 2 + 4] = 1          # the centre stays visible
+    res = pm.batch.analyse_batch_starmask(torch.from_numpy(x).cuda(), 100.0, 5.0, torch.from_numpy(star).cuda(), 3, 15)
+    rows, segs = res.rows.cpu().numpy(), res.segmap.cpu().numpy()
+    for b in range(B):
+        d = x[b].astype(np.float64)
+        st = star[b].astype(np.float64)
+        seg = O.pixelmap(d, 105.0, 3, st)
+        assert np.array_equal(segs[b], seg.astype(np.uint8))
+        im = d - 100.0
+        rmax = O.calcRmax(im, seg)
+        ap = O.aperpixmap(n, rmax, 9, 0.1)
+        apix = O.minapix(im, seg, ap, st)
+        s180 = _single.rotated_mask(torch.from_numpy(st).cuda(), 180.0, apix[0], apix[1]).cpu().numpy()
+        s90 = _single.rotated_mask(torch.from_numpy(st).cuda(), 90.0, apix[0], apix[1]).cpu().numpy()
+        seg2 = seg * s180
+        A = O.calcA(im * s180, seg2.copy(), ap, apix, 180.0, None, True)
+        As = O.calcA(seg2, seg2, ap, apix, 180.0, None)[0]
+        As90 = O.calcA(seg2 * s90, seg2, ap, apix, 90.0, None)[0]
+        r20, r80 = O.calcR20_R80(im, seg2, apix, rmax)
+        want = dict(apix_col=apix[0], apix_row=apix[1], rmax=rmax, r20=r20, r80=r80, C=O.concentration(r20, r80), A=A[0], Abgr=A[1],
+                    S=O.smoothness(im, seg2, apix, rmax, r20, 100.0) if int(r20) >= 1 else -99.0, As=As,      # uniform_filter(size=0) raises upstream
+                    As90=As90, gini=O.gini(im, seg2), m20=O.m20(im, seg2),
+                    object_edge=float(O.checkPixelmapEdges(seg)), status=0.0)
+        errs = compare_row(P.rowd(rows, b), want, 1e-8, f"[{b}] ")
+        assert not errs, "\n".join(errs)
+    # all-ones masks give the plain path
+    plain = pm.batch.analyse_batch(torch.from_numpy(x).cuda(), 100.0, 5.0, 3, 15).rows.cpu().numpy()
+    ones = pm.batch.analyse_batch_starmask(torch.from_numpy(x).cuda(), 100.0, 5.0, torch.ones((B, n, n), dtype=torch.uint8).cuda(), 3, 15)
+    np.testing.assert_allclose(ones.rows.cpu().numpy(), plain, rtol=1e-9, equal_nan=True)
