@@ -36,6 +36,8 @@ extern "C" int pm_front_min_ctas(void);
 extern "C" int pm_tail_cta_min_ctas(void);
 extern "C" int pm_tail_cta_threads(void);
 extern "C" int pm_front_threads(void);
+extern "C" int pm_mono_threads(void);
+extern "C" int pm_mono_min_ctas(void);
 extern "C" int pm_minapix_threads(void);
 
 #ifndef PM_EMULATE
@@ -219,7 +221,7 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
     }
     unsigned smem = 0;
     int ctas = 1;
-    launch_shape(n, filter_size, &smem, &ctas);
+    launch_shape(n, filter_size, &smem, &ctas, pm_mono_min_ctas());
     if (smem < smem_fixed_bytes(n, filter_size) + 4096) { snprintf(g_err, sizeof g_err, "shared memory too small for n"); return PM_EINVAL; }
     long long grid_cap = (long long)g_sm_count * ctas;
     if (grid_cap > PM_MAX_GRID) grid_cap = PM_MAX_GRID;
@@ -243,7 +245,7 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
         p.b0 = 0; p.nb = B;
         const long long grid = grid_cap < B ? grid_cap : B;
         lrc = zero_counters();
-        PM_LAUNCH(pm_analyse, grid, kThreads, smem);
+        PM_LAUNCH(pm_analyse, grid, pm_mono_threads(), smem);
         return lrc;
     }
     // ---- the split path, chunk by chunk
@@ -295,7 +297,7 @@ int pm_analyse_batch(const void* images, int dtype, int64_t B, int n, const doub
         }
         // the monolith pass over whatever the front kernel handed over (normally nothing)
         p.smem_bytes = smem; p.scratch_per_cta = scratch_bytes_per_cta(n);
-        PM_LAUNCH(pm_big, grid, kThreads, smem);
+        PM_LAUNCH(pm_big, grid, pm_mono_threads(), smem);
     }
     return lrc;
 }
