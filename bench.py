@@ -446,6 +446,40 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     sky_ms = s0.elapsed_time(s1) / 3
     sky_iters = float(sky_rows[:, 4].mean().item())
+    # ---- the pre-processing rows of SURVEY.md §8(f) on the same resident cutouts (rank 0; CUDA events, 1 warm-up + 2 timed)
+    prep = None
+    if rank == 0 and not args.no_configs:
+        def timed(fn, reps=2):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps, out
+        P_ = min(B, 8192)
+        xp = x[:P_]
+        img_bytes = P_ * n * n * 4
+        clip_ms, clip = timed(lambda: pm.skyBackground.clipped_stats_batch(xp, 3.0, 5))
+        fit_ms, fit = timed(lambda: pm.skyBackground.gaussfit_batch(xp, stats=clip))
+        bgr_ms, bgr = timed(lambda: pm.skyBackground.skybgr_batch(xp))
+        star_ms, star = timed(lambda: pm.imageutils.maskstars_batch(xp, seed=1))
+        gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
+        prep = {"cutouts": P_, "n": n, "per_gpu": True,
+                "clipped_stats": {"value": P_ / (clip_ms * 1e-3), "unit": "cutouts/s", "kernel": "pm_clipstats_kernel<float>", "kernel_ms": clip_ms,
+                                  "algorithmic_gbs": gbs(img_bytes, clip_ms), "mean_iterations": float(clip[:, 4].mean().item())},
+                "gaussfit": {"value": P_ / (fit_ms * 1e-3), "unit": "cutouts/s", "kernel": "pm_gaussfit_kernel<float>", "kernel_ms": fit_ms,
+                             "algorithmic_gbs": gbs(img_bytes, fit_ms), "mean_iterations": float(fit[:, 8].mean().item()),
+                             "converged_fraction": float((fit[:, 9] == 0).double().mean().item())},
+                "skybgr": {"value": P_ / (bgr_ms * 1e-3), "unit": "cutouts/s", "ms": bgr_ms, "algorithmic_gbs": gbs(img_bytes, bgr_ms),
+                           "ok_fraction": float((np.asarray(bgr["status"]) == 0).mean()),
+                           "note": "whole skyBackground.skybgr flow: clipped statistics, Gaussian fit, source check, sky-region statistics"},
+                "maskstarsSEG": {"value": P_ / (star_ms * 1e-3), "unit": "cutouts/s", "ms": star_ms, "algorithmic_gbs": gbs(2 * img_bytes, star_ms),
+                                 "mean_segments": float(torch.as_tensor(star["info"])[:, 0].double().mean().item()),
+                                 "note": "two clipped-statistics launches + the smooth/threshold/label/replace kernel (reads and writes the cutout)"}}
+        del clip, fit, bgr, star
 
     if rank != 0:
         if world > 1:
@@ -567,6 +601,8 @@ def run_ours(args):
                           "cutouts": S_, "mean_clip_iterations": sky_iters, "per_gpu": True,
                           "note": "sky-region statistics of skyBackground._calcSkybgr with random fitted ellipses; L2/issue bound, see profiles/r1i_sky_ncu_summary.txt"},
             "gpu_launches": int(launches), "clocks": clocks}
+    if prep:
+        line["prep"] = prep
     if dist_info:
         line["distributed_check"] = dist_info
     if strong:

@@ -179,6 +179,11 @@ int pm_sky_stats_batch(const void *images, int dtype, int64_t B, int n, const do
 #define PM_CLIP_COLS 10
 int pm_clipped_stats_batch(const void *images, int dtype, int64_t B, int n, double sigma, int maxiters, double *out, void *cuda_stream);
 
+/* How pm_sky_stats_batch (with_mask = 1) / pm_clipped_stats_batch (with_mask = 0) run a cutout size: CTAs per thread-block
+ * cluster sharing one cutout (1, 2, 4 or 8), whether the cutout is held in the cluster's shared memory (read from HBM once) or
+ * left in global memory, and the dynamic shared memory per CTA.  Host-side query for tests and benchmarks. */
+int pm_stats_plan(int n, int dtype, int with_mask, int *cluster, int *resident, int *smem_bytes);
+
 /* skyBackground._gauss2dfit (skyBackground.py:306-331): the least-squares fit of gaussfitter.twodgaussian (gaussfitter.py:87-148)
  * to each cutout that scipy.optimize.curve_fit performs from the start values of gaussfitter.moments (:40-84) — here a
  * Levenberg-Marquardt iteration with the analytic Jacobian run to the optimum (curve_fit stops at ftol = xtol = 1.5e-8, so the

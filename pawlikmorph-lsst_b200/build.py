@@ -9,7 +9,7 @@ REPO = os.path.dirname(HERE)
 # PM_NVCC_DEFINES (e.g. "PM_FRONT_MIN_CTAS=3 PM_TAILCTA_MIN_CTAS=3"); the library is then libpawlik_b200_<name>.so
 VARIANT = os.environ.get("PM_LIB_VARIANT", "")
 SO = os.path.join(HERE, "libpawlik_b200.so" if not VARIANT else f"libpawlik_b200_{VARIANT}.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_tail.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_k_prep.cu", "pm_prep.cuh", "pm_launch.cuh", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh", "pm_sky.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("pm_capi.cu", "pm_tail.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_k_prep.cu", "pm_k_stats.cu", "pm_stats.cuh", "pm_prep.cuh", "pm_launch.cuh", "pm_kernels.cuh", "pm_block.cuh", "pm_platform.cuh", "pm_fits.cuh")] + \
     [os.path.join(REPO, "include", "pawlik_b200.h")]
 
 
@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         common.insert(1, "-D" + d)
     if verbose:
         common[1:1] = ["-Xptxas", "-v"]
-    units = ["pm_capi.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_tail.cu", "pm_k_prep.cu"]
+    units = ["pm_capi.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu", "pm_k_tailcta.cu", "pm_tail.cu", "pm_k_prep.cu", "pm_k_stats.cu"]
 
     def one(u):
         o = os.path.join(objdir, u.replace(".cu", ".o"))

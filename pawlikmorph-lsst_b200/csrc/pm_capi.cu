@@ -11,7 +11,6 @@
 
 #include "pm_kernels.cuh"
 #include "pm_fits.cuh"
-#include "pm_sky.cuh"
 
 using namespace pmk;
 
@@ -44,10 +43,6 @@ extern "C" int pm_minapix_threads(void);
 __global__ void __launch_bounds__(kThreads, 1)
 pm_aperpixmap_kernel(int n, const double* rad, long long B, int ns, double frac, uint8_t* mask_out, unsigned smem_bytes) {
     aperpixmap_body(n, rad, B, ns, frac, mask_out, smem_bytes);
-}
-template <typename T> __global__ void __launch_bounds__(kThreads, 3)
-pm_sky_stats_kernel(const T* images, long long B, int n, const double* ellipse, double* out) {
-    sky_body<T>(images, B, n, ellipse, out);
 }
 static thread_local int g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0, g_dev = -1;
 static thread_local size_t g_smem_optin = 0;
@@ -397,46 +392,6 @@ int pm_fits_decode_window_batch(const void* payload, int bitpix, double bzero, d
                 const size_t dst = ((size_t)b * npix + r) * npix + c;
                 if (out_dtype == PM_F32) ((float*)out)[dst] = (float)v; else ((double*)out)[dst] = v;
             }
-#endif
-    g_launches.fetch_add(1);
-    return PM_OK;
-}
-
-int pm_sky_stats_batch(const void* images, int dtype, int64_t B, int n, const double* ellipse, double* out, void* cuda_stream) {
-    g_err[0] = 0;
-    if (B == 0) return PM_OK;
-    if (!images || !ellipse || !out || B < 0 || n < 1 || n > PM_MAX_N || (dtype != PM_F32 && dtype != PM_F64)) {
-        snprintf(g_err, sizeof g_err, "bad argument");
-        return PM_EINVAL;
-    }
-    const unsigned smem = sky_smem_bytes(n);
-#ifndef PM_EMULATE
-    int rc = device_props();
-    if (rc != PM_OK) return rc;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    // persistent CTAs, one wave: 3 per SM is what the registers allow.  Measured at 256^2 (cutouts/s): 1 per SM 293k, 2 470k,
-    // 3 528k, 4 420k (a second, unbalanced wave), 8 516k.  Keeping the cutouts in flight inside the L2 (2 per SM) does not pay:
-    // the passes are bound by instruction issue (67 % of the issue slots, profiles/r1i_sky_ncu_summary.txt), not by DRAM.
-    long long per_sm = 3;
-    if (const char* env = getenv("PM_SKY_CTAS_PER_SM")) per_sm = atoll(env);      // tuning hook
-    per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
-    const long long grid = B < per_sm * g_sm_count ? B : per_sm * g_sm_count;
-    cudaError_t e = dtype == PM_F32
-        ? cudaFuncSetAttribute(pm_sky_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-        : cudaFuncSetAttribute(pm_sky_stats_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        if (dtype == PM_F32) pm_sky_stats_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, ellipse, out);
-        else pm_sky_stats_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, B, n, ellipse, out);
-        e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "pm_sky_stats_batch: %s", cudaGetErrorString(e)); return PM_ECUDA; }
-#else
-    (void)cuda_stream;
-    const long long grid = B < 4 ? B : 4;
-    for (long long blk = 0; blk < grid; blk++) {
-        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { sky_body<float>((const float*)images, B, n, ellipse, out); });
-        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { sky_body<double>((const double*)images, B, n, ellipse, out); });
-    }
 #endif
     g_launches.fetch_add(1);
     return PM_OK;

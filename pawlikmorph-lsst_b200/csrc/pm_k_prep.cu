@@ -1,4 +1,4 @@
-// pm_k_prep.cu — C ABI and launches of the pre-processing kernels (pm_prep.cuh): clipped statistics, the Gaussian fit of
+// pm_k_prep.cu — C ABI and launches of the pre-processing kernels (pm_prep.cuh): the Gaussian fit of
 // skyBackground._gauss2dfit, source detection + the cleaning of imageutils.maskstarsSEG.  One CTA per cutout.
 #include <stdio.h>
 #include <string.h>
@@ -12,10 +12,6 @@ extern "C" void pm_set_error(const char* msg);
 extern "C" void pm_count_launch(void);
 
 #ifndef PM_EMULATE
-template <typename T> __global__ void __launch_bounds__(kThreads, 3)
-pm_clipstats_kernel(const T* images, long long B, int n, double sigma, int maxiters, double* out) {
-    clipstats_body<T>(images, B, n, sigma, maxiters, out);
-}
 template <typename T> __global__ void __launch_bounds__(kThreads, 1)
 pm_gaussfit_kernel(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0, double* out) {
     gaussfit_body<T>(images, B, n, median, vmax, p0, out);
@@ -51,35 +47,6 @@ static bool bad_images(const void* images, int dtype, int64_t B, int n) {
 }
 
 extern "C" {
-
-int pm_clipped_stats_batch(const void* images, int dtype, int64_t B, int n, double sigma, int maxiters, double* out, void* cuda_stream) {
-    pm_set_error("");
-    if (B == 0) return PM_OK;
-    if (bad_images(images, dtype, B, n) || !out || !(sigma > 0.0)) { pm_set_error("bad argument"); return PM_EINVAL; }
-    const unsigned smem = sky_smem_bytes(n);
-    const int sm = sm_count();
-    if (sm <= 0) { pm_set_error("no CUDA device"); return PM_ENODEV; }
-    const long long grid = B < 3LL * sm ? B : 3LL * sm;
-#ifndef PM_EMULATE
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (dtype == PM_F32) {
-        cudaFuncSetAttribute(pm_clipstats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pm_clipstats_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, sigma, maxiters, out);
-    } else {
-        cudaFuncSetAttribute(pm_clipstats_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pm_clipstats_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, B, n, sigma, maxiters, out);
-    }
-    PREP_CHECK("pm_clipped_stats_batch");
-#else
-    (void)cuda_stream;
-    for (long long blk = 0; blk < grid; blk++) {
-        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { clipstats_body<float>((const float*)images, B, n, sigma, maxiters, out); });
-        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { clipstats_body<double>((const double*)images, B, n, sigma, maxiters, out); });
-    }
-#endif
-    pm_count_launch();
-    return PM_OK;
-}
 
 int pm_gaussfit_batch(const void* images, int dtype, int64_t B, int n, const double* median, const double* vmax, const double* p0,
                       double* out, void* cuda_stream) {

@@ -133,6 +133,25 @@ PM_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_sh
 PM_DEV unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 PM_DEV float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 PM_DEV double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+// thread-block clusters: the CTAs of one cluster read each other's shared memory (distributed shared memory)
+PM_DEV unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+PM_DEV unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+PM_DEV unsigned cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+PM_DEV unsigned cluster_count() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+// every thread of every CTA of the cluster; shared-memory writes made before it are visible cluster-wide after it
+PM_DEV void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location (32-bit shared address `a` of this CTA) in the CTA of rank `rank`
+PM_DEV unsigned dsmem_addr(unsigned a, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+// (volatile keeps them behind the cluster barrier, itself a volatile asm; no memory clobber: several may be in flight)
+PM_DEV unsigned dsmem_ld_u32(unsigned a) { unsigned v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+PM_DEV unsigned long long dsmem_ld_u64(unsigned a) { unsigned long long v; asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+PM_DEV double dsmem_ld_f64(unsigned a) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 }  // namespace pm_common
 #if defined(PM_GROUP_WARP)
 namespace pm_grp_warp {

@@ -1,7 +1,5 @@
 // pm_prep.cuh — the pre-processing around the morphology path, one CTA per cutout:
-//   * clipstats_body   astropy.stats.sigma_clipped_stats(image, sigma, maxiters) over a whole cutout, plus the plain
-//                      statistics and the maximum: imageutils.py:62, photutils.detect_threshold (skyBackground.py:109,
-//                      imageutils.py:67) and gaussfitter.moments' median / max (gaussfitter.py:71-72)
+//   (the clipped statistics that feed both — astropy.stats.sigma_clipped_stats — are pm_stats.cuh)
 //   * gaussfit_body    skyBackground._gauss2dfit (skyBackground.py:306-331): gaussfitter.moments start values and the
 //                      least-squares fit of gaussfitter.twodgaussian that scipy.optimize.curve_fit performs, as a
 //                      Levenberg-Marquardt iteration with the analytic Jacobian
@@ -10,59 +8,9 @@
 //                      imageutils.maskstarsSEG (:42-91) with a counter-based (Philox) normal generator in place of the
 //                      reference's unseeded np.random.normal
 #pragma once
-#include "pm_sky.cuh"
+#include "pm_kernels.cuh"
 
 namespace pmk {
-
-// ----------------------------------------------------------------------------------------------------
-// clipped statistics
-// ----------------------------------------------------------------------------------------------------
-constexpr int kClipCols = 10;   // count, mean, median, std (all pixels), iterations, clipped count, mean, median, std, max
-
-template <typename T>
-PM_DEV void clipstats_body(const T* images, long long B, int n, double sigma, int maxiters, double* out) {
-    unsigned char* smem = pm::dyn_smem(0);
-    Sh& sh = *(Sh*)smem;
-    SkyScratch& sc = *(SkyScratch*)(smem + align16((unsigned)sizeof(Sh)));
-    unsigned* mask = (unsigned*)(smem + align16((unsigned)sizeof(Sh)) + align16((unsigned)sizeof(SkyScratch)));
-    sh.par[pm::tid()] = 0;
-    const int nw = (n + 31) / 32;
-    for (int i = pm::tid(); i < n * nw; i += kThreads) {
-        const int w = i % nw;
-        mask[i] = (w == nw - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;     // every pixel belongs to the set
-    }
-    pm::sync();
-    const double inf = 1.7976931348623157e308 * 2.0;
-    for (long long b = pm::block(); b < B; b += pm::nblocks()) {
-        SkySet<T> s;
-        s.img = images + (size_t)b * n * n;
-        s.mask = mask;
-        s.n = n;
-        s.nw = nw;
-        s.set_bounds(-inf, inf);
-        SkyStats cur = sky_stats(sh, sc, s, (double)pm::ldg(s.img));
-        const SkyStats all = cur;
-        double vmax = -inf;
-        sky_for_each(s, [&](T x, decltype(sky_key(T()))) { vmax = fmax(vmax, (double)x); });
-        vmax = block_max(sh, vmax);
-        // astropy SigmaClip: bounds median -/+ sigma * std (inclusive) from the surviving values, until a round removes
-        // nothing or maxiters rounds are done (maxiters <= 0: until convergence)
-        double iters = 0.0, changed = 1.0;
-        while (changed != 0.0 && (maxiters <= 0 || iters < (double)maxiters) && cur.cnt > 0.0) {
-            iters += 1.0;
-            s.set_bounds(fmax(s.lo, cur.median - cur.std * sigma), fmin(s.hi, cur.median + cur.std * sigma));
-            const SkyStats nxt = sky_stats(sh, sc, s, cur.median);
-            changed = cur.cnt - nxt.cnt;
-            cur = nxt;
-        }
-        if (pm::tid() == 0) {
-            double* o = out + (size_t)b * kClipCols;
-            o[0] = all.cnt; o[1] = all.mean; o[2] = all.median; o[3] = all.std; o[4] = iters;
-            o[5] = cur.cnt; o[6] = cur.mean; o[7] = cur.median; o[8] = cur.std; o[9] = vmax;
-        }
-        pm::sync();
-    }
-}
 
 // ----------------------------------------------------------------------------------------------------
 // Gaussian fit
@@ -109,22 +57,59 @@ struct GaussShared {
     int flag;
 };
 
+// Far from the centre the Gaussian term is below 1e-10 of its amplitude (exp(-q/2), q > 46: farther than 6.8 times the
+// larger width), the residual is height - data and only the height column of the Jacobian is non-zero.  Those pixels
+// enter through three sums that do not depend on the parameters — their number, sum (d - m0) and sum (d - m0)^2 about a
+// fixed level m0 near the data (no cancellation) —, taken once per cutout; a pass then evaluates the model only inside
+// the bounding box of that ellipse and corrects the sums by the box's own.  (curve_fit stops at 1.5e-8: the neglected
+// terms are far below what decides its optimum.)
+struct GaussFar { double m0, s1, s2; };     // level, sum (d - m0), sum (d - m0)^2 over the WHOLE cutout
+constexpr double kGaussReach = 6.8;
+
+template <typename T> PM_DEV GaussFar gauss_far_sums(Sh& sh, const T* img, int n, double m0) {
+    double a[2] = {0.0, 0.0};
+    for (int i = pm::tid(); i < n * n; i += kThreads) {
+        const double d = (double)pm::ldg(img + i) - m0;
+        a[0] += d; a[1] += d * d;
+    }
+    block_sum<2>(sh, a);
+    GaussFar f;
+    f.m0 = m0; f.s1 = a[0]; f.s2 = a[1];
+    return f;
+}
+
 // one pass over the cutout at parameters q: cost = sum r^2, and (with_jac) J^T J, J^T r for r = model - data
 template <typename T>
-PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const double* q, bool with_jac, double* cost, double* jtj, double* jtr) {
+PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const GaussFar& far, const double* q, bool with_jac, double* cost, double* jtj, double* jtr) {
     const double h = q[0], A = q[1], xo = q[2], yo = q[3], sx = q[4], sy = q[5], th = q[6];
     const double c = cos(th), s = sin(th);
     const double isx = 1.0 / sx, isy = 1.0 / sy;
-    double acc[36];
+    // bounding box of the ellipse beyond which the Gaussian is dropped: rows about xo, columns about yo
+    int r0 = 0, r1 = n - 1, c0 = 0, c1 = n - 1;
+    {
+        const double reach = kGaussReach * fmax(fabs(sx), fabs(sy)) + 1.0;
+        if (reach == reach && xo == xo && yo == yo && reach < 4.0 * (double)n) {
+            const double a0 = floor(xo - reach), a1 = ceil(xo + reach), b0 = floor(yo - reach), b1 = ceil(yo + reach);
+            r0 = a0 > 0.0 ? (a0 < (double)n ? (int)a0 : n) : 0;
+            r1 = a1 < (double)(n - 1) ? (a1 >= 0.0 ? (int)a1 : -1) : n - 1;
+            c0 = b0 > 0.0 ? (b0 < (double)n ? (int)b0 : n) : 0;
+            c1 = b1 < (double)(n - 1) ? (b1 >= 0.0 ? (int)b1 : -1) : n - 1;
+        }
+    }
+    const int bw = c1 >= c0 ? c1 - c0 + 1 : 0, bh = r1 >= r0 ? r1 - r0 + 1 : 0;
+    double acc[38];
 #pragma unroll
-    for (int k = 0; k < 36; k++) acc[k] = 0.0;
-    for (int i = pm::tid(); i < n * n; i += kThreads) {
-        const int row = i / n, col = i - row * n;
+    for (int k = 0; k < 38; k++) acc[k] = 0.0;
+    for (int i = pm::tid(); i < bw * bh; i += kThreads) {
+        const int rr = i / bw, row = r0 + rr, col = c0 + (i - rr * bw);
         // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
         const double dx = yo - (double)col, dy = xo - (double)row;
         const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
         const double E = exp(-0.5 * (u * u + v * v));
-        const double r = h + A * E - (double)pm::ldg(img + i);
+        const double dat = (double)pm::ldg(img + (size_t)row * n + col);
+        const double r = h + A * E - dat;
+        const double dm = dat - far.m0;
+        acc[36] += dm; acc[37] += dm * dm;
         acc[35] += r * r;
         if (with_jac) {
             const double AE = A * E;
@@ -144,15 +129,25 @@ PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const double* q, bool with_j
             }
         }
     }
-    // 36 block sums, eight per barrier
-    for (int base = 0; base < 36; base += 8) {
+    // 38 block sums, eight per barrier
+    for (int base = 0; base < 40; base += 8) {
         if (!with_jac && base < 32) continue;
         double t[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) t[k] = base + k < 36 ? acc[base + k] : 0.0;
+        for (int k = 0; k < 8; k++) t[k] = base + k < 38 ? acc[base + k] : 0.0;
         block_sum<8>(sh, t);
 #pragma unroll
-        for (int k = 0; k < 8; k++) if (base + k < 36) acc[base + k] = t[k];
+        for (int k = 0; k < 8; k++) if (base + k < 38) acc[base + k] = t[k];
+    }
+    // the pixels outside the box: r = (h - m0) - (d - m0), J = (1, 0, ..., 0)
+    {
+        const double nf = (double)n * (double)n - (double)bw * (double)bh;
+        const double f1 = far.s1 - acc[36], f2 = far.s2 - acc[37], hm = h - far.m0;
+        if (nf > 0.0) {
+            acc[35] += nf * hm * hm - 2.0 * hm * f1 + f2;
+            acc[0] += nf;                    // J0 J0
+            acc[28] += nf * hm - f1;         // J0 r
+        }
     }
     *cost = acc[35];
     if (with_jac) {
@@ -189,12 +184,13 @@ PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* med
         }
         double cost = 0.0, jtj[28], jtr[7];
         int iter = 0;
+        const GaussFar far = gauss_far_sums(sh, img, n, p[0] == p[0] && fabs(p[0]) < 1.7e308 ? p[0] : 0.0);
         if (status == 0) {
             // Levenberg-Marquardt with MINPACK's trust-region logic (lmder: scaling by the running maximum of the column
             // norms, step bound delta, ratio of actual to predicted reduction steering delta and the damping parameter) —
             // curve_fit's algorithm with the analytic Jacobian, stopped at 1e-13 instead of 1.5e-8.  An undamped or merely
             // Marquardt-damped iteration walks off to needle-shaped Gaussians from the start values of gaussfitter.moments.
-            gauss_pass(sh, img, n, p, true, &cost, jtj, jtr);
+            gauss_pass(sh, img, n, far, p, true, &cost, jtj, jtr);
             status = 1;
             if (!(cost == cost) || !(cost < 1.7e308)) status = 2;
             double dg[7], xnorm = 0.0, par = 0.0;
@@ -229,7 +225,7 @@ PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* med
                 if (!solved) { status = 3; break; }
                 double q[7], cost_q, jtj_q[28], jtr_q[7];
                 for (int k = 0; k < 7; k++) q[k] = p[k] + d[k];
-                gauss_pass(sh, img, n, q, true, &cost_q, jtj_q, jtr_q);
+                gauss_pass(sh, img, n, far, q, true, &cost_q, jtj_q, jtr_q);
                 if (iter == 0) delta = fmin(delta, pnorm);
                 const bool finite_q = cost_q == cost_q && cost_q < 1.7e308;
                 const double actred = finite_q ? 1.0 - cost_q / cost : -1.0;

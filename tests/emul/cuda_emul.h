@@ -238,6 +238,16 @@ PM_DEV int nblocks() { return g_blk->nblocks; }
 PM_DEV int sync_or(int p) { return block_sync_or_(p); }
 PM_DEV void sync() { (void)block_sync_or_(0); }
 PM_DEV unsigned char* dyn_smem(unsigned) { return g_blk->smem; }
+// thread-block clusters: the emulator runs clusters of one CTA
+PM_DEV unsigned cluster_rank() { return 0u; }
+PM_DEV unsigned cluster_size() { return 1u; }
+PM_DEV unsigned cluster_id() { return (unsigned)g_blk->block_id; }
+PM_DEV unsigned cluster_count() { return (unsigned)g_blk->nblocks; }
+PM_DEV void cluster_sync() { (void)block_sync_or_(0); }
+PM_DEV unsigned dsmem_addr(unsigned a, unsigned) { return a; }
+PM_DEV unsigned dsmem_ld_u32(unsigned a) { return lds_u32(a); }
+PM_DEV unsigned long long dsmem_ld_u64(unsigned a) { unsigned long long v; memcpy(&v, g_blk->smem + a, 8); return v; }
+PM_DEV double dsmem_ld_f64(unsigned a) { return lds_f64(a); }
 }  // namespace pm_grp_cta
 namespace pm = pm_grp_cta;
 #endif

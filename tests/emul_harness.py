@@ -33,7 +33,7 @@ def build(force=False):
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DPM_EMULATE",
            "-I" + os.path.join(REPO, "tests", "emul"), "-I" + os.path.join(REPO, "include"),
            "-x", "c++"] + [os.path.join(PKG, "csrc", u) for u in ("pm_capi.cu", "pm_k_mono.cu", "pm_k_front.cu", "pm_k_minapix.cu",
-                                                                   "pm_k_tailcta.cu", "pm_tail.cu", "pm_k_prep.cu")] + [
+                                                                   "pm_k_tailcta.cu", "pm_tail.cu", "pm_k_prep.cu", "pm_k_stats.cu")] + [
            os.path.join(REPO, "tests", "emul", "cuda_emul.cpp"),
            "-o", SO]
     subprocess.run(cmd, check=True)
