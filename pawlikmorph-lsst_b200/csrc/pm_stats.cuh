@@ -42,12 +42,12 @@ struct StatScratch {
     unsigned pad;
 };
 
-// order-preserving keys; -0.0 is filed as +0.0 (numpy compares them equal)
-PM_DEV unsigned stat_key(float x) { x = x == 0.0f ? 0.0f : x; const unsigned u = pm::f2bits(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+// order-preserving keys.  -0.0 and +0.0 get adjacent keys (numpy compares them equal: a bound that is a zero is
+// widened to take in both, set_bounds; as a median either one is the same number)
+PM_DEV unsigned stat_key(float x) { const unsigned u = pm::f2bits(x); return u ^ ((unsigned)((int)u >> 31) | 0x80000000u); }
 PM_DEV unsigned long long stat_key(double x) {
-    x = x == 0.0 ? 0.0 : x;
     const unsigned long long u = (unsigned long long)pm::d2bits(x);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    return u ^ ((unsigned long long)((long long)u >> 63) | 0x8000000000000000ull);
 }
 PM_DEV double stat_val(unsigned k, float) { return (double)pm::bits2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 PM_DEV double stat_val(unsigned long long k, double) {
@@ -73,8 +73,10 @@ template <typename T> struct StatSet {      // pixels of this CTA's rows that be
         lo = lo_; hi = hi_;
         klo = stat_key((T)lo_);
         if (stat_val(klo, T()) < lo_) klo += (K)1;        // (T)lo rounded down: the next key up is the first one inside
+        if ((T)lo_ == (T)0 && lo_ <= 0.0) klo = stat_key(-(T)0);     // x >= 0 holds for -0.0 too
         khi = stat_key((T)hi_);
         if (stat_val(khi, T()) > hi_) khi -= (K)1;
+        if ((T)hi_ == (T)0 && hi_ >= 0.0) khi = stat_key((T)0);      // x <= 0 holds for +0.0 too
     }
 };
 
@@ -239,9 +241,13 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
     unsigned mine = 0;
     int rem = 0;
     bool first_hist = false;
+    const bool top = !bounded && sizeof(K) == 4;      // 32-bit keys: the first digit is the top 12 bits of any key
     if (bounded && s.klo <= s.khi) {
         rem = KB - stat_clz((K)(s.klo ^ s.khi));
         first_hist = rem > 0;
+    } else if (top) {
+        rem = KB;
+        first_hist = true;
     }
     if (first_hist) {
         const int bits = rem < kStatDigit ? rem : kStatDigit, shr = rem - bits;
@@ -249,11 +255,20 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
         for (int t = pm::tid(); t < kStatBins; t += kThreads) hist[t] = 0u;
         pm::sync();
         const unsigned bmask = (1u << bits) - 1u;
-        stat_for_each(s, [&](T x, K key) {
-            const double d = (double)x - shift;
-            mine++; a[1] += d; a[2] += d * d;
-            pm::atomic_add(&hist[(unsigned)(key >> shr) & bmask], 1u);
-        });
+        if (top) {
+            stat_for_each(s, [&](T x, K key) {
+                const double d = (double)x - shift;
+                mine++; a[1] += d; a[2] += d * d;
+                kmax = key > kmax ? key : kmax;
+                pm::atomic_add(&hist[(unsigned)(key >> shr) & bmask], 1u);
+            });
+        } else {
+            stat_for_each(s, [&](T x, K key) {
+                const double d = (double)x - shift;
+                mine++; a[1] += d; a[2] += d * d;
+                pm::atomic_add(&hist[(unsigned)(key >> shr) & bmask], 1u);
+            });
+        }
     } else {
         stat_for_each(s, [&](T x, K key) {
             const double d = (double)x - shift;
@@ -268,7 +283,8 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
         if (cl.size == 1) pm::sync();
     }
     double v[5] = {a[0], a[1], a[2], inf, -inf};
-    if (!first_hist) { v[3] = block_min(sh, mine ? stat_val(kmin, T()) : inf); v[4] = block_max(sh, mine ? stat_val(kmax, T()) : -inf); }
+    if (!first_hist) v[3] = block_min(sh, mine ? stat_val(kmin, T()) : inf);
+    if (!first_hist || top) v[4] = block_max(sh, mine ? stat_val(kmax, T()) : -inf);
     stat_exchange(sc, cl, v);
     st.cnt = v[0];
     st.vmax = v[4];
