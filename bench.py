@@ -466,6 +466,8 @@ def run_ours(args):
         fit_ms, fit = timed(lambda: pm.skyBackground.gaussfit_batch(xp, stats=clip))
         bgr_ms, bgr = timed(lambda: pm.skyBackground.skybgr_batch(xp))
         star_ms, star = timed(lambda: pm.imageutils.maskstars_batch(xp, seed=1))
+        flow_ms, flow = timed(lambda: pm.main._device_group(xp, None, None, None, FLAGS_ALL, 3, True, 1), reps=1)
+        flow_ok = float((flow[0][:, pm._abi.ROW_FIELDS.index("status")] == 0).mean())
         gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
         prep = {"cutouts": P_, "n": n, "per_gpu": True,
                 "clipped_stats": {"value": P_ / (clip_ms * 1e-3), "unit": "cutouts/s", "kernel": "pm_clipstats_kernel<float>", "kernel_ms": clip_ms,
@@ -479,7 +481,10 @@ def run_ours(args):
                 "maskstarsSEG": {"value": P_ / (star_ms * 1e-3), "unit": "cutouts/s", "ms": star_ms, "algorithmic_gbs": gbs(2 * img_bytes, star_ms),
                                  "mean_segments": float(torch.as_tensor(star["info"])[:, 0].double().mean().item()),
                                  "note": "two clipped-statistics launches + the smooth/threshold/label/replace kernel (reads and writes the cutout)"}}
-        del clip, fit, bgr, star
+        prep["reference_default_flow"] = {"value": P_ / (flow_ms * 1e-3), "unit": "galaxies/s", "ms": flow_ms, "ok_fraction": flow_ok,
+                                          "note": "main.py:349-495 as upstream runs it by default, on resident cutouts: skybgr, pixelmap with the sky in, "
+                                                  "img - sky, maskstarsSEG, the statistics on the cleaned image (rows read back to the host)"}
+        del clip, fit, bgr, star, flow
 
     if rank != 0:
         if world > 1:
@@ -599,7 +604,7 @@ def run_ours(args):
                                 "kernel_ms": dec_ms, "algorithmic_bytes_per_pixel": 6, "pixels": D * n * n, "traffic": dec_traffic},
             "sky_stats": {"value": S_ / (sky_ms * 1e-3), "unit": "cutouts/s", "kernel": "pm_sky_stats_kernel<float>", "kernel_ms": sky_ms,
                           "cutouts": S_, "mean_clip_iterations": sky_iters, "per_gpu": True,
-                          "note": "sky-region statistics of skyBackground._calcSkybgr with random fitted ellipses; L2/issue bound, see profiles/r1i_sky_ncu_summary.txt"},
+                          "note": "sky-region statistics of skyBackground._calcSkybgr with random fitted ellipses; instruction-issue bound, passes through L2, see profiles/r2u_sky_ncu_summary.txt"},
             "gpu_launches": int(launches), "clocks": clocks}
     if prep:
         line["prep"] = prep

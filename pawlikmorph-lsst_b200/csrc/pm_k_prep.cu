@@ -12,7 +12,10 @@ extern "C" void pm_set_error(const char* msg);
 extern "C" void pm_count_launch(void);
 
 #ifndef PM_EMULATE
-template <typename T> __global__ void __launch_bounds__(kThreads, 1)
+#ifndef PM_GAUSS_MIN_CTAS
+#define PM_GAUSS_MIN_CTAS 1
+#endif
+template <typename T> __global__ void __launch_bounds__(kThreads, PM_GAUSS_MIN_CTAS)
 pm_gaussfit_kernel(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0, double* out) {
     gaussfit_body<T>(images, B, n, median, vmax, p0, out);
 }
@@ -56,7 +59,9 @@ int pm_gaussfit_batch(const void* images, int dtype, int64_t B, int n, const dou
     const unsigned smem = align16((unsigned)sizeof(Sh));
     const int sm = sm_count();
     if (sm <= 0) { pm_set_error("no CUDA device"); return PM_ENODEV; }
-    const long long grid = B < 2LL * sm ? B : 2LL * sm;
+    // iteration counts differ a lot between cutouts: eight short static slices per resident CTA balance the SMs (the
+    // scheduler hands out the later CTAs as the earlier ones finish)
+    const long long grid = B < 8LL * PM_GAUSS_MIN_CTAS * sm ? B : 8LL * PM_GAUSS_MIN_CTAS * sm;
 #ifndef PM_EMULATE
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (dtype == PM_F32) pm_gaussfit_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, median, vmax, p0, out);
