@@ -11,10 +11,10 @@ extern "C" const char* pm_last_cuda_error(void);
 extern "C" void pm_set_error(const char* msg);
 extern "C" void pm_count_launch(void);
 
-#ifndef PM_EMULATE
 #ifndef PM_GAUSS_MIN_CTAS
 #define PM_GAUSS_MIN_CTAS 1
 #endif
+#ifndef PM_EMULATE
 template <typename T> __global__ void __launch_bounds__(kThreads, PM_GAUSS_MIN_CTAS)
 pm_gaussfit_kernel(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0, double* out) {
     gaussfit_body<T>(images, B, n, median, vmax, p0, out);

@@ -65,6 +65,10 @@ struct GaussShared {
 // terms are far below what decides its optimum.)
 struct GaussFar { double m0, s1, s2; };     // level, sum (d - m0), sum (d - m0)^2 over the WHOLE cutout
 constexpr double kGaussReach = 6.8;
+#ifndef PM_GAUSS_UNROLL
+#define PM_GAUSS_UNROLL 2
+#endif
+constexpr int kGaussUnroll = PM_GAUSS_UNROLL;      // pixel steps interleaved by the compiler (tuning hook)
 
 template <typename T> PM_DEV GaussFar gauss_far_sums(Sh& sh, const T* img, int n, double m0) {
     double a[2] = {0.0, 0.0};
@@ -100,13 +104,25 @@ PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const GaussFar& far, const d
     double acc[38];
 #pragma unroll
     for (int k = 0; k < 38; k++) acc[k] = 0.0;
-    for (int i = pm::tid(); i < bw * bh; i += kThreads) {
+    // the pixel values of the next two steps are requested before the current one is worked on: a step is ~100 FP64
+    // instructions, an L2 read several hundred cycles, and only 8 warps fit an SM at this register count
+    const int total = bw * bh;
+    auto fetch = [&](int i) -> T {
+        if (i >= total) return (T)0;
+        const int rr = i / bw;
+        return pm::ldg(img + (size_t)(r0 + rr) * n + (c0 + (i - rr * bw)));
+    };
+    T ahead1 = fetch(pm::tid()), ahead2 = fetch(pm::tid() + kThreads);
+#pragma unroll (kGaussUnroll)
+    for (int i = pm::tid(); i < total; i += kThreads) {
+        const double dat = (double)ahead1;
+        ahead1 = ahead2;
+        ahead2 = fetch(i + 2 * kThreads);
         const int rr = i / bw, row = r0 + rr, col = c0 + (i - rr * bw);
         // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
         const double dx = yo - (double)col, dy = xo - (double)row;
         const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
         const double E = exp(-0.5 * (u * u + v * v));
-        const double dat = (double)pm::ldg(img + (size_t)row * n + col);
         const double r = h + A * E - dat;
         const double dm = dat - far.m0;
         acc[36] += dm; acc[37] += dm * dm;
