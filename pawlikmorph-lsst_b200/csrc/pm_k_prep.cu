@@ -11,8 +11,10 @@ extern "C" const char* pm_last_cuda_error(void);
 extern "C" void pm_set_error(const char* msg);
 extern "C" void pm_count_launch(void);
 
+// Gaussian fit: 4 CTAs/SM (64 registers; the 7 x 7 algebra of warp 0 spills, the pixel loop does not).  Measured on 8 192 x 256^2:
+// 84 k / 98 k / 105 k / 108 k cutouts/s at 1 / 2 / 3 / 4 CTAs per SM (profiles/r2af_gauss_dmma.txt).
 #ifndef PM_GAUSS_MIN_CTAS
-#define PM_GAUSS_MIN_CTAS 1
+#define PM_GAUSS_MIN_CTAS 4
 #endif
 #ifndef PM_EMULATE
 template <typename T> __global__ void __launch_bounds__(kThreads, PM_GAUSS_MIN_CTAS)
@@ -56,7 +58,7 @@ int pm_gaussfit_batch(const void* images, int dtype, int64_t B, int n, const dou
     pm_set_error("");
     if (B == 0) return PM_OK;
     if (bad_images(images, dtype, B, n) || !out || (!p0 && (!median || !vmax))) { pm_set_error("bad argument"); return PM_EINVAL; }
-    const unsigned smem = align16((unsigned)sizeof(Sh));
+    const unsigned smem = align16((unsigned)sizeof(Sh)) + align16((unsigned)sizeof(GaussSmem));
     const int sm = sm_count();
     if (sm <= 0) { pm_set_error("no CUDA device"); return PM_ENODEV; }
     // iteration counts differ a lot between cutouts: eight short static slices per resident CTA balance the SMs (the

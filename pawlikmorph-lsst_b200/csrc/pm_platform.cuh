@@ -133,6 +133,11 @@ PM_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_sh
 PM_DEV unsigned lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 PM_DEV float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 PM_DEV double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+// FP64 tensor-core product of the warp, D (8 x 8) += A (8 x 4) B (4 x 8) (SASS DMMA.8x8x4).  Lane 4 g + t holds A[g][t] in
+// `a`, B[t][g] in `b`, and D[g][2 t], D[g][2 t + 1] in c0, c1.
+PM_DEV void dmma_8x8x4(double a, double b, double& c0, double& c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 // thread-block clusters: the CTAs of one cluster read each other's shared memory (distributed shared memory)
 PM_DEV unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 PM_DEV unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }

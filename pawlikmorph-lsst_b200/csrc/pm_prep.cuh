@@ -65,10 +65,6 @@ struct GaussShared {
 // terms are far below what decides its optimum.)
 struct GaussFar { double m0, s1, s2; };     // level, sum (d - m0), sum (d - m0)^2 over the WHOLE cutout
 constexpr double kGaussReach = 6.8;
-#ifndef PM_GAUSS_UNROLL
-#define PM_GAUSS_UNROLL 2
-#endif
-constexpr int kGaussUnroll = PM_GAUSS_UNROLL;      // pixel steps interleaved by the compiler (tuning hook)
 
 template <typename T> PM_DEV GaussFar gauss_far_sums(Sh& sh, const T* img, int n, double m0) {
     double a[2] = {0.0, 0.0};
@@ -82,9 +78,25 @@ template <typename T> PM_DEV GaussFar gauss_far_sums(Sh& sh, const T* img, int n
     return f;
 }
 
-// one pass over the cutout at parameters q: cost = sum r^2, and (with_jac) J^T J, J^T r for r = model - data
+// Shared memory of the fit behind Sh: per warp a staging tile of the 8 augmented Jacobian columns (J0..J6, r) of its 32
+// pixels, [8][kGaussTileStride] doubles (stride 36: the tensor-core fragment reads of a warp then take the minimum of two
+// wavefronts), the warps' 8 x 8 products, and their sum.
+constexpr int kGaussTileStride = 36;
+struct GaussSmem {
+    double tile[kWarps][8 * kGaussTileStride];
+    double prod[kWarps][64];
+    double total[64];
+    double trial[8];      // the next trial point, posted by warp 0
+    int go;
+};
+
+// One pass over the cutout at parameters q: cost = sum r^2, J^T J, J^T r for r = model - data.  With the residual as an
+// eighth column, all 36 sums are the upper triangle of ONE 8 x 8 product [J r]^T [J r] accumulated over the pixels — a
+// rank update, done on the FP64 tensor cores (DMMA.8x8x4: four pixels per instruction, the 8 x 8 accumulator spread
+// over the warp, two registers per lane instead of 36 accumulators each): a lane evaluates the model at its pixel,
+// the warp transposes the 32 x 8 values through the staging tile, eight DMMAs add their outer products.
 template <typename T>
-PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const GaussFar& far, const double* q, bool with_jac, double* cost, double* jtj, double* jtr) {
+PM_DEV void gauss_pass(Sh& sh, GaussSmem& gs, const T* img, int n, const GaussFar& far, const double* q, double* cost, double* jtj, double* jtr) {
     const double h = q[0], A = q[1], xo = q[2], yo = q[3], sx = q[4], sy = q[5], th = q[6];
     const double c = cos(th), s = sin(th);
     const double isx = 1.0 / sx, isy = 1.0 / sy;
@@ -101,35 +113,39 @@ PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const GaussFar& far, const d
         }
     }
     const int bw = c1 >= c0 ? c1 - c0 + 1 : 0, bh = r1 >= r0 ? r1 - r0 + 1 : 0;
-    double acc[38];
-#pragma unroll
-    for (int k = 0; k < 38; k++) acc[k] = 0.0;
-    // the pixel values of the next two steps are requested before the current one is worked on: a step is ~100 FP64
-    // instructions, an L2 read several hundred cycles, and only 8 warps fit an SM at this register count
     const int total = bw * bh;
-    auto fetch = [&](int i) -> T {
-        if (i >= total) return (T)0;
-        const int rr = i / bw;
-        return pm::ldg(img + (size_t)(r0 + rr) * n + (c0 + (i - rr * bw)));
-    };
-    T ahead1 = fetch(pm::tid()), ahead2 = fetch(pm::tid() + kThreads);
-#pragma unroll (kGaussUnroll)
-    for (int i = pm::tid(); i < total; i += kThreads) {
+    // the pixel values of the next two steps are requested before the current one is worked on (a step is ~70 FP64
+    // instructions, an L2 read several hundred cycles).  Box coordinates advance by the thread count per step without
+    // divisions: (row, col) += (kThreads / bw, kThreads % bw) with one carry.
+    const int bw1 = bw > 0 ? bw : 1;
+    const int step_r = kThreads / bw1, step_c = kThreads - step_r * bw1;
+    struct Pos { int r, c; };
+    auto advance = [&](Pos& p) { p.r += step_r; p.c += step_c; if (p.c >= bw1) { p.c -= bw1; p.r++; } };
+    auto fetch = [&](const Pos& p) -> T { return p.r < bh ? pm::ldg(img + (size_t)(r0 + p.r) * n + (c0 + p.c)) : (T)0; };
+    double* tile = gs.tile[pm::warp()];
+    const int lane = pm::lane(), g = lane >> 2, t = lane & 3;
+    double d0 = 0.0, d1 = 0.0, sm1 = 0.0, sm2 = 0.0;       // this lane's two entries of the 8 x 8 product; box sums of (d - m0)
+    Pos cur, nxt;
+    cur.r = pm::tid() / bw1; cur.c = pm::tid() - cur.r * bw1;
+    nxt = cur;
+    T ahead1 = fetch(nxt);
+    advance(nxt);
+    T ahead2 = fetch(nxt);
+    for (int i = pm::tid(); i - lane < total; i += kThreads) {          // (whole warps: the product is a warp operation)
         const double dat = (double)ahead1;
         ahead1 = ahead2;
-        ahead2 = fetch(i + 2 * kThreads);
-        const int rr = i / bw, row = r0 + rr, col = c0 + (i - rr * bw);
-        // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
-        const double dx = yo - (double)col, dy = xo - (double)row;
-        const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
-        const double E = exp(-0.5 * (u * u + v * v));
-        const double r = h + A * E - dat;
-        const double dm = dat - far.m0;
-        acc[36] += dm; acc[37] += dm * dm;
-        acc[35] += r * r;
-        if (with_jac) {
+        advance(nxt);
+        ahead2 = fetch(nxt);
+        double J[8];
+        if (i < total) {
+            const int row = r0 + cur.r, col = c0 + cur.c;
+            // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
+            const double dx = yo - (double)col, dy = xo - (double)row;
+            const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
+            const double E = exp(-0.5 * (u * u + v * v));
             const double AE = A * E;
-            double J[7];
+            const double dm = dat - far.m0;
+            sm1 += dm; sm2 += dm * dm;
             J[0] = 1.0;
             J[1] = E;
             J[2] = AE * (u * s * isx - v * c * isy);
@@ -137,28 +153,44 @@ PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const GaussFar& far, const d
             J[4] = AE * u * u * isx;
             J[5] = AE * v * v * isy;
             J[6] = AE * u * v * (sy * isx - sx * isy);
+            J[7] = h + AE - dat;
+        } else {
 #pragma unroll
-            for (int a = 0; a < 7; a++) {
-                acc[28 + a] += J[a] * r;
-#pragma unroll
-                for (int b2 = 0; b2 <= a; b2++) acc[a * (a + 1) / 2 + b2] += J[a] * J[b2];
-            }
+            for (int k = 0; k < 8; k++) J[k] = 0.0;
         }
-    }
-    // 38 block sums, eight per barrier
-    for (int base = 0; base < 40; base += 8) {
-        if (!with_jac && base < 32) continue;
-        double t[8];
+        advance(cur);
 #pragma unroll
-        for (int k = 0; k < 8; k++) t[k] = base + k < 38 ? acc[base + k] : 0.0;
-        block_sum<8>(sh, t);
+        for (int k = 0; k < 8; k++) tile[k * kGaussTileStride + lane] = J[k];
+        pm::syncwarp();
 #pragma unroll
-        for (int k = 0; k < 8; k++) if (base + k < 38) acc[base + k] = t[k];
+        for (int k = 0; k < 8; k++) {
+            const double a = tile[g * kGaussTileStride + 4 * k + t];      // column g of pixel 4 k + t: A[g][t] and B[t][g] alike
+            pm::dmma_8x8x4(a, a, d0, d1);
+        }
+        pm::syncwarp();
     }
+    // the warps' products, summed in warp order
+    gs.prod[pm::warp()][g * 8 + 2 * t] = d0;
+    gs.prod[pm::warp()][g * 8 + 2 * t + 1] = d1;
+    double bs[2] = {sm1, sm2};
+    block_sum<2>(sh, bs);                  // (its barrier also orders the products)
+    if (pm::tid() < 64) {
+        double v = 0.0;
+        for (int w = 0; w < kWarps; w++) v += gs.prod[w][pm::tid()];
+        gs.total[pm::tid()] = v;
+    }
+    pm::sync();
+    double acc[36];
+    for (int a = 0; a < 7; a++) {
+        acc[28 + a] = gs.total[a * 8 + 7];
+        for (int b2 = 0; b2 <= a; b2++) acc[a * (a + 1) / 2 + b2] = gs.total[a * 8 + b2];
+    }
+    acc[35] = gs.total[63];
+    pm::sync();                            // gs.total is rewritten by the next pass
     // the pixels outside the box: r = (h - m0) - (d - m0), J = (1, 0, ..., 0)
     {
         const double nf = (double)n * (double)n - (double)bw * (double)bh;
-        const double f1 = far.s1 - acc[36], f2 = far.s2 - acc[37], hm = h - far.m0;
+        const double f1 = far.s1 - bs[0], f2 = far.s2 - bs[1], hm = h - far.m0;
         if (nf > 0.0) {
             acc[35] += nf * hm * hm - 2.0 * hm * f1 + f2;
             acc[0] += nf;                    // J0 J0
@@ -166,16 +198,15 @@ PM_DEV void gauss_pass(Sh& sh, const T* img, int n, const GaussFar& far, const d
         }
     }
     *cost = acc[35];
-    if (with_jac) {
-        for (int k = 0; k < 28; k++) jtj[k] = acc[k];
-        for (int k = 0; k < 7; k++) jtr[k] = acc[28 + k];
-    }
+    for (int k = 0; k < 28; k++) jtj[k] = acc[k];
+    for (int k = 0; k < 7; k++) jtr[k] = acc[28 + k];
 }
 
 template <typename T>
 PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0_in, double* out) {
     unsigned char* smem = pm::dyn_smem(0);
     Sh& sh = *(Sh*)smem;
+    GaussSmem& gs = *(GaussSmem*)(smem + align16((unsigned)sizeof(Sh)));
     sh.par[pm::tid()] = 0;
     pm::sync();
     for (long long b = pm::block(); b < B; b += pm::nblocks()) {
@@ -204,73 +235,94 @@ PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* med
         if (status == 0) {
             // Levenberg-Marquardt with MINPACK's trust-region logic (lmder: scaling by the running maximum of the column
             // norms, step bound delta, ratio of actual to predicted reduction steering delta and the damping parameter) —
-            // curve_fit's algorithm with the analytic Jacobian, stopped at 1e-10 instead of 1.5e-8 (the iteration converges linearly on these noisy
-            // frames: 1e-10 leaves the widths within 2e-5 of the optimum, curve_fit's own stop within 2e-4; 1e-13 costs 20 % more steps).  An undamped or merely
-            // Marquardt-damped iteration walks off to needle-shaped Gaussians from the start values of gaussfitter.moments.
-            gauss_pass(sh, img, n, far, p, true, &cost, jtj, jtr);
+            // curve_fit's algorithm with the analytic Jacobian, stopped at 1e-10 instead of 1.5e-8 (the iteration converges
+            // linearly on these noisy frames: 1e-10 leaves the widths within 2e-5 of the optimum, curve_fit's own stop within
+            // 2e-4; 1e-13 costs 20 % more steps).  An undamped or merely Marquardt-damped iteration walks off to needle-shaped
+            // Gaussians from the start values of gaussfitter.moments.
+            // The passes over the pixels are the whole CTA's; the 7 x 7 algebra between them is warp 0's alone (the other
+            // warps wait at the barrier and leave the issue slots to the CTAs sharing the SM): it posts the next trial
+            // point, or the end, in gs.trial / gs.go.
+            const bool lead = pm::warp() == 0;
+            gauss_pass(sh, gs, img, n, far, p, &cost, jtj, jtr);
             status = 1;
             if (!(cost == cost) || !(cost < 1.7e308)) status = 2;
-            double dg[7], xnorm = 0.0, par = 0.0;
-            for (int k = 0; k < 7; k++) {
-                const double a = jtj[k * (k + 1) / 2 + k];
-                dg[k] = a > 0.0 ? sqrt(a) : 1.0;
-                xnorm += dg[k] * p[k] * dg[k] * p[k];
-            }
-            xnorm = sqrt(xnorm);
-            double delta = xnorm > 0.0 ? 100.0 * xnorm : 100.0;
+            double dg[7], d[7], xnorm = 0.0, par = 0.0, pnorm = 0.0, delta = 100.0;
             const double tol = 1e-10;
-            if (status == 1 && cost == 0.0) status = 0;
-            for (; status == 1 && iter < kGaussMaxIter; iter++) {
-                double maxratio = 0.0;
+            if (lead) {
                 for (int k = 0; k < 7; k++) {
                     const double a = jtj[k * (k + 1) / 2 + k];
-                    if (a > 0.0) dg[k] = fmax(dg[k], sqrt(a));
-                    maxratio = fmax(maxratio, a / (dg[k] * dg[k]));
+                    dg[k] = a > 0.0 ? sqrt(a) : 1.0;
+                    xnorm += dg[k] * p[k] * dg[k] * p[k];
                 }
-                double d[7], g[7], pnorm = 0.0;
-                for (int k = 0; k < 7; k++) g[k] = -jtr[k];
-                bool solved = false;
-                for (int inner = 0; inner < 80; inner++) {
-                    if (!lm_solve7(jtj, g, par, dg, d)) { par = fmax(par * 4.0, 1e-12 * fmax(maxratio, 1e-300)); continue; }
-                    pnorm = 0.0;
-                    for (int k = 0; k < 7; k++) pnorm += dg[k] * d[k] * dg[k] * d[k];
-                    pnorm = sqrt(pnorm);
-                    solved = true;
-                    if (pnorm <= 1.1 * delta) break;
-                    par = fmax(par * 4.0, 1e-8 * fmax(maxratio, 1e-300));
+                xnorm = sqrt(xnorm);
+                delta = xnorm > 0.0 ? 100.0 * xnorm : 100.0;
+                if (status == 1 && cost == 0.0) status = 0;
+            }
+            for (;;) {
+                if (lead) {
+                    bool go = status == 1 && iter < kGaussMaxIter;
+                    if (go) {
+                        double maxratio = 0.0;
+                        for (int k = 0; k < 7; k++) {
+                            const double a = jtj[k * (k + 1) / 2 + k];
+                            if (a > 0.0) dg[k] = fmax(dg[k], sqrt(a));
+                            maxratio = fmax(maxratio, a / (dg[k] * dg[k]));
+                        }
+                        double g[7];
+                        for (int k = 0; k < 7; k++) g[k] = -jtr[k];
+                        bool solved = false;
+                        for (int inner = 0; inner < 80; inner++) {
+                            if (!lm_solve7(jtj, g, par, dg, d)) { par = fmax(par * 4.0, 1e-12 * fmax(maxratio, 1e-300)); continue; }
+                            pnorm = 0.0;
+                            for (int k = 0; k < 7; k++) pnorm += dg[k] * d[k] * dg[k] * d[k];
+                            pnorm = sqrt(pnorm);
+                            solved = true;
+                            if (pnorm <= 1.1 * delta) break;
+                            par = fmax(par * 4.0, 1e-8 * fmax(maxratio, 1e-300));
+                        }
+                        if (!solved) { status = 3; go = false; }
+                    }
+                    if (pm::lane() == 0) {
+                        gs.go = go ? 1 : 0;
+                        for (int k = 0; k < 7; k++) gs.trial[k] = p[k] + d[k];
+                    }
                 }
-                if (!solved) { status = 3; break; }
+                pm::sync();
+                if (!gs.go) break;
                 double q[7], cost_q, jtj_q[28], jtr_q[7];
-                for (int k = 0; k < 7; k++) q[k] = p[k] + d[k];
-                gauss_pass(sh, img, n, far, q, true, &cost_q, jtj_q, jtr_q);
-                if (iter == 0) delta = fmin(delta, pnorm);
-                const bool finite_q = cost_q == cost_q && cost_q < 1.7e308;
-                const double actred = finite_q ? 1.0 - cost_q / cost : -1.0;
-                double jd2 = 0.0;                             // |J d|^2 = d^T (J^T J) d
-                for (int a = 0; a < 7; a++)
-                    for (int b2 = 0; b2 < 7; b2++) jd2 += d[a] * d[b2] * jtj[a >= b2 ? a * (a + 1) / 2 + b2 : b2 * (b2 + 1) / 2 + a];
-                const double t1 = jd2 / cost, t2 = par * pnorm * pnorm / cost;
-                const double prered = t1 + 2.0 * t2, dirder = -(t1 + t2);
-                const double ratio = prered != 0.0 ? actred / prered : 0.0;
-                if (ratio <= 0.25) {
-                    double temp = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
-                    if (!finite_q || 0.1 * cost_q >= cost || temp < 0.1) temp = 0.1;
-                    delta = temp * fmin(delta, pnorm / 0.1);
-                    par /= temp;
-                } else if (par == 0.0 || ratio >= 0.75) {
-                    delta = pnorm / 0.5;
-                    par *= 0.5;
+                for (int k = 0; k < 7; k++) q[k] = gs.trial[k];
+                gauss_pass(sh, gs, img, n, far, q, &cost_q, jtj_q, jtr_q);
+                if (lead) {
+                    if (iter == 0) delta = fmin(delta, pnorm);
+                    const bool finite_q = cost_q == cost_q && cost_q < 1.7e308;
+                    const double actred = finite_q ? 1.0 - cost_q / cost : -1.0;
+                    double jd2 = 0.0;                             // |J d|^2 = d^T (J^T J) d
+                    for (int a = 0; a < 7; a++)
+                        for (int b2 = 0; b2 < 7; b2++) jd2 += d[a] * d[b2] * jtj[a >= b2 ? a * (a + 1) / 2 + b2 : b2 * (b2 + 1) / 2 + a];
+                    const double t1 = jd2 / cost, t2 = par * pnorm * pnorm / cost;
+                    const double prered = t1 + 2.0 * t2, dirder = -(t1 + t2);
+                    const double ratio = prered != 0.0 ? actred / prered : 0.0;
+                    if (ratio <= 0.25) {
+                        double temp = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+                        if (!finite_q || 0.1 * cost_q >= cost || temp < 0.1) temp = 0.1;
+                        delta = temp * fmin(delta, pnorm / 0.1);
+                        par /= temp;
+                    } else if (par == 0.0 || ratio >= 0.75) {
+                        delta = pnorm / 0.5;
+                        par *= 0.5;
+                    }
+                    if (ratio >= 1e-4) {
+                        for (int k = 0; k < 7; k++) p[k] = q[k];
+                        cost = cost_q;
+                        for (int k = 0; k < 28; k++) jtj[k] = jtj_q[k];
+                        for (int k = 0; k < 7; k++) jtr[k] = jtr_q[k];
+                        xnorm = 0.0;
+                        for (int k = 0; k < 7; k++) xnorm += dg[k] * p[k] * dg[k] * p[k];
+                        xnorm = sqrt(xnorm);
+                    }
+                    if ((fabs(actred) <= tol && prered <= tol && 0.5 * ratio <= 1.0) || delta <= tol * xnorm || cost == 0.0) status = 0;
+                    iter++;
                 }
-                if (ratio >= 1e-4) {
-                    for (int k = 0; k < 7; k++) p[k] = q[k];
-                    cost = cost_q;
-                    for (int k = 0; k < 28; k++) jtj[k] = jtj_q[k];
-                    for (int k = 0; k < 7; k++) jtr[k] = jtr_q[k];
-                    xnorm = 0.0;
-                    for (int k = 0; k < 7; k++) xnorm += dg[k] * p[k] * dg[k] * p[k];
-                    xnorm = sqrt(xnorm);
-                }
-                if ((fabs(actred) <= tol && prered <= tol && 0.5 * ratio <= 1.0) || delta <= tol * xnorm || cost == 0.0) status = 0;
             }
         }
         if (pm::tid() == 0) {

@@ -115,6 +115,19 @@ template <typename T> PM_DEV T shfl_xor(T v, int m) { uint64_t o[32]; warp_excha
 template <typename T> PM_DEV T shfl_up(T v, int d) { uint64_t o[32]; warp_exchange_(to_bits_(v), o); int s = lane() - d; return s < 0 ? v : from_bits_<T>(o[s]); }
 template <typename T> PM_DEV T shfl_down(T v, int d) { uint64_t o[32]; warp_exchange_(to_bits_(v), o); int s = lane() + d; return s > 31 ? v : from_bits_<T>(o[s]); }
 
+// D (8 x 8) += A (8 x 4) B (4 x 8) of the warp, fragments as mma.sync.m8n8k4.f64 lays them out (pm_platform.cuh)
+PM_DEV void dmma_8x8x4(double a, double b, double& c0, double& c1) {
+    uint64_t oa[32], ob[32];
+    warp_exchange_(to_bits_(a), oa);
+    warp_exchange_(to_bits_(b), ob);
+    const int g = lane() >> 2, t = lane() & 3;
+    for (int k = 0; k < 4; k++) {
+        const double A = from_bits_<double>(oa[4 * g + k]);
+        c0 += A * from_bits_<double>(ob[(2 * t) * 4 + k]);
+        c1 += A * from_bits_<double>(ob[(2 * t + 1) * 4 + k]);
+    }
+}
+
 // warp reductions: one rendez-vous, then the same xor-butterfly order the GPU code uses
 template <typename T, typename F> PM_DEV T warp_tree_(T v, F f) {
     uint64_t o[32]; warp_exchange_(to_bits_(v), o);
