@@ -32,6 +32,7 @@ constexpr int kStatBins = 1 << kStatDigit;
 constexpr int kStatRun = kStatBins / kThreads;     // histogram bins a thread owns when the rank is located
 static_assert(kStatBins % kThreads == 0 && kStatRun >= 1, "bins per thread");
 constexpr unsigned kNoBin = 0xffffffffu;
+constexpr int kStatCollect = 512;      // a prefix holding at most this many keys is finished by gathering them (one pass)
 
 struct StatScratch {
     unsigned hist[2][kStatBins];      // alternating: the other CTAs may still read the previous pass's counters
@@ -39,7 +40,9 @@ struct StatScratch {
     double xd[2][8];                  // cluster exchange slots, alternating per exchange
     double xall[40];                  // the slots of all CTAs, gathered
     unsigned bin, left, val;          // result of locating a rank (written by the owner of the bin)
-    unsigned pad;
+    unsigned nlist;
+    unsigned long long found[2];
+    unsigned long long list[kStatCollect];   // the keys under a sparsely populated prefix, gathered for a direct selection
 };
 
 // order-preserving keys.  -0.0 and +0.0 get adjacent keys (numpy compares them equal: a bound that is a zero is
@@ -193,7 +196,7 @@ PM_DEV void stat_locate64(Sh& sh, StatScratch& sc, unsigned val, unsigned kk) {
 // The bin holding rank kk of the cluster's histogram h and the rank inside it; with want_next also the bin of rank
 // kk + 1 (kNoBin when the histogram ends first).  Call after the barrier that ends the pass.  The results are the
 // same in every thread of every CTA.
-struct StatLoc { unsigned bin, left, next; };
+struct StatLoc { unsigned bin, left, next, count; };
 PM_DEV StatLoc stat_locate(Sh& sh, StatScratch& sc, const StatCl& cl, unsigned h, unsigned kk, bool want_next) {
     StatLoc L;
     const unsigned cbase = pm::smem_addr(sc.coarse[h]), hbase = pm::smem_addr(sc.hist[h]);
@@ -205,7 +208,7 @@ PM_DEV StatLoc stat_locate(Sh& sh, StatScratch& sc, const StatCl& cl, unsigned h
     const unsigned fval = t < 64 ? (cl.size > 1 ? stat_cluster_word(cl, hbase, cbin * kStatFine + t) : sc.hist[h][cbin * kStatFine + t]) : 0u;
     stat_locate64(sh, sc, fval, cleft);
     const unsigned fbin = sc.bin, fval_at = sc.val;
-    L.bin = cbin * kStatFine + fbin; L.left = sc.left; L.next = kNoBin;
+    L.bin = cbin * kStatFine + fbin; L.left = sc.left; L.next = kNoBin; L.count = fval_at;
     pm::sync();
     if (want_next) {
         if (L.left + 1u < fval_at) L.next = L.bin;
@@ -241,7 +244,7 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
     unsigned mine = 0;
     int rem = 0;
     bool first_hist = false;
-    const bool top = !bounded && sizeof(K) == 4;      // 32-bit keys: the first digit is the top 12 bits of any key
+    const bool top = !bounded;      // the first digit of the first set: the top 12 bits of any key
     if (bounded && s.klo <= s.khi) {
         rem = KB - stat_clz((K)(s.klo ^ s.khi));
         first_hist = rem > 0;
@@ -344,6 +347,37 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
         }
         prefix = (prefix << bits) | bin;
         rem = shr;
+        if (rem > 0 && loc.count <= (unsigned)kStatCollect && cl.size == 1) {
+            // few keys are left under the prefix (64-bit keys of sparse data: after two or three digits): gather them and
+            // rank them against each other instead of resolving the remaining digits pass by pass
+            if (pm::tid() == 0) sc.nlist = 0u;
+            pm::sync();
+            StatSet<T> sub = s;
+            const K plo = (K)(prefix << rem), phi = (K)(plo | (K)((((K)1) << rem) - (K)1));
+            sub.klo = s.klo > plo ? s.klo : plo;
+            sub.khi = s.khi < phi ? s.khi : phi;
+            stat_for_each(sub, [&](T, K key) { sc.list[pm::atomic_add(&sc.nlist, 1u)] = (unsigned long long)key; });
+            pm::sync();
+            const unsigned m = sc.nlist;                       // == loc.count
+            for (unsigned i = (unsigned)pm::tid(); i < m; i += (unsigned)kThreads) {
+                const unsigned long long mine_k = sc.list[i];
+                unsigned rank = 0;
+                for (unsigned j = 0; j < m; j++) {
+                    const unsigned long long o = sc.list[j];
+                    rank += (o < mine_k || (o == mine_k && j < i)) ? 1u : 0u;
+                }
+                if (rank == k) sc.found[0] = mine_k;
+                if (rank == k + 1u) sc.found[1] = mine_k;
+            }
+            pm::sync();
+            k1 = (K)sc.found[0];
+            if (even) {
+                if (k + 1u < m) upper = (K)sc.found[1];
+                else upper_known = false;
+            } else upper = k1;
+            pm::sync();
+            rem = 0;
+        }
     }
     double med = stat_val(k1, T());
     double up = stat_val(upper, T());
