@@ -13,8 +13,8 @@ Differences from upstream, all on purpose:
   * `-lif` takes a number (upstream declares it store_true, which makes `-li` unusable: imganalysis.py:24, main.py:325);
   * `--seed` seeds the cleaning noise of maskstarsSEG (unseeded upstream), `--no-clean` skips that step, `-S` adds the
     smoothness statistic (main.py:494 leaves the call commented out), `--device` picks the GPU;
-  * `-par` / `-n` are accepted and ignored (the batch is the parallelism); `-spm`, `-sci`, `-sersic`, `-cc`, `-segmap`,
-    `-starmask`, `-d` and `-src LSST` belong to parts of the reference this build does not cover and raise NotImplementedError.
+  * `-par` / `-n` are accepted and ignored (the batch is the parallelism); `-sersic` fits the Sersic profile on the device
+    (sersic.py); `-spm`, `-sci`, `-cc`, `-segmap`, `-starmask`, `-d` and `-src LSST` belong to parts of the reference this build does not cover and raise NotImplementedError.
 """
 import sys
 from argparse import ArgumentParser
@@ -25,7 +25,7 @@ def build_parser():
     parser.add_argument("-A", action="store_true", help="Calculate asymmetry parameter")
     parser.add_argument("-As", action="store_true", help="Calculate shape asymmetry parameter")
     parser.add_argument("-Aall", action="store_true", help="Calculate all asymmetries parameters")
-    parser.add_argument("-sersic", "--sersic", action="store_true", help="Calculate sersic profile (not covered).")
+    parser.add_argument("-sersic", "--sersic", action="store_true", help="Calculate sersic profile")
     parser.add_argument("-spm", "--savesegmap", action="store_true", help="Save calculated binary pixelmaps (not covered).")
     parser.add_argument("-sci", "--savecleanimg", action="store_true", help="Save cleaned image (not covered).")
     parser.add_argument("-li", "--largeimage", action="store_true", help="Use large cutout for sky background estimation.")

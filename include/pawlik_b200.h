@@ -196,6 +196,19 @@ int pm_stats_plan(int n, int dtype, int with_mask, int *cluster, int *resident, 
 int pm_gaussfit_batch(const void *images, int dtype, int64_t B, int n, const double *median, const double *vmax, const double *p0,
                       double *out, void *cuda_stream);
 
+/* sersic.fitSersic (sersic.py:53-136), the two pieces that touch pixels.
+ * pm_ellipse_sum_batch: photutils EllipticalAperture((xc, yc), a, b, theta).do_photometry(image, method="exact")[0][0]
+ * (sersic.py:46-47, :101-121) — the sum of image x (exact area of ellipse ∩ pixel; pixel (row r, column c) is the unit square
+ * about (x, y) = (c, r)).  M entries; ell: DEVICE double [M, 5] = xc, yc, a, b, theta; idx: DEVICE int64 [M] cutout of each entry
+ * (NULL: entry i is cutout i) so that the root search of sersic.py:103-116 can probe the same cutouts again; out: DEVICE double [M].
+ * pm_sersicfit_batch: the least-squares fit of astropy's Sersic2D (amplitude, r_eff, n, x_0, y_0, ellip, theta; x = column) that
+ * LevMarLSQFitter performs at sersic.py:134 (scipy leastsq, stopped at 1e-8) — here the same trust-region iteration with the analytic
+ * Jacobian run to 1e-10.  p0: DEVICE double [B, 7] start values (sersic.py:98-129); out: DEVICE double [B, PM_GAUSS_COLS] = the 7
+ * parameters, cost, iterations, status (as pm_gaussfit_batch). */
+int pm_ellipse_sum_batch(const void *images, int dtype, int n, int64_t M, const int64_t *idx, const double *ell, double *out,
+                         void *cuda_stream);
+int pm_sersicfit_batch(const void *images, int dtype, int64_t B, int n, const double *p0, double *out, void *cuda_stream);
+
 /* photutils.detect_sources(image, threshold, npixels, kernel = 3 x 3 Gaussian of FWHM 3) as skyBackground.py:104-110 and
  * imageutils.py:66-71 call it — smooth, `> threshold[b]`, 8-connected labels, segments of fewer than npixels pixels dropped —
  * and, when clean_out is given, the cleaning of imageutils.maskstarsSEG (imageutils.py:73-89): every kept segment whose bounding

@@ -43,10 +43,11 @@ class Outputs(C.Structure):
 
 EXPORTS = ("pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
            "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch",
-           "pm_fits_decode_window_batch", "pm_sky_stats_batch", "pm_clipped_stats_batch", "pm_stats_plan", "pm_gaussfit_batch",
+           "pm_fits_decode_window_batch", "pm_sky_stats_batch", "pm_clipped_stats_batch", "pm_stats_plan", "pm_gaussfit_batch", "pm_ellipse_sum_batch", "pm_sersicfit_batch",
            "pm_maskstars_workspace_bytes", "pm_maskstars_batch")
 PM_CLIP_COLS, PM_GAUSS_COLS, PM_STAR_COLS = 10, 10, 4
 CLIP_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_count", "clipped_mean", "clipped_median", "clipped_std", "max")
+SERSIC_FIELDS = ("amplitude", "r_eff", "n", "x_0", "y_0", "ellip", "theta", "cost", "iterations", "status")
 GAUSS_FIELDS = ("height", "amplitude", "xo", "yo", "sigma_x", "sigma_y", "theta", "cost", "iterations", "status")
 PM_SKY_COLS = 12
 SKY_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_count", "clipped_mean", "clipped_median", "clipped_std",
@@ -80,6 +81,10 @@ def declare(lib):
                                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.pm_clipped_stats_batch.restype = C.c_int
     lib.pm_clipped_stats_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    lib.pm_ellipse_sum_batch.restype = C.c_int
+    lib.pm_ellipse_sum_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pm_sersicfit_batch.restype = C.c_int
+    lib.pm_sersicfit_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_stats_plan.restype = C.c_int
     lib.pm_stats_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pm_gaussfit_batch.restype = C.c_int

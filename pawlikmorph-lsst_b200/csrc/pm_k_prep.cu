@@ -21,6 +21,14 @@ template <typename T> __global__ void __launch_bounds__(kThreads, PM_GAUSS_MIN_C
 pm_gaussfit_kernel(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0, double* out) {
     gaussfit_body<T>(images, B, n, median, vmax, p0, out);
 }
+template <typename T> __global__ void __launch_bounds__(kThreads, PM_GAUSS_MIN_CTAS)
+pm_sersicfit_kernel(const T* images, long long B, int n, const double* p0, double* out) {
+    sersicfit_body<T>(images, B, n, p0, out);
+}
+template <typename T> __global__ void __launch_bounds__(kThreads, 4)
+pm_ellipse_sum_kernel(const T* images, int n, long long M, const long long* idx, const double* ell, double* out) {
+    ellipse_sum_body<T>(images, n, M, idx, ell, out);
+}
 template <typename T> __global__ void __launch_bounds__(kThreads, 2)
 pm_maskstars_kernel(const T* images, long long B, int n, const double* threshold, int npixels, const double* mean, const double* std_,
                     unsigned long long seed, int* labels_out, T* clean_out, double* out, unsigned char* scratch,
@@ -125,5 +133,55 @@ int pm_maskstars_batch(const void* images, int dtype, int64_t B, int n, const do
     pm_count_launch();
     return PM_OK;
 }
+
+int pm_sersicfit_batch(const void* images, int dtype, int64_t B, int n, const double* p0, double* out, void* cuda_stream) {
+    pm_set_error("");
+    if (B == 0) return PM_OK;
+    if (bad_images(images, dtype, B, n) || !out || !p0) { pm_set_error("bad argument"); return PM_EINVAL; }
+    const unsigned smem = align16((unsigned)sizeof(Sh)) + align16((unsigned)sizeof(GaussSmem));
+    const int sm = sm_count();
+    if (sm <= 0) { pm_set_error("no CUDA device"); return PM_ENODEV; }
+    const long long grid = B < 8LL * PM_GAUSS_MIN_CTAS * sm ? B : 8LL * PM_GAUSS_MIN_CTAS * sm;
+#ifndef PM_EMULATE
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (dtype == PM_F32) pm_sersicfit_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, B, n, p0, out);
+    else pm_sersicfit_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, B, n, p0, out);
+    PREP_CHECK("pm_sersicfit_batch");
+#else
+    (void)cuda_stream;
+    for (long long blk = 0; blk < grid; blk++) {
+        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { sersicfit_body<float>((const float*)images, B, n, p0, out); });
+        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { sersicfit_body<double>((const double*)images, B, n, p0, out); });
+    }
+#endif
+    pm_count_launch();
+    return PM_OK;
+}
+
+int pm_ellipse_sum_batch(const void* images, int dtype, int n, int64_t M, const int64_t* idx, const double* ell, double* out,
+                         void* cuda_stream) {
+    pm_set_error("");
+    if (M == 0) return PM_OK;
+    if (bad_images(images, dtype, M, n) || !ell || !out) { pm_set_error("bad argument"); return PM_EINVAL; }
+    const unsigned smem = align16((unsigned)sizeof(Sh));
+    const int sm = sm_count();
+    if (sm <= 0) { pm_set_error("no CUDA device"); return PM_ENODEV; }
+    const long long grid = M < 8LL * sm ? M : 8LL * sm;
+#ifndef PM_EMULATE
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (dtype == PM_F32) pm_ellipse_sum_kernel<float><<<(unsigned)grid, kThreads, smem, st>>>((const float*)images, n, M, (const long long*)idx, ell, out);
+    else pm_ellipse_sum_kernel<double><<<(unsigned)grid, kThreads, smem, st>>>((const double*)images, n, M, (const long long*)idx, ell, out);
+    PREP_CHECK("pm_ellipse_sum_batch");
+#else
+    (void)cuda_stream;
+    for (long long blk = 0; blk < grid; blk++) {
+        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { ellipse_sum_body<float>((const float*)images, n, M, (const long long*)idx, ell, out); });
+        else pm_emul::run_block((int)blk, (int)grid, kThreads, smem, [&]() { ellipse_sum_body<double>((const double*)images, n, M, (const long long*)idx, ell, out); });
+    }
+#endif
+    pm_count_launch();
+    return PM_OK;
+}
+
 
 }  // extern "C"

@@ -13,11 +13,11 @@
 namespace pmk {
 
 // ----------------------------------------------------------------------------------------------------
-// Gaussian fit
+// Least-squares fits of 7-parameter surface models: the Gaussian of skybgr, the Sersic profile of fitSersic
 // ----------------------------------------------------------------------------------------------------
-// out: height, amplitude, xo, yo, sigma_x, sigma_y, theta (the raw optimum, before the np.abs of skyBackground.py:331),
-//      final cost (sum of squared residuals), iterations, status (0 converged, 1 iteration limit — curve_fit's
-//      RuntimeError —, 2 NaN in the start values — gaussfitter.py:76-77 —, 3 singular normal equations)
+// out: the 7 parameters (the raw optimum), final cost (sum of squared residuals), iterations, status (0 converged,
+//      1 iteration limit — curve_fit's RuntimeError —, 2 NaN in the start values / first residuals — gaussfitter.py:76-77 —,
+//      3 singular normal equations)
 constexpr int kGaussCols = 10;
 constexpr int kGaussMaxIter = 200;
 
@@ -51,42 +51,15 @@ PM_DEV bool lm_solve7(const double* A /* packed lower triangle, 28 */, const dou
     return true;
 }
 
-struct GaussShared {
-    double p[7], trial[7], jtj[28], jtr[7];
-    double cost;
-    int flag;
-};
-
-// Far from the centre the Gaussian term is below 1e-10 of its amplitude (exp(-q/2), q > 46: farther than 6.8 times the
-// larger width), the residual is height - data and only the height column of the Jacobian is non-zero.  Those pixels
-// enter through three sums that do not depend on the parameters — their number, sum (d - m0) and sum (d - m0)^2 about a
-// fixed level m0 near the data (no cancellation) —, taken once per cutout; a pass then evaluates the model only inside
-// the bounding box of that ellipse and corrects the sums by the box's own.  (curve_fit stops at 1.5e-8: the neglected
-// terms are far below what decides its optimum.)
-struct GaussFar { double m0, s1, s2; };     // level, sum (d - m0), sum (d - m0)^2 over the WHOLE cutout
-constexpr double kGaussReach = 6.8;
-
-template <typename T> PM_DEV GaussFar gauss_far_sums(Sh& sh, const T* img, int n, double m0) {
-    double a[2] = {0.0, 0.0};
-    for (int i = pm::tid(); i < n * n; i += kThreads) {
-        const double d = (double)pm::ldg(img + i) - m0;
-        a[0] += d; a[1] += d * d;
-    }
-    block_sum<2>(sh, a);
-    GaussFar f;
-    f.m0 = m0; f.s1 = a[0]; f.s2 = a[1];
-    return f;
-}
-
-// Shared memory of the fit behind Sh: per warp a staging tile of the 8 augmented Jacobian columns (J0..J6, r) of its 32
+// Shared memory of a fit behind Sh: per warp a staging tile of the 8 augmented Jacobian columns (J0..J6, r) of its 32
 // pixels, [8][kGaussTileStride] doubles (stride 36: the tensor-core fragment reads of a warp then take the minimum of two
-// wavefronts), the warps' 8 x 8 products, and their sum.
+// wavefronts), the warps' 8 x 8 products, their sum, and the next trial point posted by warp 0.
 constexpr int kGaussTileStride = 36;
 struct GaussSmem {
     double tile[kWarps][8 * kGaussTileStride];
     double prod[kWarps][64];
     double total[64];
-    double trial[8];      // the next trial point, posted by warp 0
+    double trial[8];
     int go;
 };
 
@@ -95,24 +68,13 @@ struct GaussSmem {
 // rank update, done on the FP64 tensor cores (DMMA.8x8x4: four pixels per instruction, the 8 x 8 accumulator spread
 // over the warp, two registers per lane instead of 36 accumulators each): a lane evaluates the model at its pixel,
 // the warp transposes the 32 x 8 values through the staging tile, eight DMMAs add their outer products.
-template <typename T>
-PM_DEV void gauss_pass(Sh& sh, GaussSmem& gs, const T* img, int n, const GaussFar& far, const double* q, double* cost, double* jtj, double* jtr) {
-    const double h = q[0], A = q[1], xo = q[2], yo = q[3], sx = q[4], sy = q[5], th = q[6];
-    const double c = cos(th), s = sin(th);
-    const double isx = 1.0 / sx, isy = 1.0 / sy;
-    // bounding box of the ellipse beyond which the Gaussian is dropped: rows about xo, columns about yo
-    int r0 = 0, r1 = n - 1, c0 = 0, c1 = n - 1;
-    {
-        const double reach = kGaussReach * fmax(fabs(sx), fabs(sy)) + 1.0;
-        if (reach == reach && xo == xo && yo == yo && reach < 4.0 * (double)n) {
-            const double a0 = floor(xo - reach), a1 = ceil(xo + reach), b0 = floor(yo - reach), b1 = ceil(yo + reach);
-            r0 = a0 > 0.0 ? (a0 < (double)n ? (int)a0 : n) : 0;
-            r1 = a1 < (double)(n - 1) ? (a1 >= 0.0 ? (int)a1 : -1) : n - 1;
-            c0 = b0 > 0.0 ? (b0 < (double)n ? (int)b0 : n) : 0;
-            c1 = b1 < (double)(n - 1) ? (b1 >= 0.0 ? (int)b1 : -1) : n - 1;
-        }
-    }
-    const int bw = c1 >= c0 ? c1 - c0 + 1 : 0, bh = r1 >= r0 ? r1 - r0 + 1 : 0;
+// Model: setup(q, n) fixes the per-pass constants and the box [r0, r1] x [c0, c1] of pixels to visit; columns(row, col,
+// dat, J) fills J0..J6 and the residual J7; finish(acc, ...) adds what the pixels outside the box contribute.
+template <typename T, typename Model>
+PM_DEV void fit_pass(Sh& sh, GaussSmem& gs, const T* img, int n, Model& model, const double* q, double* cost, double* jtj, double* jtr) {
+    model.setup(q, n);
+    const int r0 = model.r0, c0 = model.c0;
+    const int bw = model.c1 >= model.c0 ? model.c1 - model.c0 + 1 : 0, bh = model.r1 >= model.r0 ? model.r1 - model.r0 + 1 : 0;
     const int total = bw * bh;
     // the pixel values of the next two steps are requested before the current one is worked on (a step is ~70 FP64
     // instructions, an L2 read several hundred cycles).  Box coordinates advance by the thread count per step without
@@ -124,7 +86,7 @@ PM_DEV void gauss_pass(Sh& sh, GaussSmem& gs, const T* img, int n, const GaussFa
     auto fetch = [&](const Pos& p) -> T { return p.r < bh ? pm::ldg(img + (size_t)(r0 + p.r) * n + (c0 + p.c)) : (T)0; };
     double* tile = gs.tile[pm::warp()];
     const int lane = pm::lane(), g = lane >> 2, t = lane & 3;
-    double d0 = 0.0, d1 = 0.0, sm1 = 0.0, sm2 = 0.0;       // this lane's two entries of the 8 x 8 product; box sums of (d - m0)
+    double d0 = 0.0, d1 = 0.0;       // this lane's two entries of the 8 x 8 product
     Pos cur, nxt;
     cur.r = pm::tid() / bw1; cur.c = pm::tid() - cur.r * bw1;
     nxt = cur;
@@ -137,24 +99,8 @@ PM_DEV void gauss_pass(Sh& sh, GaussSmem& gs, const T* img, int n, const GaussFa
         advance(nxt);
         ahead2 = fetch(nxt);
         double J[8];
-        if (i < total) {
-            const int row = r0 + cur.r, col = c0 + cur.c;
-            // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
-            const double dx = yo - (double)col, dy = xo - (double)row;
-            const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
-            const double E = exp(-0.5 * (u * u + v * v));
-            const double AE = A * E;
-            const double dm = dat - far.m0;
-            sm1 += dm; sm2 += dm * dm;
-            J[0] = 1.0;
-            J[1] = E;
-            J[2] = AE * (u * s * isx - v * c * isy);
-            J[3] = -AE * (u * c * isx + v * s * isy);
-            J[4] = AE * u * u * isx;
-            J[5] = AE * v * v * isy;
-            J[6] = AE * u * v * (sy * isx - sx * isy);
-            J[7] = h + AE - dat;
-        } else {
+        if (i < total) model.columns(r0 + cur.r, c0 + cur.c, dat, J);
+        else {
 #pragma unroll
             for (int k = 0; k < 8; k++) J[k] = 0.0;
         }
@@ -172,7 +118,7 @@ PM_DEV void gauss_pass(Sh& sh, GaussSmem& gs, const T* img, int n, const GaussFa
     // the warps' products, summed in warp order
     gs.prod[pm::warp()][g * 8 + 2 * t] = d0;
     gs.prod[pm::warp()][g * 8 + 2 * t + 1] = d1;
-    double bs[2] = {sm1, sm2};
+    double bs[2] = {model.box_s1, model.box_s2};
     block_sum<2>(sh, bs);                  // (its barrier also orders the products)
     if (pm::tid() < 64) {
         double v = 0.0;
@@ -187,20 +133,178 @@ PM_DEV void gauss_pass(Sh& sh, GaussSmem& gs, const T* img, int n, const GaussFa
     }
     acc[35] = gs.total[63];
     pm::sync();                            // gs.total is rewritten by the next pass
+    model.finish(acc, n, bw, bh, bs);
+    *cost = acc[35];
+    for (int k = 0; k < 28; k++) jtj[k] = acc[k];
+    for (int k = 0; k < 7; k++) jtr[k] = acc[28 + k];
+}
+
+// Levenberg-Marquardt with MINPACK's trust-region logic (lmder: scaling by the running maximum of the column norms,
+// step bound delta, ratio of actual to predicted reduction steering delta and the damping parameter) — the algorithm
+// behind scipy's curve_fit / leastsq with the analytic Jacobian, stopped at `tol` where they stop at 1.5e-8 (the
+// iteration converges linearly on noisy frames: 1e-10 leaves the Gaussian widths within 2e-5 of the optimum, curve_fit's
+// own stop within 2e-4; 1e-13 costs 20 % more steps).  An undamped or merely Marquardt-damped iteration walks off to
+// needle-shaped Gaussians from the start values of gaussfitter.moments.
+// The passes over the pixels are the whole CTA's; the 7 x 7 algebra between them is warp 0's alone (the other warps wait
+// at the barrier and leave the issue slots to the CTAs sharing the SM): it posts the next trial point, or the end, in
+// gs.trial / gs.go.  p: start values in, optimum out (meaningful in warp 0); returns the status (warp 0).
+template <typename T, typename Model>
+PM_DEV int lm_minimise(Sh& sh, GaussSmem& gs, const T* img, int n, Model& model, double* p, double tol, double* cost_out, int* iter_out) {
+    double cost = 0.0, jtj[28], jtr[7];
+    int iter = 0, status = 1;
+    const bool lead = pm::warp() == 0;
+    fit_pass(sh, gs, img, n, model, p, &cost, jtj, jtr);
+    if (!(cost == cost) || !(cost < 1.7e308)) status = 2;
+    double dg[7], d[7], xnorm = 0.0, par = 0.0, pnorm = 0.0, delta = 100.0;
+    if (lead) {
+        for (int k = 0; k < 7; k++) {
+            const double a = jtj[k * (k + 1) / 2 + k];
+            dg[k] = a > 0.0 ? sqrt(a) : 1.0;
+            xnorm += dg[k] * p[k] * dg[k] * p[k];
+            d[k] = 0.0;
+        }
+        xnorm = sqrt(xnorm);
+        delta = xnorm > 0.0 ? 100.0 * xnorm : 100.0;
+        if (status == 1 && cost == 0.0) status = 0;
+    }
+    for (;;) {
+        if (lead) {
+            bool go = status == 1 && iter < kGaussMaxIter;
+            if (go) {
+                double maxratio = 0.0;
+                for (int k = 0; k < 7; k++) {
+                    const double a = jtj[k * (k + 1) / 2 + k];
+                    if (a > 0.0) dg[k] = fmax(dg[k], sqrt(a));
+                    maxratio = fmax(maxratio, a / (dg[k] * dg[k]));
+                }
+                double g[7];
+                for (int k = 0; k < 7; k++) g[k] = -jtr[k];
+                bool solved = false;
+                for (int inner = 0; inner < 80; inner++) {
+                    if (!lm_solve7(jtj, g, par, dg, d)) { par = fmax(par * 4.0, 1e-12 * fmax(maxratio, 1e-300)); continue; }
+                    pnorm = 0.0;
+                    for (int k = 0; k < 7; k++) pnorm += dg[k] * d[k] * dg[k] * d[k];
+                    pnorm = sqrt(pnorm);
+                    solved = true;
+                    if (pnorm <= 1.1 * delta) break;
+                    par = fmax(par * 4.0, 1e-8 * fmax(maxratio, 1e-300));
+                }
+                if (!solved) { status = 3; go = false; }
+            }
+            if (pm::lane() == 0) {
+                gs.go = go ? 1 : 0;
+                for (int k = 0; k < 7; k++) gs.trial[k] = p[k] + d[k];
+            }
+        }
+        pm::sync();
+        if (!gs.go) break;
+        double q[7], cost_q, jtj_q[28], jtr_q[7];
+        for (int k = 0; k < 7; k++) q[k] = gs.trial[k];
+        fit_pass(sh, gs, img, n, model, q, &cost_q, jtj_q, jtr_q);
+        if (lead) {
+            if (iter == 0) delta = fmin(delta, pnorm);
+            const bool finite_q = cost_q == cost_q && cost_q < 1.7e308;
+            const double actred = finite_q ? 1.0 - cost_q / cost : -1.0;
+            double jd2 = 0.0;                             // |J d|^2 = d^T (J^T J) d
+            for (int a = 0; a < 7; a++)
+                for (int b2 = 0; b2 < 7; b2++) jd2 += d[a] * d[b2] * jtj[a >= b2 ? a * (a + 1) / 2 + b2 : b2 * (b2 + 1) / 2 + a];
+            const double t1 = jd2 / cost, t2 = par * pnorm * pnorm / cost;
+            const double prered = t1 + 2.0 * t2, dirder = -(t1 + t2);
+            const double ratio = prered != 0.0 ? actred / prered : 0.0;
+            if (ratio <= 0.25) {
+                double temp = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+                if (!finite_q || 0.1 * cost_q >= cost || temp < 0.1) temp = 0.1;
+                delta = temp * fmin(delta, pnorm / 0.1);
+                par /= temp;
+            } else if (par == 0.0 || ratio >= 0.75) {
+                delta = pnorm / 0.5;
+                par *= 0.5;
+            }
+            if (ratio >= 1e-4) {
+                for (int k = 0; k < 7; k++) p[k] = q[k];
+                cost = cost_q;
+                for (int k = 0; k < 28; k++) jtj[k] = jtj_q[k];
+                for (int k = 0; k < 7; k++) jtr[k] = jtr_q[k];
+                xnorm = 0.0;
+                for (int k = 0; k < 7; k++) xnorm += dg[k] * p[k] * dg[k] * p[k];
+                xnorm = sqrt(xnorm);
+            }
+            if ((fabs(actred) <= tol && prered <= tol && 0.5 * ratio <= 1.0) || delta <= tol * xnorm || cost == 0.0) status = 0;
+            iter++;
+        }
+    }
+    *cost_out = cost;
+    *iter_out = iter;
+    return status;
+}
+
+// ---- the Gaussian of skyBackground._gauss2dfit (skyBackground.py:306-331): gaussfitter.twodgaussian
+//      parameters: height, amplitude, xo, yo, sigma_x, sigma_y, theta (raw optimum, before the np.abs of :331)
+// Far from the centre the Gaussian term is below 1e-10 of its amplitude (exp(-q/2), q > 46: farther than 6.8 times the
+// larger width), the residual is height - data and only the height column of the Jacobian is non-zero.  Those pixels
+// enter through three sums that do not depend on the parameters — their number, sum (d - m0) and sum (d - m0)^2 about a
+// fixed level m0 near the data (no cancellation) —, taken once per cutout; a pass then evaluates the model only inside
+// the bounding box of that ellipse and corrects the sums by the box's own.  (curve_fit stops at 1.5e-8: the neglected
+// terms are far below what decides its optimum.)
+constexpr double kGaussReach = 6.8;
+struct GaussModel {
+    double m0, s1, s2;                     // level, sum (d - m0), sum (d - m0)^2 over the WHOLE cutout
+    double h, A, xo, yo, sx, sy, c, s, isx, isy;
+    int r0, r1, c0, c1;
+    double box_s1, box_s2;                 // this thread's sums of (d - m0), (d - m0)^2 over the box pixels it visited
+    template <typename T> PM_DEV void whole_frame_sums(Sh& sh, const T* img, int n, double level) {
+        double a[2] = {0.0, 0.0};
+        for (int i = pm::tid(); i < n * n; i += kThreads) {
+            const double d = (double)pm::ldg(img + i) - level;
+            a[0] += d; a[1] += d * d;
+        }
+        block_sum<2>(sh, a);
+        m0 = level; s1 = a[0]; s2 = a[1];
+    }
+    PM_DEV void setup(const double* q, int n) {
+        h = q[0]; A = q[1]; xo = q[2]; yo = q[3]; sx = q[4]; sy = q[5];
+        c = cos(q[6]); s = sin(q[6]);
+        isx = 1.0 / sx; isy = 1.0 / sy;
+        box_s1 = box_s2 = 0.0;
+        r0 = 0; r1 = n - 1; c0 = 0; c1 = n - 1;
+        // bounding box of the ellipse beyond which the Gaussian is dropped: rows about xo, columns about yo
+        const double reach = kGaussReach * fmax(fabs(sx), fabs(sy)) + 1.0;
+        if (reach == reach && xo == xo && yo == yo && reach < 4.0 * (double)n) {
+            const double a0 = floor(xo - reach), a1 = ceil(xo + reach), b0 = floor(yo - reach), b1 = ceil(yo + reach);
+            r0 = a0 > 0.0 ? (a0 < (double)n ? (int)a0 : n) : 0;
+            r1 = a1 < (double)(n - 1) ? (a1 >= 0.0 ? (int)a1 : -1) : n - 1;
+            c0 = b0 > 0.0 ? (b0 < (double)n ? (int)b0 : n) : 0;
+            c1 = b1 < (double)(n - 1) ? (b1 >= 0.0 ? (int)b1 : -1) : n - 1;
+        }
+    }
+    PM_DEV void columns(int row, int col, double dat, double (&J)[8]) {
+        // gaussfitter.twodgaussian: centre (column yo, row xo) — center_y, center_x = xo, yo (gaussfitter.py:132)
+        const double dx = yo - (double)col, dy = xo - (double)row;
+        const double u = (dx * c - dy * s) * isx, v = (dx * s + dy * c) * isy;
+        const double E = exp(-0.5 * (u * u + v * v));
+        const double AE = A * E;
+        const double dm = dat - m0;
+        box_s1 += dm; box_s2 += dm * dm;
+        J[0] = 1.0;
+        J[1] = E;
+        J[2] = AE * (u * s * isx - v * c * isy);
+        J[3] = -AE * (u * c * isx + v * s * isy);
+        J[4] = AE * u * u * isx;
+        J[5] = AE * v * v * isy;
+        J[6] = AE * u * v * (sy * isx - sx * isy);
+        J[7] = h + AE - dat;
+    }
     // the pixels outside the box: r = (h - m0) - (d - m0), J = (1, 0, ..., 0)
-    {
+    PM_DEV void finish(double* acc, int n, int bw, int bh, const double* bs) const {
         const double nf = (double)n * (double)n - (double)bw * (double)bh;
-        const double f1 = far.s1 - bs[0], f2 = far.s2 - bs[1], hm = h - far.m0;
+        const double f1 = s1 - bs[0], f2 = s2 - bs[1], hm = h - m0;
         if (nf > 0.0) {
             acc[35] += nf * hm * hm - 2.0 * hm * f1 + f2;
             acc[0] += nf;                    // J0 J0
             acc[28] += nf * hm - f1;         // J0 r
         }
     }
-    *cost = acc[35];
-    for (int k = 0; k < 28; k++) jtj[k] = acc[k];
-    for (int k = 0; k < 7; k++) jtr[k] = acc[28 + k];
-}
+};
 
 template <typename T>
 PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* median, const double* vmax, const double* p0_in, double* out) {
@@ -229,107 +333,181 @@ PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* med
             p[4] = sqrt(a4[0] / a4[1]); p[5] = sqrt(a4[2] / a4[3]); p[6] = 90.0 * 3.141592653589793 / 180.0;
             if (p[4] != p[4] || p[5] != p[5] || p[0] != p[0] || p[1] != p[1]) status = 2;
         }
-        double cost = 0.0, jtj[28], jtr[7];
+        double cost = 0.0;
         int iter = 0;
-        const GaussFar far = gauss_far_sums(sh, img, n, p[0] == p[0] && fabs(p[0]) < 1.7e308 ? p[0] : 0.0);
-        if (status == 0) {
-            // Levenberg-Marquardt with MINPACK's trust-region logic (lmder: scaling by the running maximum of the column
-            // norms, step bound delta, ratio of actual to predicted reduction steering delta and the damping parameter) —
-            // curve_fit's algorithm with the analytic Jacobian, stopped at 1e-10 instead of 1.5e-8 (the iteration converges
-            // linearly on these noisy frames: 1e-10 leaves the widths within 2e-5 of the optimum, curve_fit's own stop within
-            // 2e-4; 1e-13 costs 20 % more steps).  An undamped or merely Marquardt-damped iteration walks off to needle-shaped
-            // Gaussians from the start values of gaussfitter.moments.
-            // The passes over the pixels are the whole CTA's; the 7 x 7 algebra between them is warp 0's alone (the other
-            // warps wait at the barrier and leave the issue slots to the CTAs sharing the SM): it posts the next trial
-            // point, or the end, in gs.trial / gs.go.
-            const bool lead = pm::warp() == 0;
-            gauss_pass(sh, gs, img, n, far, p, &cost, jtj, jtr);
-            status = 1;
-            if (!(cost == cost) || !(cost < 1.7e308)) status = 2;
-            double dg[7], d[7], xnorm = 0.0, par = 0.0, pnorm = 0.0, delta = 100.0;
-            const double tol = 1e-10;
-            if (lead) {
-                for (int k = 0; k < 7; k++) {
-                    const double a = jtj[k * (k + 1) / 2 + k];
-                    dg[k] = a > 0.0 ? sqrt(a) : 1.0;
-                    xnorm += dg[k] * p[k] * dg[k] * p[k];
-                }
-                xnorm = sqrt(xnorm);
-                delta = xnorm > 0.0 ? 100.0 * xnorm : 100.0;
-                if (status == 1 && cost == 0.0) status = 0;
-            }
-            for (;;) {
-                if (lead) {
-                    bool go = status == 1 && iter < kGaussMaxIter;
-                    if (go) {
-                        double maxratio = 0.0;
-                        for (int k = 0; k < 7; k++) {
-                            const double a = jtj[k * (k + 1) / 2 + k];
-                            if (a > 0.0) dg[k] = fmax(dg[k], sqrt(a));
-                            maxratio = fmax(maxratio, a / (dg[k] * dg[k]));
-                        }
-                        double g[7];
-                        for (int k = 0; k < 7; k++) g[k] = -jtr[k];
-                        bool solved = false;
-                        for (int inner = 0; inner < 80; inner++) {
-                            if (!lm_solve7(jtj, g, par, dg, d)) { par = fmax(par * 4.0, 1e-12 * fmax(maxratio, 1e-300)); continue; }
-                            pnorm = 0.0;
-                            for (int k = 0; k < 7; k++) pnorm += dg[k] * d[k] * dg[k] * d[k];
-                            pnorm = sqrt(pnorm);
-                            solved = true;
-                            if (pnorm <= 1.1 * delta) break;
-                            par = fmax(par * 4.0, 1e-8 * fmax(maxratio, 1e-300));
-                        }
-                        if (!solved) { status = 3; go = false; }
-                    }
-                    if (pm::lane() == 0) {
-                        gs.go = go ? 1 : 0;
-                        for (int k = 0; k < 7; k++) gs.trial[k] = p[k] + d[k];
-                    }
-                }
-                pm::sync();
-                if (!gs.go) break;
-                double q[7], cost_q, jtj_q[28], jtr_q[7];
-                for (int k = 0; k < 7; k++) q[k] = gs.trial[k];
-                gauss_pass(sh, gs, img, n, far, q, &cost_q, jtj_q, jtr_q);
-                if (lead) {
-                    if (iter == 0) delta = fmin(delta, pnorm);
-                    const bool finite_q = cost_q == cost_q && cost_q < 1.7e308;
-                    const double actred = finite_q ? 1.0 - cost_q / cost : -1.0;
-                    double jd2 = 0.0;                             // |J d|^2 = d^T (J^T J) d
-                    for (int a = 0; a < 7; a++)
-                        for (int b2 = 0; b2 < 7; b2++) jd2 += d[a] * d[b2] * jtj[a >= b2 ? a * (a + 1) / 2 + b2 : b2 * (b2 + 1) / 2 + a];
-                    const double t1 = jd2 / cost, t2 = par * pnorm * pnorm / cost;
-                    const double prered = t1 + 2.0 * t2, dirder = -(t1 + t2);
-                    const double ratio = prered != 0.0 ? actred / prered : 0.0;
-                    if (ratio <= 0.25) {
-                        double temp = actred >= 0.0 ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
-                        if (!finite_q || 0.1 * cost_q >= cost || temp < 0.1) temp = 0.1;
-                        delta = temp * fmin(delta, pnorm / 0.1);
-                        par /= temp;
-                    } else if (par == 0.0 || ratio >= 0.75) {
-                        delta = pnorm / 0.5;
-                        par *= 0.5;
-                    }
-                    if (ratio >= 1e-4) {
-                        for (int k = 0; k < 7; k++) p[k] = q[k];
-                        cost = cost_q;
-                        for (int k = 0; k < 28; k++) jtj[k] = jtj_q[k];
-                        for (int k = 0; k < 7; k++) jtr[k] = jtr_q[k];
-                        xnorm = 0.0;
-                        for (int k = 0; k < 7; k++) xnorm += dg[k] * p[k] * dg[k] * p[k];
-                        xnorm = sqrt(xnorm);
-                    }
-                    if ((fabs(actred) <= tol && prered <= tol && 0.5 * ratio <= 1.0) || delta <= tol * xnorm || cost == 0.0) status = 0;
-                    iter++;
-                }
-            }
-        }
+        GaussModel model;
+        model.whole_frame_sums(sh, img, n, p[0] == p[0] && fabs(p[0]) < 1.7e308 ? p[0] : 0.0);
+        if (status == 0) status = lm_minimise(sh, gs, img, n, model, p, 1e-10, &cost, &iter);
         if (pm::tid() == 0) {
             double* o = out + (size_t)b * kGaussCols;
             for (int k = 0; k < 7; k++) o[k] = p[k];
             o[7] = cost; o[8] = (double)iter; o[9] = (double)status;
         }
+        pm::sync();
+    }
+}
+
+// ---- the Sersic profile of sersic.fitSersic (sersic.py:125-134): astropy Sersic2D.evaluate
+//      f = amplitude exp(-b_n (z^(1/n) - 1)),  z^2 = (x_maj / r_eff)^2 + (x_min / ((1 - ellip) r_eff))^2,  b_n = gammaincinv(2 n, 1/2)
+//      parameters: amplitude, r_eff, n, x_0, y_0, ellip, theta; x = column, y = row (np.mgrid, sersic.py:131)
+// regularised lower incomplete gamma P(a, x) for x < a + 1 (series) and its inverse at 1/2 by Newton steps from the
+// asymptotic value a - 1/3 + 8 / (405 a) (Ciotti & Bertin 1999 for b_n with a = 2 n)
+PM_DEV double gamma_p_series(double a, double x) {
+    double term = 1.0 / a, sum = term;
+    for (int k = 1; k < 500; k++) {
+        term *= x / (a + (double)k);
+        sum += term;
+        if (fabs(term) < fabs(sum) * 1e-17) break;
+    }
+    return sum * exp(-x + a * log(x) - lgamma(a));
+}
+PM_DEV double gammaincinv_half(double a) {
+    if (!(a > 0.0)) return pm::bits2d(0x7ff8000000000000ll);
+    double x = a - 1.0 / 3.0 + 8.0 / (405.0 * a);
+    if (!(x > 0.0)) x = 0.5 * a;
+    for (int it = 0; it < 60; it++) {
+        const double f = gamma_p_series(a, x) - 0.5;
+        const double df = exp(-x + (a - 1.0) * log(x) - lgamma(a));
+        double step = f / df;
+        if (!(step == step)) break;
+        if (x - step <= 0.0) step = 0.5 * x;             // stay positive
+        x -= step;
+        if (fabs(step) <= 1e-16 * x) break;
+    }
+    return x;
+}
+struct SersicModel {
+    double A, re, nn, x0, y0, el, ct, st, bn, dbn, ia, ib, inv_n;
+    int r0, r1, c0, c1;
+    double box_s1, box_s2;
+    PM_DEV void setup(const double* q, int n) {
+        A = q[0]; re = q[1]; nn = q[2]; x0 = q[3]; y0 = q[4]; el = q[5];
+        ct = cos(q[6]); st = sin(q[6]);
+        bn = gammaincinv_half(2.0 * nn);
+        const double hstep = 1e-6 * fmax(fabs(nn), 1e-3);
+        dbn = (gammaincinv_half(2.0 * (nn + hstep)) - gammaincinv_half(2.0 * (nn - hstep))) / (2.0 * hstep);
+        ia = 1.0 / re; ib = 1.0 / ((1.0 - el) * re); inv_n = 1.0 / nn;
+        r0 = 0; r1 = n - 1; c0 = 0; c1 = n - 1;
+        box_s1 = box_s2 = 0.0;
+    }
+    PM_DEV void columns(int row, int col, double dat, double (&J)[8]) {
+        const double dx = (double)col - x0, dy = (double)row - y0;
+        const double xmaj = dx * ct + dy * st, xmin = -dx * st + dy * ct;
+        const double ua = xmaj * ia, ub = xmin * ib;
+        const double z2 = ua * ua + ub * ub, z = sqrt(z2);
+        const double lz = log(z);                                    // -inf at the centre: w = 0 there
+        const double w = z > 0.0 ? exp(lz * inv_n) : 0.0;
+        const double e = exp(-bn * (w - 1.0));
+        const double f = A * e;
+        // df/dz = -b_n f w / (n z); the cusp at z = 0 (one pixel at most) is given slope 0
+        const double fz = z > 0.0 ? -bn * f * w * inv_n / z : 0.0;
+        const double iz = z > 0.0 ? 1.0 / z : 0.0;
+        J[0] = e;
+        J[1] = fz * (-z * ia);                                                           // z ~ 1 / r_eff
+        J[2] = z > 0.0 ? -f * (dbn * (w - 1.0) - bn * w * lz * inv_n * inv_n) : -f * dbn * (w - 1.0);
+        J[3] = fz * iz * (-ua * ia * ct + ub * ib * st);
+        J[4] = fz * iz * (-ua * ia * st - ub * ib * ct);
+        J[5] = fz * iz * (ub * ub / (1.0 - el));                                         // d b / d ellip = -r_eff
+        J[6] = fz * iz * (xmaj * xmin * (ia * ia - ib * ib));
+        J[7] = f - dat;
+    }
+    PM_DEV void finish(double*, int, int, int, const double*) const {}
+};
+
+// p0: DEVICE [B, 7] start values (sersic.py:98-123, the caller's); out: as the Gaussian fit
+template <typename T>
+PM_DEV void sersicfit_body(const T* images, long long B, int n, const double* p0_in, double* out) {
+    unsigned char* smem = pm::dyn_smem(0);
+    Sh& sh = *(Sh*)smem;
+    GaussSmem& gs = *(GaussSmem*)(smem + align16((unsigned)sizeof(Sh)));
+    sh.par[pm::tid()] = 0;
+    pm::sync();
+    for (long long b = pm::block(); b < B; b += pm::nblocks()) {
+        const T* img = images + (size_t)b * n * n;
+        double p[7];
+        int status = 0;
+        for (int k = 0; k < 7; k++) { p[k] = p0_in[7 * b + k]; if (p[k] != p[k]) status = 2; }
+        double cost = 0.0;
+        int iter = 0;
+        SersicModel model;
+        if (status == 0) status = lm_minimise(sh, gs, img, n, model, p, 1e-10, &cost, &iter);
+        if (pm::tid() == 0) {
+            double* o = out + (size_t)b * kGaussCols;
+            for (int k = 0; k < 7; k++) o[k] = p[k];
+            o[7] = cost; o[8] = (double)iter; o[9] = (double)status;
+        }
+        pm::sync();
+    }
+}
+
+// ---- exact elliptical aperture sums (photutils EllipticalAperture.do_photometry(method="exact"), sersic.py:46-47, :101-121)
+// Area of (pixel ∩ ellipse): the pixel's corners are mapped to the frame in which the ellipse is the unit circle; the
+// area of (parallelogram ∩ unit disc) is the sum over the edges of a triangle about the origin for the part of the edge
+// inside the disc and of circular sectors for the parts outside (signed; counter-clockwise corners).
+PM_DEV double unit_disc_edge(double px, double py, double qx, double qy) {
+    const double dx = qx - px, dy = qy - py;
+    const double a = dx * dx + dy * dy, b = 2.0 * (px * dx + py * dy), c = px * px + py * py - 1.0;
+    const double disc = b * b - 4.0 * a * c;
+    double t1 = 0.0, t2 = 0.0;
+    bool hit = false;
+    if (disc > 0.0 && a > 0.0) {
+        const double sq = sqrt(disc);
+        t1 = fmin(fmax((-b - sq) / (2.0 * a), 0.0), 1.0);
+        t2 = fmin(fmax((-b + sq) / (2.0 * a), 0.0), 1.0);
+        hit = t2 > t1;
+    }
+    if (!hit) {
+        const bool q_in = qx * qx + qy * qy - 1.0 <= 0.0;
+        if (c <= 0.0 && q_in) return 0.5 * (px * qy - py * qx);
+        return 0.5 * atan2(px * qy - py * qx, px * qx + py * qy);
+    }
+    const double ax = px + t1 * dx, ay = py + t1 * dy, bx = px + t2 * dx, by = py + t2 * dy;
+    double v = 0.5 * (ax * by - ay * bx);
+    if (t1 > 0.0) v += 0.5 * atan2(px * ay - py * ax, px * ax + py * ay);
+    if (t2 < 1.0) v += 0.5 * atan2(bx * qy - by * qx, bx * qx + by * qy);
+    return v;
+}
+// ell: (xc, yc, a, b, theta) per entry; idx: cutout of each entry (nullptr: entry i is cutout i); out: the sums
+template <typename T>
+PM_DEV void ellipse_sum_body(const T* images, int n, long long M, const long long* idx, const double* ell, double* out) {
+    unsigned char* smem = pm::dyn_smem(0);
+    Sh& sh = *(Sh*)smem;
+    sh.par[pm::tid()] = 0;
+    pm::sync();
+    for (long long m = pm::block(); m < M; m += pm::nblocks()) {
+        const T* img = images + (size_t)(idx ? idx[m] : m) * n * n;
+        const double xc = ell[5 * m], yc = ell[5 * m + 1], a = ell[5 * m + 2], b = ell[5 * m + 3], th = ell[5 * m + 4];
+        const double ct = cos(th), st = sin(th);
+        const double ex = sqrt(a * ct * a * ct + b * st * b * st), ey = sqrt(a * st * a * st + b * ct * b * ct);
+        double sum = 0.0;
+        if (a > 0.0 && b > 0.0 && ex == ex && ey == ey && xc == xc && yc == yc && ex < 1e9 && ey < 1e9) {
+            const double fc0 = floor(xc - ex - 0.5), fc1 = ceil(xc + ex + 0.5), fr0 = floor(yc - ey - 0.5), fr1 = ceil(yc + ey + 0.5);
+            const int c0 = fc0 > 0.0 ? (fc0 < (double)n ? (int)fc0 : n) : 0, c1 = fc1 < (double)(n - 1) ? (fc1 >= 0.0 ? (int)fc1 : -1) : n - 1;
+            const int r0 = fr0 > 0.0 ? (fr0 < (double)n ? (int)fr0 : n) : 0, r1 = fr1 < (double)(n - 1) ? (fr1 >= 0.0 ? (int)fr1 : -1) : n - 1;
+            const int bw = c1 >= c0 ? c1 - c0 + 1 : 0, bh = r1 >= r0 ? r1 - r0 + 1 : 0;
+            const double ia = 1.0 / a, ib = 1.0 / b;
+            for (int i = pm::tid(); i < bw * bh; i += kThreads) {
+                const int rr = i / bw, row = r0 + rr, col = c0 + (i - rr * bw);
+                double u[4], v[4];
+                bool all_in = true;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {                       // counter-clockwise corners
+                    const double x = (double)col + ((k == 1 || k == 2) ? 0.5 : -0.5) - xc, y = (double)row + (k >= 2 ? 0.5 : -0.5) - yc;
+                    u[k] = (x * ct + y * st) * ia; v[k] = (-x * st + y * ct) * ib;
+                    all_in = all_in && (u[k] * u[k] + v[k] * v[k] <= 1.0);
+                }
+                double wgt = 1.0;
+                if (!all_in) {
+                    double area = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) area += unit_disc_edge(u[k], v[k], u[(k + 1) & 3], v[(k + 1) & 3]);
+                    wgt = fmin(fmax(area * a * b, 0.0), 1.0);
+                }
+                if (wgt != 0.0) sum += wgt * (double)pm::ldg(img + (size_t)row * n + col);
+            }
+        } else sum = pm::bits2d(0x7ff8000000000000ll);
+        sum = block_sum1(sh, sum);
+        if (pm::tid() == 0) out[m] = sum;
         pm::sync();
     }
 }

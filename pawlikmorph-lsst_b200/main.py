@@ -10,8 +10,8 @@ The cut-out of Image.py:135-138, :175-186 is kept too: with `npix` not larger th
 npix x npix window around the catalogue position is analysed (sky -> pixel on the host, the copy fused with the decode
 on the device); otherwise the whole frame, like the reference.
 `skybgr` (skyBackground.py) and the `maskstarsSEG` cleaning (imageutils.py:42-91, with a seeded generator in place of the
-reference's unseeded one) run on the device too.  What is not here: star catalogues, Sersic
-fits, segmap / clean-image FITS output, diagnostic plots.  Options that would need them raise NotImplementedError.
+reference's unseeded one) run on the device too, and so does `fitSersic` (`calculateSersic`, sersic.py).  What is not here
+(DESIGN §7): star catalogues, segmap / clean-image FITS output, diagnostic plots.  Options that would need them raise NotImplementedError.
 """
 import csv
 import os
@@ -67,10 +67,11 @@ def _decode_dtype(bitpix, bzero, bscale):
     return payload_dtype(bitpix, bzero, bscale)
 
 
-def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed):
+def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, sersic=False):
     """One group of equally sized cutouts that already live on the GPU through main.py:349-495: skybgr (unless sky is given),
     pixelmap on the image with the sky in (:421), `img -= sky`, maskstarsSEG (:442-445), the rest on the cleaned image.
-    Returns rows [B, 16], sky, sky_err [B], fwhms [B, 2], theta [B] as numpy arrays."""
+    Returns rows [B, 16], sky, sky_err [B], fwhms [B, 2], theta [B] as numpy arrays — and, with sersic=True, the fitted Sersic2D
+    parameters [B, 7] of main.py:480-488 (-99 where there is no fit)."""
     import torch
 
     from .batch import analyse_batch
@@ -87,8 +88,11 @@ def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed):
     dev = images.device
     sky_d = torch.as_tensor(np.asarray(sky, dtype=np.float64), device=dev)
     err_d = torch.as_tensor(np.asarray(sky_err, dtype=np.float64), device=dev)
+    final = None                                                          # the image fitSersic sees: img - sky, cleaned
     if not clean:
         rows = analyse_batch(images, sky_d, err_d, filterSize, flags).rows.cpu().numpy()
+        if sersic:
+            final = images.to(torch.float64) - sky_d[:, None, None]
     else:
         first = analyse_batch(images, sky_d, err_d, filterSize, flags | _abi.PM_STOP_AFTER_PIXELMAP, want_segmap=True)
         sub = images.to(torch.float64) - sky_d[:, None, None]                                   # main.py:442
@@ -100,9 +104,23 @@ def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed):
         rows[:, col("object_edge")] = rows1[:, col("object_edge")]                               # main.py:427 (pixelmap path)
         faint = rows1[:, col("status")] == 1
         rows[faint] = rows1[faint]                                                               # main.py:420-424
+        final = cleaned
     rows[sky_fail] = -99.0
     rows[sky_fail, _abi.ROW_FIELDS.index("status")] = 1.0
-    return rows, np.where(sky_fail, -99.0, sky), np.where(sky_fail, 99.0, sky_err), fwhms, theta
+    out = (rows, np.where(sky_fail, -99.0, sky), np.where(sky_fail, 99.0, sky_err), fwhms, theta)
+    if not sersic:
+        return out
+    # main.py:480-488: fitSersic(img, apix, fwhms, theta) on the analysed cutouts (apix = (x, y) = (column, row))
+    from .sersic import fitSersic_batch
+    col = _abi.ROW_FIELDS.index
+    ser = np.full((B, 7), -99.0)
+    okrow = np.nonzero((rows[:, col("status")] == 0) & ~sky_fail & (rows[:, col("apix_col")] >= 0))[0]
+    if okrow.size:
+        sel = final if okrow.size == B else final[torch.as_tensor(okrow, device=dev)]
+        fit = fitSersic_batch(sel, rows[okrow][:, [col("apix_col"), col("apix_row")]], fwhms[okrow], theta[okrow])
+        good = np.isin(fit["status"], (0, 1))
+        ser[okrow[good]] = fit["params"][good]
+    return out + (ser,)
 
 
 def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filterSize=3, parallelLibrary="none", cores=1,
@@ -128,10 +146,12 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     frame, as upstream); a frame that cannot be read, or whose window leaves it (image.PartialOverlapError, the
     `Cutout2D(mode="strict")` error), gets the default Result and the run carries on (main.py:331-339); so does a frame
     whose sky estimate fails (main.py:350-368)."""
-    for name, val in (("calculateSersic", calculateSersic), ("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
+    for name, val in (("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
                       ("catalogue", catalogue), ("segmap", segmap), ("starMask", starMask)):
         if val:
             raise NotImplementedError(f"{name}: outside the morphology path this package covers")
+    if calculateSersic and (sky is not None or gauss is not None):
+        raise NotImplementedError("calculateSersic needs the widths and the angle of the sky estimate: run with sky=None, like upstream")
     if isinstance(sky, str) and sky == "border":
         sky = border_sky
     from . import batch as _batch                    # needs torch + the CUDA library; fails loudly without them
@@ -193,6 +213,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     for i in failed:
         rows[i, _abi.ROW_FIELDS.index("status")] = 1.0                         # -> the default Result (main.py:331-339)
     fw_all, th_all = np.full((len(infos), 2), -99.0), np.full(len(infos), -99.0)
+    ser_all = np.full((len(infos), 7), -99.0)
     for (n, H, W, windowed, bitpix, bzero, bscale, n_large, large_windowed), idx in groups.items():
         pay = np.empty((len(idx), H * W * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
         for k, i in enumerate(idx):
@@ -215,9 +236,12 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                 else:
                     large = decode_payload(pd, bitpix, (len(idx), H, W), bzero, bscale, dt)
             have_sky = sky is not None
-            r, sk, er, fw, th = _device_group(images, large, np.array([frames[i][1] for i in idx]) if have_sky else None,
-                                              np.array([frames[i][2] for i in idx]) if have_sky else None, flags, filterSize, clean,
-                                              seed)
+            got = _device_group(images, large, np.array([frames[i][1] for i in idx]) if have_sky else None,
+                                np.array([frames[i][2] for i in idx]) if have_sky else None, flags, filterSize, clean,
+                                seed, sersic=bool(calculateSersic))
+            r, sk, er, fw, th = got[:5]
+            if calculateSersic:
+                ser_all[idx] = got[5]
             rows[idx] = r
             fw_all[idx], th_all[idx] = fw, th
             for k, i in enumerate(idx):
@@ -243,6 +267,9 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
         r = Result.from_row(rows[i], file=os.path.basename(f), sky=frames[i][1], sky_err=frames[i][2])      # main.py:341: file.name
         if r.status != 1 and fw_all[i, 0] != -99.0:
             r.fwhms, r.theta = [float(fw_all[i, 0]), float(fw_all[i, 1])], float(th_all[i])                # main.py:349
+        if calculateSersic and r.status != 1:                                                              # main.py:480-488
+            (r.sersic_amplitude, r.sersic_r_eff, r.sersic_n, r.sersic_x_0, r.sersic_y_0, r.sersic_ellip,
+             r.sersic_theta) = (float(v) for v in ser_all[i])
         r.outfolder = str(outfolder)
         r.time = per_image
         results.append(r)

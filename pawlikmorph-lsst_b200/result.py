@@ -30,7 +30,7 @@ class Result:
     objectEdge: bool = False
     fwhms: List[float] = field(default_factory=lambda: [-99., -99.])    # result.py:40; filled by skybgr (out of scope)
     theta: float = -99.
-    sersic_amplitude: float = -99.                                      # result.py:56-68; -sersic is out of scope
+    sersic_amplitude: float = -99.                                      # result.py:56-68; filled by calculateSersic (main.py:480-488)
     sersic_r_eff: float = -99.
     sersic_n: float = -99.
     sersic_x_0: float = -99.

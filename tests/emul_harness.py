@@ -176,6 +176,34 @@ def gaussfit(images, p0=None):
     return out
 
 
+def ellipse_sums(images, ell, idx=None):
+    """exact elliptical aperture sums: ell [M, 5] = xc, yc, a, b, theta; idx [M] cutout per entry (None: identity)."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    _, n, _ = images.shape
+    ell = np.ascontiguousarray(np.asarray(ell, dtype=np.float64).reshape(-1, 5))
+    M = ell.shape[0]
+    idx = None if idx is None else np.ascontiguousarray(np.asarray(idx, dtype=np.int64))
+    out = np.full(M, np.nan)
+    rc = L.pm_ellipse_sum_batch(images.ctypes.data, abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64, n, M, _p(idx), ell.ctypes.data,
+                                out.ctypes.data, None)
+    abi.check(L, rc, "pm_ellipse_sum_batch")
+    return out
+
+
+def sersicfit(images, p0):
+    """-> [B, 10] (SERSIC_FIELDS) from the start values p0 [B, 7]."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    B, n, _ = images.shape
+    p0 = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(B, 7))
+    out = np.full((B, abi.PM_GAUSS_COLS), np.nan)
+    rc = L.pm_sersicfit_batch(images.ctypes.data, abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64, B, n, p0.ctypes.data,
+                              out.ctypes.data, None)
+    abi.check(L, rc, "pm_sersicfit_batch")
+    return out
+
+
 def maskstars(images, seed=0, nsigma=1.5, npixels=8, clean=True):
     """imageutils.maskstarsSEG through the emulator build: dict(clean, labels, info)."""
     L = lib()
