@@ -468,6 +468,13 @@ def run_ours(args):
         star_ms, star = timed(lambda: pm.imageutils.maskstars_batch(xp, seed=1))
         flow_ms, flow = timed(lambda: pm.main._device_group(xp, None, None, None, FLAGS_ALL, 3, True, 1), reps=1)
         flow_ok = float((flow[0][:, pm._abi.ROW_FIELDS.index("status")] == 0).mean())
+        # fitSersic on the sky-subtracted cutouts with the widths / angle of the Gaussian fit and the apix of the rows
+        S_n = min(P_, 2048)
+        fitn = fit[:S_n].cpu().numpy()
+        ser_in = xp[:S_n] - float(synth.SKY)
+        ser_cen = rows[:S_n, :2].cpu().numpy()
+        ser_fw = 2.3548200450309493 * np.abs(fitn[:, 4:6])
+        ser_ms, ser = timed(lambda: pm.sersic.fitSersic_batch(ser_in, ser_cen, ser_fw, np.abs(fitn[:, 6])), reps=1)
         gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
         prep = {"cutouts": P_, "n": n, "per_gpu": True,
                 "clipped_stats": {"value": P_ / (clip_ms * 1e-3), "unit": "cutouts/s", "kernel": "pm_clipstats_kernel<float>", "kernel_ms": clip_ms,
@@ -481,10 +488,13 @@ def run_ours(args):
                 "maskstarsSEG": {"value": P_ / (star_ms * 1e-3), "unit": "cutouts/s", "ms": star_ms, "algorithmic_gbs": gbs(2 * img_bytes, star_ms),
                                  "mean_segments": float(torch.as_tensor(star["info"])[:, 0].double().mean().item()),
                                  "note": "two clipped-statistics launches + the smooth/threshold/label/replace kernel (reads and writes the cutout)"}}
+        prep["fitSersic"] = {"value": S_n / (ser_ms * 1e-3), "unit": "cutouts/s", "ms": ser_ms, "cutouts": S_n,
+                             "ok_fraction": float(np.isin(ser["status"], (0, 1)).mean()), "mean_iterations": float(np.nanmean(ser["iterations"])),
+                             "note": "exact elliptical aperture sums (walk + bisection in lock-step, one launch per step) + Sersic2D fit"}
         prep["reference_default_flow"] = {"value": P_ / (flow_ms * 1e-3), "unit": "galaxies/s", "ms": flow_ms, "ok_fraction": flow_ok,
                                           "note": "main.py:349-495 as upstream runs it by default, on resident cutouts: skybgr, pixelmap with the sky in, "
                                                   "img - sky, maskstarsSEG, the statistics on the cleaned image (rows read back to the host)"}
-        del clip, fit, bgr, star, flow
+        del clip, fit, bgr, star, flow, ser, ser_in
 
     if rank != 0:
         if world > 1:
