@@ -14,7 +14,7 @@ Differences from upstream, all on purpose:
   * `--seed` seeds the cleaning noise of maskstarsSEG (unseeded upstream), `--no-clean` skips that step, `-S` adds the
     smoothness statistic (main.py:494 leaves the call commented out), `--device` picks the GPU;
   * `-par` / `-n` are accepted and ignored (the batch is the parallelism); `-sersic` fits the Sersic profile on the device
-    (sersic.py); `-spm`, `-sci`, `-cc`, `-segmap`, `-starmask`, `-d` and `-src LSST` belong to parts of the reference this build does not cover and raise NotImplementedError.
+    (sersic.py); `-cc` runs the star-catalogue flow; `-spm`, `-sci`, `-segmap`, `-starmask`, `-d` and `-src LSST` belong to parts of the reference this build does not cover and raise NotImplementedError.
 """
 import sys
 from argparse import ArgumentParser
@@ -36,7 +36,7 @@ def build_parser():
     parser.add_argument("-src", "--imgsource", type=str, default="SDSS", choices=["SDSS", "LSST"],
                         help="Telescope source of the image. Default is SDSS.")
     parser.add_argument("-s", "--imgsize", type=int, default=128, help="Size of image cutout to analyse")
-    parser.add_argument("-cc", "--catalogue", type=str, help="Star catalogue (not covered).")
+    parser.add_argument("-cc", "--catalogue", type=str, help="Star catalogue of the objects to mask (objID, ra, dec, psfMag_r, type)")
     parser.add_argument("-ns", "--numsig", type=float, default=5., help="Radial extent to which mask out stars if a catalogue is provided.")
     parser.add_argument("-fs", "--filtersize", type=int, default=3, choices=[1, 3, 5, 7, 9, 11, 13, 15], help="Size of kernel for mean filter")
     parser.add_argument("-par", "--parlib", type=str, default="none", choices=["multi", "parsl", "none"],

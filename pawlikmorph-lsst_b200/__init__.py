@@ -10,7 +10,7 @@ compute modules without the built library, or calling them without a CUDA device
 """
 from . import _abi  # noqa: F401
 
-__all__ = ["pixmap", "apertures", "asymmetry", "casgm", "result", "batch", "image", "helpers", "main", "skyBackground", "imageutils", "sersic"]
+__all__ = ["pixmap", "apertures", "asymmetry", "casgm", "result", "batch", "image", "helpers", "main", "skyBackground", "imageutils", "sersic", "objectMasker"]
 
 
 def __getattr__(name):

@@ -160,7 +160,7 @@ def _rotated_masks(star, angle, cx, cy):
     return (star.to(torch.uint8) * rot)
 
 
-def analyse_batch_starmask(images, sky, sky_err, starmask, filter_size=3, flags=PM_DO_ALL, stream=None):
+def analyse_batch_starmask(images, sky, sky_err, starmask, filter_size=3, flags=PM_DO_ALL, stream=None, cleaned=None):
     """The path with a star mask per cutout (1 = keep) — the `-starmask` flow of main.py:395-413 and what follows it:
     pixelmap(img, thr, fs, starMask) (pixmap.py:156-158), calcRmax without the mask, minapix on image * segmap * starMask
     (asymmetry.py:82-86), calcA with S = starMask * rotate(starMask) about apix, the segmap multiplied by S in place
@@ -168,6 +168,8 @@ def analyse_batch_starmask(images, sky, sky_err, starmask, filter_size=3, flags=
     A composition of launches of the fused kernel with its overrides (the mask changes between the steps once apix is
     known), for the rare catalogue / star-mask runs; `pm_analyse_batch` itself rejects `starmask`.  With noisecorrect the
     reference's result depends on ~1e-14 leakage of skimage's bilinear rotation of the mask; the exact 0/1 mask is used.
+    cleaned: CUDA float64 [B, n, n], the sky-subtracted image after main.py:442-445 (`img -= sky`, maskstarsSEG) — everything
+    after the pixelmap then runs on it, as in the catalogue flow of main.py:372-395; None: img - sky itself.
     Returns a BatchResult (rows + the pixelmap)."""
     if not torch.is_tensor(images) or not images.is_cuda:
         raise TypeError("analyse_batch_starmask needs a CUDA tensor (there is no CPU path)")
@@ -183,13 +185,15 @@ def analyse_batch_starmask(images, sky, sky_err, starmask, filter_size=3, flags=
     rows = p1.rows.clone()
     seg = p1.segmap
     ok = rows[:, col("status")] == 0
+    zero = torch.zeros_like(sky_t)
+    base, base_sky = (images, sky_t) if cleaned is None else (cleaned, zero)
     # 2. rmax from the unmasked image and the map (pixmap.calcRmax, main.py:463)
-    p2 = analyse_batch(images, sky_t, err_t, filter_size, _abi.PM_STOP_AFTER_RMAX, segmap_in=seg, **kw)
+    p2 = analyse_batch(base, base_sky, err_t, filter_size, _abi.PM_STOP_AFTER_RMAX, segmap_in=seg, **kw)
     rmax = p2.rows[:, col("rmax")].contiguous()
     rows[:, col("rmax")] = torch.where(ok, rmax, rows[:, col("rmax")])
     status2 = p2.rows[:, col("status")]
     # 3. minapix: image * segmap * starMask == the map with the masked pixels taken out
-    p3 = analyse_batch(images, sky_t, err_t, filter_size, 0, segmap_in=seg * star, radius_in=torch.where(rmax > 0, rmax, torch.ones_like(rmax)), **kw)
+    p3 = analyse_batch(base, base_sky, err_t, filter_size, 0, segmap_in=seg * star, radius_in=torch.where(rmax > 0, rmax, torch.ones_like(rmax)), **kw)
     for name in ("apix_col", "apix_row", "n_candidates"):
         rows[:, col(name)] = torch.where(ok, p3.rows[:, col(name)], rows[:, col(name)])
     status3 = p3.rows[:, col("status")]
@@ -199,8 +203,7 @@ def analyse_batch_starmask(images, sky, sky_err, starmask, filter_size=3, flags=
     good = ok & (status2 == 0) & (status3 == 0)
     # 4. A, Abgr, As, r20, r80, C, Gini, M20 on I = (img - sky) * S180 with the map * S180
     s180 = _rotated_masks(star, 180, cx, cy)
-    sub = images.to(torch.float64) - sky_t[:, None, None]
-    zero = torch.zeros_like(sky_t)
+    sub = images.to(torch.float64) - sky_t[:, None, None] if cleaned is None else cleaned
     seg180 = seg * s180
     f4 = flags & (_abi.PM_DO_A | _abi.PM_DO_AS | _abi.PM_DO_CAS)
     if f4:

@@ -5,7 +5,8 @@ with a 3 x 3 Gaussian kernel and npixels = 8 (:68-71); every segment whose bound
 an external source (:78-82) and is painted over with `np.random.normal(mean, std)` (:85-89).  The reference's generator is
 UNSEEDED, which makes its output irreproducible; here the normal deviate of (seed, cutout index, pixel index) comes from a
 counter-based generator (Philox4x32-10 + Box-Muller), the same on the device and in the CPU checker.
-`maskstarsPSF` and the catalogue helpers (:94-333) belong to the star-catalogue path and are not covered.
+`maskstarsPSF` and its helpers (:94-333, the star-catalogue path) are kept as host functions: a handful of circles per frame
+rasterised from header scalars and catalogue rows — there is no per-pixel work in them worth a kernel.
 """
 import numpy as np
 import torch
@@ -70,3 +71,96 @@ def maskstarsSEG(image, seed=0, device="cuda:0"):
     """imageutils.maskstarsSEG (imageutils.py:42-91) for one image: the cleaned image as a float64 numpy array."""
     x = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float64))[None].to(device)
     return maskstars_batch(x, seed=seed)["clean"][0].cpu().numpy()
+
+
+# ---- the star-catalogue path (imageutils.py:94-333): host functions ------------------------------------------------------
+def _circle_mask(shape, centre, radius):
+    """imageutils.py:94-132: boolean disc (x - cx)^2 + (y - cy)^2 <= radius^2 with x the FIRST array axis (the angular factor of
+    the original, theta % 2 pi <= 2 pi, is true everywhere except where theta is NaN)."""
+    x, y = np.ogrid[:shape[0], :shape[1]]
+    cx, cy = centre
+    r2 = (x - cx) * (x - cx) + (y - cy) * (y - cy)
+    theta = np.arctan2(x - cx, y - cy) % (2 * np.pi)
+    return (r2 <= radius * radius) * (theta <= 2. * np.pi)
+
+
+def _calculateRadius(y, A, sigma):
+    """imageutils.py:135-165: sigma * sqrt(|2 ln(A / y)|)"""
+    return sigma * np.sqrt(abs(2. * np.log(A / y)))
+
+
+def _subpixel_disc(shape, pixelPos, radius, subpixels=5):
+    """np.where(CircularAperture(pixelPos, r).to_mask(method="subpixel").to_image(shape) > 0, 1., 0.) (imageutils.py:243-245):
+    a pixel counts when any of its subpixels x subpixels sample points lies inside the circle (photutils' circular_overlap_grid
+    with use_exact = 0; pixel (row, col) is the unit square about (x, y) = (col, row))."""
+    out = np.zeros(shape)
+    px, py = float(pixelPos[0]), float(pixelPos[1])
+    if not (radius > 0) or not np.isfinite([px, py, radius]).all():
+        return out
+    c0, c1 = max(0, int(np.floor(px - radius - 0.5))), min(shape[1] - 1, int(np.ceil(px + radius + 0.5)))
+    r0, r1 = max(0, int(np.floor(py - radius - 0.5))), min(shape[0] - 1, int(np.ceil(py + radius + 0.5)))
+    if c1 < c0 or r1 < r0:
+        return out
+    off = (np.arange(subpixels) + 0.5) / subpixels - 0.5
+    ys = (np.arange(r0, r1 + 1)[:, None] + off[None, :]).ravel() - py
+    xs = (np.arange(c0, c1 + 1)[:, None] + off[None, :]).ravel() - px
+    inside = (ys[:, None] ** 2 + xs[None, :] ** 2) < radius * radius
+    hit = inside.reshape(r1 - r0 + 1, subpixels, c1 - c0 + 1, subpixels).any(axis=(1, 3))
+    out[r0:r1 + 1, c0:c1 + 1] = hit
+    return out
+
+
+def _calculateAdaptiveRadius(mask, pixelPos, image, skyCount, sky_err):
+    """imageutils.py:262-333: walk away from the image centre along the star's column; the run of consecutive profile points
+    above mean + sky_err gives the extra radius."""
+    maskedImage = image * ~mask + ((skyCount + 1000) * mask)
+    yinit = maskedImage[int(pixelPos[1]), int(pixelPos[0])]
+    imgsize = image.shape[0]
+    delta = 1 if pixelPos[1] > int(imgsize / 2) else -1
+    if pixelPos[1] >= imgsize - 1 or pixelPos[1] <= 0:
+        return 0
+    ypos = int(pixelPos[1]) + delta
+    ys = [yinit]
+    for _ in range(int(imgsize / 2)):
+        ys.append(maskedImage[ypos, int(pixelPos[0])])
+        ypos += delta
+        if ypos >= imgsize or ypos < 0:
+            break
+    thres = np.mean(ys) + sky_err
+    arr = np.where(ys > thres)[0]
+    i = 0                                   # (upstream leaves `i` unbound when nothing exceeds the threshold: UnboundLocalError)
+    for i, val in enumerate(arr):
+        if i + 1 > arr.shape[0] - 1:
+            break
+        if val + 1 != arr[i + 1]:
+            break
+    return i
+
+
+def maskstarsPSF(image, objs, header, skyCount, numSigmas=5., adaptive=True, sky_err=0.0):
+    """imageutils.py:168-259: mask (True = keep) of the catalogue stars `objs` ([ra, dec, type, psfMag_r] rows): for each a disc of
+    numSigmas * sigma_PSF * sqrt(|2 ln(psfMag / skyMag)|) pixels about its position, the sky magnitude from the SDSS photometric
+    header cards (asinh magnitudes).  header: mapping with PSF_S1, PSF_S2, EXPTIME, PHT_AA, PHT_KK, AIRMASS, SOFTBIAS, PHT_B
+    (KeyError when one is missing, which main.py:389-391 catches) and the WCS cards `image.sky_to_pixel` understands (TAN).
+    With no objects the mask is all ones, like upstream."""
+    from .image import sky_to_pixel
+    sigma1, sigma2 = header["PSF_S1"], header["PSF_S2"]
+    expTime, aa, kk = header["EXPTIME"], header["PHT_AA"], header["PHT_KK"]
+    airMass, softwareBias, b = header["AIRMASS"], header["SOFTBIAS"], header["PHT_B"]
+    skyCount = skyCount - softwareBias
+    factor = 0.4 * (aa + kk * airMass)
+    skyFluxRatio = (skyCount / expTime) * 10 ** factor
+    skyMag = -(2.5 / np.log(10.)) * (np.arcsinh(skyFluxRatio / (2 * b)) + np.log(b))
+    image = np.asarray(image)
+    if len(objs) == 0:
+        return np.ones_like(image)
+    starmask = np.zeros_like(image)
+    for obj in objs:
+        pixelPos = sky_to_pixel(header, obj[0], obj[1])
+        sigma = max(sigma1, sigma2)
+        radius = numSigmas * _calculateRadius(skyMag, obj[3], sigma)
+        starmask = np.logical_or(starmask, _circle_mask(starmask.shape, (pixelPos[1], pixelPos[0]), radius))
+        if adaptive:
+            extra = _calculateAdaptiveRadius(starmask, pixelPos, image, skyCount, sky_err)
+            starmask = np.logical_or(starmask, _subpixel_disc(image.shape, pixelPos, radius + extra))
+    return ~starmask

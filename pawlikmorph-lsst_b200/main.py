@@ -11,7 +11,9 @@ npix x npix window around the catalogue position is analysed (sky -> pixel on th
 on the device); otherwise the whole frame, like the reference.
 `skybgr` (skyBackground.py) and the `maskstarsSEG` cleaning (imageutils.py:42-91, with a seeded generator in place of the
 reference's unseeded one) run on the device too, and so does `fitSersic` (`calculateSersic`, sersic.py).  What is not here
-(DESIGN §7): star catalogues, segmap / clean-image FITS output, diagnostic plots.  Options that would need them raise NotImplementedError.
+(DESIGN §7): segmap / clean-image FITS input and output, diagnostic plots.  The star-catalogue flow (`catalogue`,
+main.py:372-395: objectOccluded, maskstarsPSF, the statistics with the mask) runs as host mask construction + the star-mask
+composition of batch.analyse_batch_starmask.  Options that would need them raise NotImplementedError.
 """
 import csv
 import os
@@ -67,11 +69,14 @@ def _decode_dtype(bitpix, bzero, bscale):
     return payload_dtype(bitpix, bzero, bscale)
 
 
-def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, sersic=False):
+def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, sersic=False, catalogue=None):
     """One group of equally sized cutouts that already live on the GPU through main.py:349-495: skybgr (unless sky is given),
     pixelmap on the image with the sky in (:421), `img -= sky`, maskstarsSEG (:442-445), the rest on the cleaned image.
     Returns rows [B, 16], sky, sky_err [B], fwhms [B, 2], theta [B] as numpy arrays — and, with sersic=True, the fitted Sersic2D
-    parameters [B, 7] of main.py:480-488 (-99 where there is no fit)."""
+    parameters [B, 7] of main.py:480-488 (-99 where there is no fit).
+    catalogue: dict(path, radec [B, 2], headers [B], numberSigmas) — the `-cc` flow of main.py:372-395: the catalogue objects
+    near each frame that fall on its pixelmap (objectOccluded), the PSF-sized star mask of those (maskstarsPSF, adaptive=False),
+    the pixelmap and all statistics with that mask; the return value then ends with (star_flag [B], masked fraction [B])."""
     import torch
 
     from .batch import analyse_batch
@@ -89,7 +94,41 @@ def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, s
     sky_d = torch.as_tensor(np.asarray(sky, dtype=np.float64), device=dev)
     err_d = torch.as_tensor(np.asarray(sky_err, dtype=np.float64), device=dev)
     final = None                                                          # the image fitSersic sees: img - sky, cleaned
-    if not clean:
+    star = None
+    star_flag, masked = np.zeros(B, dtype=bool), np.full(B, -99.0)
+    if catalogue is not None:
+        from .batch import analyse_batch_starmask
+        from .imageutils import maskstarsPSF
+        from .objectMasker import objectOccluded
+        from .pixmap import calcMaskedFraction
+        first = analyse_batch(images, sky_d, err_d, filterSize, flags | _abi.PM_STOP_AFTER_PIXELMAP, want_segmap=True)
+        rows1 = first.rows.cpu().numpy()
+        tmpmask = first.segmap.cpu().numpy()
+        n = int(images.shape[1])
+        masks = np.ones((B, n, n))
+        dummy = np.zeros((n, n))                                          # maskstarsPSF(adaptive=False) only takes the shape
+        for k in range(B):
+            if rows1[k, _abi.ROW_FIELDS.index("status")] != 0 or sky_fail[k]:
+                continue                                                  # main.py:375-378: no pixelmap, default Result
+            ra, dec = catalogue["radec"][k]
+            star_flag[k], objs = objectOccluded(tmpmask[k], (ra, dec), catalogue["path"], catalogue["headers"][k])
+            try:
+                masks[k] = maskstarsPSF(dummy, objs, catalogue["headers"][k], float(sky[k]), catalogue["numberSigmas"], adaptive=False)
+            except KeyError as e:                                         # main.py:389-391
+                print(e, ", so not using star catalogue to mask stars!")
+        star = torch.as_tensor(masks, device=dev)
+        sub = images.to(torch.float64) - sky_d[:, None, None]
+        final = maskstars_batch(sub, seed=seed)["clean"] if clean else sub
+        res = analyse_batch_starmask(images, sky_d, err_d, star, filterSize, flags, cleaned=final)
+        rows = res.rows.cpu().numpy()
+        col = _abi.ROW_FIELDS.index
+        early = rows1[:, col("status")] != 0                              # main.py:375-378: default Result, nothing else is computed
+        rows[early] = rows1[early]
+        if flags & (_abi.PM_DO_A | _abi.PM_DO_CAS):                       # main.py:472-474
+            for k in range(B):
+                if rows[k, col("status")] == 0 and not sky_fail[k]:
+                    masked[k] = calcMaskedFraction(tmpmask[k], masks[k], [rows[k, col("apix_col")], rows[k, col("apix_row")]])
+    elif not clean:
         rows = analyse_batch(images, sky_d, err_d, filterSize, flags).rows.cpu().numpy()
         if sersic:
             final = images.to(torch.float64) - sky_d[:, None, None]
@@ -108,8 +147,9 @@ def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, s
     rows[sky_fail] = -99.0
     rows[sky_fail, _abi.ROW_FIELDS.index("status")] = 1.0
     out = (rows, np.where(sky_fail, -99.0, sky), np.where(sky_fail, 99.0, sky_err), fwhms, theta)
+    tail = () if catalogue is None else (star_flag, masked)
     if not sersic:
-        return out
+        return out + tail
     # main.py:480-488: fitSersic(img, apix, fwhms, theta) on the analysed cutouts (apix = (x, y) = (column, row))
     from .sersic import fitSersic_batch
     col = _abi.ROW_FIELDS.index
@@ -117,10 +157,11 @@ def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, s
     okrow = np.nonzero((rows[:, col("status")] == 0) & ~sky_fail & (rows[:, col("apix_col")] >= 0))[0]
     if okrow.size:
         sel = final if okrow.size == B else final[torch.as_tensor(okrow, device=dev)]
-        fit = fitSersic_batch(sel, rows[okrow][:, [col("apix_col"), col("apix_row")]], fwhms[okrow], theta[okrow])
+        smask = None if star is None else (star if okrow.size == B else star[torch.as_tensor(okrow, device=dev)])
+        fit = fitSersic_batch(sel, rows[okrow][:, [col("apix_col"), col("apix_row")]], fwhms[okrow], theta[okrow], star_masks=smask)
         good = np.isin(fit["status"], (0, 1))
         ser[okrow[good]] = fit["params"][good]
-    return out + (ser,)
+    return out + (ser,) + tail
 
 
 def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filterSize=3, parallelLibrary="none", cores=1,
@@ -147,9 +188,11 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     `Cutout2D(mode="strict")` error), gets the default Result and the run carries on (main.py:331-339); so does a frame
     whose sky estimate fails (main.py:350-368)."""
     for name, val in (("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
-                      ("catalogue", catalogue), ("segmap", segmap), ("starMask", starMask)):
+                      ("segmap", segmap), ("starMask", starMask)):
         if val:
             raise NotImplementedError(f"{name}: outside the morphology path this package covers")
+    if catalogue and (gauss is not None or (sky is not None and not clean)):
+        raise NotImplementedError("catalogue: the star-catalogue flow runs in the device flow (sky=None, or a given sky with the cleaning step)")
     if calculateSersic and (sky is not None or gauss is not None):
         raise NotImplementedError("calculateSersic needs the widths and the angle of the sky estimate: run with sky=None, like upstream")
     if isinstance(sky, str) and sky == "border":
@@ -192,7 +235,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                     n_large = H                                                     # the whole frame
         except (OSError, AttributeError, PartialOverlapError, KeyError, ValueError) as e:
             print(f"{f}: {type(e).__name__}: {e} -- default Result")
-            frames.append([None, -99., 99., None, None])
+            frames.append([None, -99., 99., None, None, None])
             failed.add(i)
             continue
         pixels = None
@@ -205,7 +248,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
             s = sky(pixels)
         else:
             s = sky[i]
-        frames.append([payload, float(s[0]), float(s[1]), origin, origin_large])
+        frames.append([payload, float(s[0]), float(s[1]), origin, origin_large, hdr])
         key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)), n_large, origin_large is not None)
         groups.setdefault(key, []).append(i)
     flags = path_flags(asymmetry, shapeAsymmetry, allAsymmetry, CAS, smoothness)
@@ -214,6 +257,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
         rows[i, _abi.ROW_FIELDS.index("status")] = 1.0                         # -> the default Result (main.py:331-339)
     fw_all, th_all = np.full((len(infos), 2), -99.0), np.full(len(infos), -99.0)
     ser_all = np.full((len(infos), 7), -99.0)
+    flag_all, masked_all = np.zeros(len(infos), dtype=bool), np.full(len(infos), -99.0)
     for (n, H, W, windowed, bitpix, bzero, bscale, n_large, large_windowed), idx in groups.items():
         pay = np.empty((len(idx), H * W * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
         for k, i in enumerate(idx):
@@ -236,12 +280,18 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                 else:
                     large = decode_payload(pd, bitpix, (len(idx), H, W), bzero, bscale, dt)
             have_sky = sky is not None
+            cat = None
+            if catalogue:                                                       # main.py:372-395; the frame's own header, like upstream
+                cat = dict(path=str(catalogue), radec=[(infos[i][1], infos[i][2]) for i in idx], headers=[frames[i][5] for i in idx],
+                           numberSigmas=numberSigmas)
             got = _device_group(images, large, np.array([frames[i][1] for i in idx]) if have_sky else None,
                                 np.array([frames[i][2] for i in idx]) if have_sky else None, flags, filterSize, clean,
-                                seed, sersic=bool(calculateSersic))
+                                seed, sersic=bool(calculateSersic), catalogue=cat)
             r, sk, er, fw, th = got[:5]
             if calculateSersic:
                 ser_all[idx] = got[5]
+            if catalogue:
+                flag_all[idx], masked_all[idx] = got[-2], got[-1]
             rows[idx] = r
             fw_all[idx], th_all[idx] = fw, th
             for k, i in enumerate(idx):
@@ -270,6 +320,8 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
         if calculateSersic and r.status != 1:                                                              # main.py:480-488
             (r.sersic_amplitude, r.sersic_r_eff, r.sersic_n, r.sersic_x_0, r.sersic_y_0, r.sersic_ellip,
              r.sersic_theta) = (float(v) for v in ser_all[i])
+        if catalogue and r.status != 1:                                                                    # main.py:380-381, :472-474
+            r.star_flag, r.maskedPixelFraction = bool(flag_all[i]), float(masked_all[i])
         r.outfolder = str(outfolder)
         r.time = per_image
         results.append(r)

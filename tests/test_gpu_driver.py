@@ -1,6 +1,7 @@
 """The file driver end to end on the GPU: the reference's 69 + 69 SDSS frames (rewritten as FITS files from the golden
 fixtures, BITPIX 16 / BZERO 32768 like sample/) -> calcMorphology -> parameters.csv, against the golden rows."""
 import ast
+import os
 import csv
 
 import numpy as np
@@ -125,3 +126,68 @@ def test_calcMorphology_with_the_sky_measured_on_the_device(tmp_path):
             [d[f] for f in ("apix_col", "apix_row", "rmax", "C", "A", "Abgr", "S", "As", "gini", "m20")], k
     with pytest.raises(pm.skyBackground._SkyError):
         pm.main.calcMorphology(infos[:2], tmp_path / "o", gauss=[([60.0, 60.0], 0.0)] * 2, root=tmp_path)
+
+
+def test_catalogue_flow(tmp_path):
+    """calcMorphology(catalogue=...) — main.py:372-395: objectOccluded on the unmasked pixelmap, maskstarsPSF(adaptive=False), then the
+    pixelmap and the statistics with that mask (checked against the same steps done by hand with the batch calls), star_flag and
+    the masked pixel fraction in the Result."""
+    import json
+
+    import torch
+
+    import pawlikmorph_lsst_b200 as pm
+    import synth
+    from tests.fits_files import fits_bytes
+    A = pm._abi
+    wcs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sdss_wcs.json")))[0]
+    cards = dict(wcs["header"])
+    n = cards["NAXIS1"]
+    cards.update(PSF_S1=1.31, PSF_S2=2.94, EXPTIME=53.907456, PHT_AA=-24.05, PHT_KK=0.09, AIRMASS=1.19, SOFTBIAS=1000, PHT_B=1.2e-10)
+    x = synth.make_batch(2, n, 314).numpy() + 1000.0                       # counts with the SDSS software bias in
+    ra0, dec0 = wcs["ra"], wcs["dec"]
+    px, py = pm.image.sky_to_pixel(cards, ra0, dec0)
+    assert abs(px - n / 2) < 2 and abs(py - n / 2) < 2                     # the catalogue position is the frame centre
+    # a bright star on the object's wing and one far away; the far one must not reach the mask
+    rows_cat = ["objID,ra,dec,psfMag_r,type",
+                f"1,{ra0 + 0.0015},{dec0 + 0.0005},15.5,STAR", f"2,{ra0 - 0.0060},{dec0 - 0.0065},16.0,STAR", f"3,{ra0 + 0.001},{dec0},17.0,GALAXY"]
+    (tmp_path / "cat.csv").write_text("\n".join(rows_cat) + "\n")
+    names = []
+    for k in range(2):
+        (tmp_path / f"f{k}.fits").write_bytes(fits_bytes(x[k], -32, extra=cards))
+        names.append(f"f{k}.fits")
+    infos = [(nm, ra0, dec0) for nm in names]
+    sky = [(synth.SKY + 1000.0, synth.SKY_ERR)] * 2
+    res = pm.main.calcMorphology(infos, str(tmp_path / "out"), catalogue=str(tmp_path / "cat.csv"), sky=sky, root=str(tmp_path), seed=5, smoothness=True)
+    # by hand
+    dev = torch.device("cuda:0")
+    img = torch.from_numpy(x.astype(np.float32)).to(dev)
+    sky_d = torch.full((2,), synth.SKY + 1000.0, dtype=torch.float64, device=dev)
+    err_d = torch.full((2,), synth.SKY_ERR, dtype=torch.float64, device=dev)
+    first = pm.batch.analyse_batch(img, sky_d, err_d, 3, 15 | A.PM_STOP_AFTER_PIXELMAP, want_segmap=True)
+    tmp = first.segmap.cpu().numpy()
+    masks, flags = [], []
+    for k in range(2):
+        flag, objs = pm.objectMasker.objectOccluded(tmp[k], (ra0, dec0), str(tmp_path / "cat.csv"), cards)
+        flags.append(flag)
+        masks.append(pm.imageutils.maskstarsPSF(np.zeros((n, n)), objs, cards, synth.SKY + 1000.0, 5.0, adaptive=False))
+    assert flags == [True, True] and all(m.dtype == bool and (~m).sum() > 50 for m in masks)
+    star = torch.as_tensor(np.stack(masks).astype(np.float64), device=dev)
+    cleaned = pm.imageutils.maskstars_batch(img.to(torch.float64) - sky_d[:, None, None], seed=5)["clean"]
+    want = pm.batch.analyse_batch_starmask(img, sky_d, err_d, star, 3, 15, cleaned=cleaned).rows.cpu().numpy()
+    col = A.ROW_FIELDS.index
+    for k, r in enumerate(res):
+        assert r.status == 0 and r.star_flag is True
+        assert r.A == [want[k, col("A")], want[k, col("Abgr")]] or np.allclose(r.A, [want[k, col("A")], want[k, col("Abgr")]], rtol=1e-12)
+        assert np.isclose(np.ravel(r.As)[0], want[k, col("As")], rtol=1e-12) and np.isclose(r.r20, want[k, col("r20")], rtol=1e-12)
+        frac = pm.pixmap.calcMaskedFraction(tmp[k], masks[k].astype(np.float64), [want[k, col("apix_col")], want[k, col("apix_row")]])
+        assert 0.0 < r.maskedPixelFraction < 1.0 and np.isclose(r.maskedPixelFraction, frac, rtol=1e-12)
+    # the mask matters: the plain flow gives another pixelmap-dependent answer
+    plain = pm.main.calcMorphology(infos, str(tmp_path / "out2"), sky=sky, root=str(tmp_path), seed=5, smoothness=True)
+    assert plain[0].star_flag is False and plain[0].maskedPixelFraction == -99.0 and np.ravel(plain[0].As)[0] != np.ravel(res[0].As)[0]
+    # a header without the PSF cards: the catalogue is ignored with a message (main.py:389-391)
+    bare = {k: v for k, v in cards.items() if not k.startswith(("PSF_", "PHT_"))}
+    (tmp_path / "g.fits").write_bytes(fits_bytes(x[0], -32, extra=bare))
+    r2 = pm.main.calcMorphology([("g.fits", ra0, dec0)], str(tmp_path / "out3"), catalogue=str(tmp_path / "cat.csv"), sky=sky[:1], root=str(tmp_path),
+                                seed=5, smoothness=True)
+    assert r2[0].star_flag is True and np.isclose(np.ravel(r2[0].As)[0], np.ravel(plain[0].As)[0], rtol=1e-12) and r2[0].maskedPixelFraction == 0.0
