@@ -467,7 +467,7 @@ def run_ours(args):
         bgr_ms, bgr = timed(lambda: pm.skyBackground.skybgr_batch(xp))
         star_ms, star = timed(lambda: pm.imageutils.maskstars_batch(xp, seed=1))
         flow_ms, flow = timed(lambda: pm.main._device_group(xp, None, None, None, FLAGS_ALL, 3, True, 1), reps=1)
-        flow_ok = float((flow[0][:, pm._abi.ROW_FIELDS.index("status")] == 0).mean())
+        flow_ok = float((flow["rows"][:, pm._abi.ROW_FIELDS.index("status")] == 0).mean())
         # fitSersic on the sky-subtracted cutouts with the widths / angle of the Gaussian fit and the apix of the rows
         S_n = min(P_, 2048)
         fitn = fit[:S_n].cpu().numpy()

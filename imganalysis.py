@@ -14,7 +14,9 @@ Differences from upstream, all on purpose:
   * `--seed` seeds the cleaning noise of maskstarsSEG (unseeded upstream), `--no-clean` skips that step, `-S` adds the
     smoothness statistic (main.py:494 leaves the call commented out), `--device` picks the GPU;
   * `-par` / `-n` are accepted and ignored (the batch is the parallelism); `-sersic` fits the Sersic profile on the device
-    (sersic.py); `-cc` runs the star-catalogue flow; `-spm`, `-sci`, `-segmap`, `-starmask`, `-d` and `-src LSST` belong to parts of the reference this build does not cover and raise NotImplementedError.
+    (sersic.py); `-cc` runs the star-catalogue flow, `-segmap` / `-starmask` read `segmap_<name>` / `starmask_<name>` from the output
+    folder and `-spm` / `-sci` write `segmap_<name>` / `clean_<name>` there, like upstream; `-d` (matplotlib plots) and `-src LSST`
+    (data butler) are not covered and raise NotImplementedError.
 """
 import sys
 from argparse import ArgumentParser

@@ -65,6 +65,44 @@ def payload_of(raw: bytes):
     return raw[off:off + nbytes], hdr
 
 
+def header_cards(raw: bytes):
+    """The 80-character cards of the primary header of a FITS file image held in memory (without END)."""
+    cards, off = [], 0
+    while True:
+        block = raw[off:off + 2880]
+        if len(block) < 2880:
+            raise IOError("truncated FITS header")
+        off += 2880
+        for i in range(0, 2880, 80):
+            card = block[i:i + 80].decode("ascii", "replace")
+            if card[:8].strip() == "END":
+                return cards
+            cards.append(card)
+
+
+def fits_image_bytes(data, cards=()):
+    """What `fits.PrimaryHDU(data=data, header=header).writeto(...)` stores for a 2-D float64 array (main.py:447-461: the clean image
+    and the pixelmap): the mandatory cards for BITPIX -64, then the cards of the source header except the structural and scaling
+    ones, big-endian pixels, 2880-byte blocks."""
+    a = np.ascontiguousarray(np.asarray(data, dtype=np.float64))
+    if a.ndim != 2:
+        raise ValueError("fits_image_bytes: a 2-D image")
+
+    def card(key, val, comment=""):
+        v = f"{'T' if val else 'F':>20}" if isinstance(val, bool) else f"{val:>20}"
+        return f"{key:<8}= {v}{' / ' + comment if comment else ''}".ljust(80)[:80]
+
+    out = [card("SIMPLE", True, "conforms to FITS standard"), card("BITPIX", -64, "array data type"), card("NAXIS", 2, "number of array dimensions"),
+           card("NAXIS1", a.shape[1]), card("NAXIS2", a.shape[0])]
+    skip = {"SIMPLE", "BITPIX", "NAXIS", "NAXIS1", "NAXIS2", "BZERO", "BSCALE", "EXTEND", "END"}
+    out += [c.ljust(80)[:80] for c in cards if c[:8].strip() not in skip]
+    out.append("END".ljust(80))
+    head = "".join(out).encode("ascii", "replace")
+    head += b" " * (-len(head) % 2880)
+    body = a.astype(">f8").tobytes()
+    return head + body + b"\0" * (-len(body) % 2880)
+
+
 def decode_payload(payload, bitpix, shape, bzero=0.0, bscale=1.0, dtype=torch.float32, stream=None):
     """Decode big-endian FITS pixels that already live on the GPU.
 

@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from . import _abi
-from .image import BYTES_PER_PIXEL, PartialOverlapError, cutout_origin, payload_of, sky_to_pixel
+from .image import BYTES_PER_PIXEL, PartialOverlapError, cutout_origin, header_cards, payload_of, sky_to_pixel
 from .result import CSV_HEADER, Result
 
 _NP = {8: ">u1", 16: ">i2", 32: ">i4", -32: ">f4", -64: ">f8"}
@@ -69,20 +69,26 @@ def _decode_dtype(bitpix, bzero, bscale):
     return payload_dtype(bitpix, bzero, bscale)
 
 
-def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, sersic=False, catalogue=None):
+def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, sersic=False, catalogue=None, star_masks=None,
+                  segmaps=None, want_maps=False):
     """One group of equally sized cutouts that already live on the GPU through main.py:349-495: skybgr (unless sky is given),
     pixelmap on the image with the sky in (:421), `img -= sky`, maskstarsSEG (:442-445), the rest on the cleaned image.
-    Returns rows [B, 16], sky, sky_err [B], fwhms [B, 2], theta [B] as numpy arrays — and, with sersic=True, the fitted Sersic2D
-    parameters [B, 7] of main.py:480-488 (-99 where there is no fit).
-    catalogue: dict(path, radec [B, 2], headers [B], numberSigmas) — the `-cc` flow of main.py:372-395: the catalogue objects
-    near each frame that fall on its pixelmap (objectOccluded), the PSF-sized star mask of those (maskstarsPSF, adaptive=False),
-    the pixelmap and all statistics with that mask; the return value then ends with (star_flag [B], masked fraction [B])."""
+    Returns a dict of numpy arrays: rows [B, 16], sky, sky_err [B], fwhms [B, 2], theta [B], and
+      sersic [B, 7]              with sersic=True: the fitted Sersic2D parameters of main.py:480-488 (-99 where there is no fit);
+      star_flag, masked [B]      with catalogue = dict(path, radec [B, 2], headers [B], numberSigmas) — the `-cc` flow of
+                                 main.py:372-395: the catalogue objects near each frame that fall on its pixelmap (objectOccluded), the
+                                 PSF-sized star mask of those (maskstarsPSF, adaptive=False), the pixelmap and all statistics with it;
+      segmap, clean              with want_maps=True: the pixelmaps [B, n, n] uint8 and the analysed images (img - sky, cleaned)
+                                 [B, n, n] float64 as CUDA tensors (main.py:447-461 writes them out).
+    star_masks: CUDA [B, n, n] (1 = keep), the `-starmask` flow of main.py:397-417; segmaps: CUDA [B, n, n] uint8, the `-segmap` flow
+    of :429-440 (no pixelmap, no edge flag)."""
     import torch
 
-    from .batch import analyse_batch
+    from .batch import analyse_batch, analyse_batch_starmask
     from .imageutils import maskstars_batch
     from .skyBackground import skybgr_batch
-    B = int(images.shape[0])
+    B, n = int(images.shape[0]), int(images.shape[1])
+    col = _abi.ROW_FIELDS.index
     fwhms, theta = np.full((B, 2), -99.0), np.full(B, -99.0)
     sky_fail = np.zeros(B, dtype=bool)
     if sky is None:
@@ -93,75 +99,80 @@ def _device_group(images, large, sky, sky_err, flags, filterSize, clean, seed, s
     dev = images.device
     sky_d = torch.as_tensor(np.asarray(sky, dtype=np.float64), device=dev)
     err_d = torch.as_tensor(np.asarray(sky_err, dtype=np.float64), device=dev)
-    final = None                                                          # the image fitSersic sees: img - sky, cleaned
-    star = None
+    zero = torch.zeros_like(sky_d)
+    need_final = clean or sersic or want_maps or catalogue is not None or star_masks is not None or segmaps is not None
+    final = None                                                          # the image everything after the pixelmap sees
+    if need_final:
+        final = images.to(torch.float64) - sky_d[:, None, None]           # main.py:442
+        if clean:
+            final = maskstars_batch(final, seed=seed)["clean"]            # main.py:445
+    star, segmap_d = None, None
     star_flag, masked = np.zeros(B, dtype=bool), np.full(B, -99.0)
-    if catalogue is not None:
-        from .batch import analyse_batch_starmask
-        from .imageutils import maskstarsPSF
-        from .objectMasker import objectOccluded
-        from .pixmap import calcMaskedFraction
+    if segmaps is not None:                                               # main.py:429-440
+        segmap_d = segmaps
+        rows = analyse_batch(final, zero, err_d, filterSize, flags, segmap_in=segmaps, smooth_sky_in=sky_d).rows.cpu().numpy()
+        rows[:, col("object_edge")] = 0.0
+    elif catalogue is not None or star_masks is not None:
         first = analyse_batch(images, sky_d, err_d, filterSize, flags | _abi.PM_STOP_AFTER_PIXELMAP, want_segmap=True)
         rows1 = first.rows.cpu().numpy()
-        tmpmask = first.segmap.cpu().numpy()
-        n = int(images.shape[1])
-        masks = np.ones((B, n, n))
-        dummy = np.zeros((n, n))                                          # maskstarsPSF(adaptive=False) only takes the shape
-        for k in range(B):
-            if rows1[k, _abi.ROW_FIELDS.index("status")] != 0 or sky_fail[k]:
-                continue                                                  # main.py:375-378: no pixelmap, default Result
-            ra, dec = catalogue["radec"][k]
-            star_flag[k], objs = objectOccluded(tmpmask[k], (ra, dec), catalogue["path"], catalogue["headers"][k])
-            try:
-                masks[k] = maskstarsPSF(dummy, objs, catalogue["headers"][k], float(sky[k]), catalogue["numberSigmas"], adaptive=False)
-            except KeyError as e:                                         # main.py:389-391
-                print(e, ", so not using star catalogue to mask stars!")
-        star = torch.as_tensor(masks, device=dev)
-        sub = images.to(torch.float64) - sky_d[:, None, None]
-        final = maskstars_batch(sub, seed=seed)["clean"] if clean else sub
+        if catalogue is not None:
+            from .imageutils import maskstarsPSF
+            from .objectMasker import objectOccluded
+            tmpmask = first.segmap.cpu().numpy()
+            masks = np.ones((B, n, n))
+            dummy = np.zeros((n, n))                                      # maskstarsPSF(adaptive=False) only takes the shape
+            for k in range(B):
+                if rows1[k, col("status")] != 0 or sky_fail[k]:
+                    continue                                              # main.py:375-378: no pixelmap, default Result
+                ra, dec = catalogue["radec"][k]
+                star_flag[k], objs = objectOccluded(tmpmask[k], (ra, dec), catalogue["path"], catalogue["headers"][k])
+                try:
+                    masks[k] = maskstarsPSF(dummy, objs, catalogue["headers"][k], float(sky[k]), catalogue["numberSigmas"], adaptive=False)
+                except KeyError as e:                                     # main.py:389-391
+                    print(e, ", so not using star catalogue to mask stars!")
+            star = torch.as_tensor(masks, device=dev)
+        else:
+            star = star_masks.to(device=dev, dtype=torch.float64)
         res = analyse_batch_starmask(images, sky_d, err_d, star, filterSize, flags, cleaned=final)
         rows = res.rows.cpu().numpy()
-        col = _abi.ROW_FIELDS.index
-        early = rows1[:, col("status")] != 0                              # main.py:375-378: default Result, nothing else is computed
+        segmap_d = res.segmap
+        early = rows1[:, col("status")] != 0                              # main.py:375-378, :401-405: default Result, nothing else is computed
         rows[early] = rows1[early]
-        if flags & (_abi.PM_DO_A | _abi.PM_DO_CAS):                       # main.py:472-474
+        if catalogue is not None and flags & (_abi.PM_DO_A | _abi.PM_DO_CAS):          # main.py:472-474
+            from .pixmap import calcMaskedFraction
             for k in range(B):
                 if rows[k, col("status")] == 0 and not sky_fail[k]:
                     masked[k] = calcMaskedFraction(tmpmask[k], masks[k], [rows[k, col("apix_col")], rows[k, col("apix_row")]])
-    elif not clean:
+    elif not clean and not want_maps:
         rows = analyse_batch(images, sky_d, err_d, filterSize, flags).rows.cpu().numpy()
-        if sersic:
-            final = images.to(torch.float64) - sky_d[:, None, None]
     else:
         first = analyse_batch(images, sky_d, err_d, filterSize, flags | _abi.PM_STOP_AFTER_PIXELMAP, want_segmap=True)
-        sub = images.to(torch.float64) - sky_d[:, None, None]                                   # main.py:442
-        cleaned = maskstars_batch(sub, seed=seed)["clean"]                                       # main.py:445
         rows1 = first.rows.cpu().numpy()
-        rows = analyse_batch(cleaned, torch.zeros_like(sky_d), err_d, filterSize, flags, segmap_in=first.segmap,
-                             smooth_sky_in=sky_d).rows.cpu().numpy()
-        col = _abi.ROW_FIELDS.index
+        segmap_d = first.segmap
+        rows = analyse_batch(final, zero, err_d, filterSize, flags, segmap_in=first.segmap, smooth_sky_in=sky_d).rows.cpu().numpy()
         rows[:, col("object_edge")] = rows1[:, col("object_edge")]                               # main.py:427 (pixelmap path)
         faint = rows1[:, col("status")] == 1
         rows[faint] = rows1[faint]                                                               # main.py:420-424
-        final = cleaned
     rows[sky_fail] = -99.0
-    rows[sky_fail, _abi.ROW_FIELDS.index("status")] = 1.0
-    out = (rows, np.where(sky_fail, -99.0, sky), np.where(sky_fail, 99.0, sky_err), fwhms, theta)
-    tail = () if catalogue is None else (star_flag, masked)
-    if not sersic:
-        return out + tail
-    # main.py:480-488: fitSersic(img, apix, fwhms, theta) on the analysed cutouts (apix = (x, y) = (column, row))
-    from .sersic import fitSersic_batch
-    col = _abi.ROW_FIELDS.index
-    ser = np.full((B, 7), -99.0)
-    okrow = np.nonzero((rows[:, col("status")] == 0) & ~sky_fail & (rows[:, col("apix_col")] >= 0))[0]
-    if okrow.size:
-        sel = final if okrow.size == B else final[torch.as_tensor(okrow, device=dev)]
-        smask = None if star is None else (star if okrow.size == B else star[torch.as_tensor(okrow, device=dev)])
-        fit = fitSersic_batch(sel, rows[okrow][:, [col("apix_col"), col("apix_row")]], fwhms[okrow], theta[okrow], star_masks=smask)
-        good = np.isin(fit["status"], (0, 1))
-        ser[okrow[good]] = fit["params"][good]
-    return out + (ser,) + tail
+    rows[sky_fail, col("status")] = 1.0
+    out = dict(rows=rows, sky=np.where(sky_fail, -99.0, sky), sky_err=np.where(sky_fail, 99.0, sky_err), fwhms=fwhms, theta=theta,
+               star_flag=star_flag, masked=masked)
+    if want_maps:
+        out["segmap"], out["clean"] = segmap_d, final
+    if sersic:
+        # main.py:480-488: fitSersic(img, apix, fwhms, theta, starMask) on the analysed cutouts (apix = (x, y) = (column, row))
+        from .sersic import fitSersic_batch
+        ser = np.full((B, 7), -99.0)
+        okrow = np.nonzero((rows[:, col("status")] == 0) & ~sky_fail & (rows[:, col("apix_col")] >= 0))[0]
+        if okrow.size:
+            pick = None if okrow.size == B else torch.as_tensor(okrow, device=dev)
+            sel = final if pick is None else final[pick]
+            smask = None if star is None else (star if pick is None else star[pick])
+            fit = fitSersic_batch(sel, rows[okrow][:, [col("apix_col"), col("apix_row")]], fwhms[okrow], theta[okrow], star_masks=smask)
+            good = np.isin(fit["status"], (0, 1))
+            ser[okrow[good]] = fit["params"][good]
+        out["sersic"] = ser
+    return out
 
 
 def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filterSize=3, parallelLibrary="none", cores=1,
@@ -187,12 +198,13 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     frame, as upstream); a frame that cannot be read, or whose window leaves it (image.PartialOverlapError, the
     `Cutout2D(mode="strict")` error), gets the default Result and the run carries on (main.py:331-339); so does a frame
     whose sky estimate fails (main.py:350-368)."""
-    for name, val in (("saveSegMap", saveSegMap), ("saveCleanImage", saveCleanImage),
-                      ("segmap", segmap), ("starMask", starMask)):
-        if val:
-            raise NotImplementedError(f"{name}: outside the morphology path this package covers")
-    if catalogue and (gauss is not None or (sky is not None and not clean)):
-        raise NotImplementedError("catalogue: the star-catalogue flow runs in the device flow (sky=None, or a given sky with the cleaning step)")
+    special = bool(catalogue or segmap or starMask or saveSegMap or saveCleanImage or calculateSersic)
+    if segmap and (catalogue or starMask):                                    # imganalysis.py:75-83
+        raise ValueError("Can't provide both a precomputed segmentation map and a star catalogue / star mask file!")
+    if starMask and catalogue:
+        raise ValueError("Can't provide both a star catalogue and precomputed star mask file!")
+    if special and gauss is not None:
+        raise NotImplementedError("catalogue / segmap / starMask / saveSegMap / saveCleanImage / calculateSersic run in the device flow (gauss=None)")
     if calculateSersic and (sky is not None or gauss is not None):
         raise NotImplementedError("calculateSersic needs the widths and the angle of the sky estimate: run with sky=None, like upstream")
     if isinstance(sky, str) and sky == "border":
@@ -201,14 +213,16 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     infos = [(str(f), ra, dec) for f, ra, dec in imageInfos]
     t0 = time.time()
     frames, groups, failed = [], {}, set()
-    device_path = (sky is None and gauss is None) or clean
+    device_path = (sky is None and gauss is None) or clean or special
     for i, (f, _, _) in enumerate(infos):
         path = f if root is None or os.path.isabs(f) else os.path.join(str(root), f)
         # main.py:331-339: an image that cannot be read or cut (IOError, AttributeError, PartialOverlapError) gets the
         # default Result and the run carries on with the others
         try:
             with open(path, "rb") as fh:
-                payload, hdr = payload_of(fh.read())
+                raw_file = fh.read()
+            payload, hdr = payload_of(raw_file)
+            cards_of_frame = header_cards(raw_file) if (saveSegMap or saveCleanImage) else None
             if hdr.get("NAXIS", 2) != 2:
                 raise ValueError(f"{f}: not a 2-D image")
             H, W = hdr["NAXIS2"], hdr["NAXIS1"]
@@ -235,7 +249,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
                     n_large = H                                                     # the whole frame
         except (OSError, AttributeError, PartialOverlapError, KeyError, ValueError) as e:
             print(f"{f}: {type(e).__name__}: {e} -- default Result")
-            frames.append([None, -99., 99., None, None, None])
+            frames.append([None, -99., 99., None, None, None, None])
             failed.add(i)
             continue
         pixels = None
@@ -248,7 +262,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
             s = sky(pixels)
         else:
             s = sky[i]
-        frames.append([payload, float(s[0]), float(s[1]), origin, origin_large, hdr])
+        frames.append([payload, float(s[0]), float(s[1]), origin, origin_large, hdr, cards_of_frame])
         key = (n, H, W, origin is not None, hdr["BITPIX"], float(hdr.get("BZERO", 0.0)), float(hdr.get("BSCALE", 1.0)), n_large, origin_large is not None)
         groups.setdefault(key, []).append(i)
     flags = path_flags(asymmetry, shapeAsymmetry, allAsymmetry, CAS, smoothness)
@@ -258,6 +272,7 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
     fw_all, th_all = np.full((len(infos), 2), -99.0), np.full(len(infos), -99.0)
     ser_all = np.full((len(infos), 7), -99.0)
     flag_all, masked_all = np.zeros(len(infos), dtype=bool), np.full(len(infos), -99.0)
+    saved = [dict() for _ in infos]
     for (n, H, W, windowed, bitpix, bzero, bscale, n_large, large_windowed), idx in groups.items():
         pay = np.empty((len(idx), H * W * BYTES_PER_PIXEL[bitpix]), dtype=np.uint8)
         for k, i in enumerate(idx):
@@ -284,14 +299,46 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
             if catalogue:                                                       # main.py:372-395; the frame's own header, like upstream
                 cat = dict(path=str(catalogue), radec=[(infos[i][1], infos[i][2]) for i in idx], headers=[frames[i][5] for i in idx],
                            numberSigmas=numberSigmas)
+            # precomputed maps of the -segmap / -starmask flows: <outfolder>/segmap_<name>, starmask_<name> (main.py:407-414, :431-438)
+            def maps_of(prefix):
+                arr = np.empty((len(idx), n, n), dtype=np.float64)
+                for k, i in enumerate(idx):
+                    with open(os.path.join(str(outfolder), prefix + os.path.basename(infos[i][0])), "rb") as fh:
+                        p_, h_ = payload_of(fh.read())
+                    a_ = _host_pixels(p_, h_)
+                    if a_.shape != (n, n):
+                        raise ValueError(f"{prefix}{os.path.basename(infos[i][0])}: {a_.shape}, expected {(n, n)}")
+                    arr[k] = a_
+                return arr
+            seg_in = torch.as_tensor((maps_of("segmap_") != 0).astype(np.uint8), device=device) if segmap else None
+            star_in = torch.as_tensor(maps_of("starmask_"), device=device) if starMask else None
+            want_maps = bool(saveSegMap or saveCleanImage)
             got = _device_group(images, large, np.array([frames[i][1] for i in idx]) if have_sky else None,
                                 np.array([frames[i][2] for i in idx]) if have_sky else None, flags, filterSize, clean,
-                                seed, sersic=bool(calculateSersic), catalogue=cat)
-            r, sk, er, fw, th = got[:5]
+                                seed, sersic=bool(calculateSersic), catalogue=cat, star_masks=star_in, segmaps=seg_in, want_maps=want_maps)
+            r, sk, er, fw, th = got["rows"], got["sky"], got["sky_err"], got["fwhms"], got["theta"]
             if calculateSersic:
-                ser_all[idx] = got[5]
+                ser_all[idx] = got["sersic"]
             if catalogue:
-                flag_all[idx], masked_all[idx] = got[-2], got[-1]
+                flag_all[idx], masked_all[idx] = got["star_flag"], got["masked"]
+            if want_maps:                                                       # main.py:447-461 (float64 images under the frame's header)
+                from .image import fits_image_bytes
+                os.makedirs(str(outfolder), exist_ok=True)
+                seg_h = got["segmap"].cpu().numpy() if saveSegMap and got["segmap"] is not None else None
+                cln_h = got["clean"].cpu().numpy() if saveCleanImage else None
+                for k, i in enumerate(idx):
+                    if r[k, _abi.ROW_FIELDS.index("status")] == 1:
+                        continue                                                # default Result: upstream returned before writing
+                    name = os.path.basename(infos[i][0])
+                    cards = frames[i][6]
+                    if cln_h is not None:
+                        saved[i]["clean"] = os.path.join(str(outfolder), "clean_" + name)
+                        with open(saved[i]["clean"], "wb") as fh:
+                            fh.write(fits_image_bytes(cln_h[k], cards))
+                    if seg_h is not None:
+                        saved[i]["segmap"] = os.path.join(str(outfolder), "segmap_" + name)
+                        with open(saved[i]["segmap"], "wb") as fh:
+                            fh.write(fits_image_bytes(seg_h[k], cards))
             rows[idx] = r
             fw_all[idx], th_all[idx] = fw, th
             for k, i in enumerate(idx):
@@ -322,6 +369,10 @@ def calcMorphology(imageInfos, outfolder, largeImgFactor=None, npix=None, filter
              r.sersic_theta) = (float(v) for v in ser_all[i])
         if catalogue and r.status != 1:                                                                    # main.py:380-381, :472-474
             r.star_flag, r.maskedPixelFraction = bool(flag_all[i]), float(masked_all[i])
+        if "clean" in saved[i]:
+            r.cleanImage = saved[i]["clean"]                                                              # main.py:451
+        if "segmap" in saved[i]:
+            r.pixelMapFile = saved[i]["segmap"]                                                            # main.py:459
         r.outfolder = str(outfolder)
         r.time = per_image
         results.append(r)

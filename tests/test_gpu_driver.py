@@ -191,3 +191,60 @@ def test_catalogue_flow(tmp_path):
     r2 = pm.main.calcMorphology([("g.fits", ra0, dec0)], str(tmp_path / "out3"), catalogue=str(tmp_path / "cat.csv"), sky=sky[:1], root=str(tmp_path),
                                 seed=5, smoothness=True)
     assert r2[0].star_flag is True and np.isclose(np.ravel(r2[0].As)[0], np.ravel(plain[0].As)[0], rtol=1e-12) and r2[0].maskedPixelFraction == 0.0
+
+
+def test_segmap_starmask_and_saved_maps(tmp_path):
+    """-spm / -sci write segmap_<name> / clean_<name> (float64 FITS under the frame's header, main.py:447-461); -segmap reads the
+    pixelmaps back (main.py:429-440: no pixelmap, no edge flag) and gives the same statistics; -starmask reads starmask_<name>
+    (main.py:397-417) and matches the star-mask composition."""
+    import torch
+
+    import pawlikmorph_lsst_b200 as pm
+    import synth
+    A = pm._abi
+    n = 128
+    x = synth.make_batch(3, n, 2718).numpy()
+    names = []
+    for k in range(3):
+        (tmp_path / f"m{k}.fits").write_bytes(fits_bytes(x[k], -32))
+        names.append(f"m{k}.fits")
+    infos = [(nm, 0.0, 0.0) for nm in names]
+    sky = [(synth.SKY, synth.SKY_ERR)] * 3
+    out = tmp_path / "out"
+    base = pm.main.calcMorphology(infos, str(out), sky=sky, root=str(tmp_path), seed=9, smoothness=True, saveSegMap=True, saveCleanImage=True)
+    dev = torch.device("cuda:0")
+    img = torch.from_numpy(x).to(dev)
+    sky_d = torch.full((3,), synth.SKY, dtype=torch.float64, device=dev)
+    err_d = torch.full((3,), synth.SKY_ERR, dtype=torch.float64, device=dev)
+    seg = pm.batch.analyse_batch(img, sky_d, err_d, 3, 15 | A.PM_STOP_AFTER_PIXELMAP, want_segmap=True).segmap.cpu().numpy()
+    cleaned = pm.imageutils.maskstars_batch(img.to(torch.float64) - sky_d[:, None, None], seed=9)["clean"].cpu().numpy()
+    for k, r in enumerate(base):
+        assert r.pixelMapFile == str(out / f"segmap_m{k}.fits") and r.cleanImage == str(out / f"clean_m{k}.fits")
+        for path, want in ((r.pixelMapFile, seg[k].astype(np.float64)), (r.cleanImage, cleaned[k])):
+            pay, hdr = pm.image.payload_of(open(path, "rb").read())
+            assert hdr["BITPIX"] == -64 and hdr["NAXIS1"] == n and hdr["CTYPE1"] == "RA---TAN"
+            assert np.array_equal(np.frombuffer(pay, dtype=">f8").reshape(n, n), want)
+    again = pm.main.calcMorphology(infos, str(out), sky=sky, root=str(tmp_path), seed=9, smoothness=True, segmap=True)
+    for a, b in zip(again, base):
+        assert a.objectEdge is False
+        for f in ("A", "As", "As90", "r20", "r80", "C", "S", "gini", "m20", "rmax", "apix"):
+            assert np.allclose(np.ravel(getattr(a, f)).astype(float), np.ravel(getattr(b, f)).astype(float), rtol=1e-12), f
+    # star masks from files
+    rng = np.random.default_rng(4)
+    star = np.ones((3, n, n))
+    for k in range(3):
+        r0, c0 = rng.integers(10, n - 30, 2)
+        star[k, r0:r0 + 12, c0:c0 + 9] = 0
+        star[k, n // 2 - 3:n // 2 + 4, n // 2 - 3:n // 2 + 4] = 1
+        (out / f"starmask_m{k}.fits").write_bytes(pm.image.fits_image_bytes(star[k]))
+    masked = pm.main.calcMorphology(infos, str(out), sky=sky, root=str(tmp_path), seed=9, smoothness=True, starMask=True)
+    want = pm.batch.analyse_batch_starmask(img, sky_d, err_d, torch.from_numpy(star).to(dev), 3, 15,
+                                           cleaned=torch.from_numpy(cleaned).to(dev)).rows.cpu().numpy()
+    col = A.ROW_FIELDS.index
+    for k, r in enumerate(masked):
+        assert r.status == 0 and r.star_flag is False and r.maskedPixelFraction == -99.0
+        assert np.allclose([r.A[0], np.ravel(r.As)[0], r.r20, r.gini], [want[k, col("A")], want[k, col("As")], want[k, col("r20")], want[k, col("gini")]], rtol=1e-12)
+    with pytest.raises(ValueError):
+        pm.main.calcMorphology(infos, str(out), sky=sky, root=str(tmp_path), segmap=True, starMask=True)
+    with pytest.raises(OSError):
+        pm.main.calcMorphology(infos, str(tmp_path / "empty"), sky=sky, root=str(tmp_path), segmap=True)
