@@ -354,7 +354,7 @@ PM_DEV void gaussfit_body(const T* images, long long B, int n, const double* med
 // asymptotic value a - 1/3 + 8 / (405 a) (Ciotti & Bertin 1999 for b_n with a = 2 n)
 PM_DEV double gamma_p_series(double a, double x) {
     double term = 1.0 / a, sum = term;
-    for (int k = 1; k < 500; k++) {
+    for (int k = 1; k < 4000; k++) {                 // (terms grow until k ~ x - a: enough for any index a fit visits)
         term *= x / (a + (double)k);
         sum += term;
         if (fabs(term) < fabs(sum) * 1e-17) break;
