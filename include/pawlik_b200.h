@@ -178,6 +178,10 @@ int pm_sky_stats_batch(const void *images, int dtype, int64_t B, int n, const do
  * out: DEVICE double [B, PM_CLIP_COLS] = count, mean, median, std, clip iterations, clipped count, mean, median, std, max. */
 #define PM_CLIP_COLS 10
 int pm_clipped_stats_batch(const void *images, int dtype, int64_t B, int n, double sigma, int maxiters, double *out, void *cuda_stream);
+/* The same for two stopping rules from ONE sequence of clipping rounds: out_first = the rows of maxiters = maxiters_first (>= 1),
+ * out_converged = the rows of maxiters = None (imageutils.py:62 and :67 ask for both of the same image). */
+int pm_clipped_stats2_batch(const void *images, int dtype, int64_t B, int n, double sigma, int maxiters_first, double *out_first,
+                            double *out_converged, void *cuda_stream);
 
 /* How pm_sky_stats_batch (with_mask = 1) / pm_clipped_stats_batch (with_mask = 0) run a cutout size: CTAs per thread-block
  * cluster sharing one cutout (1, 2, 4 or 8), whether the cutout is held in the cluster's shared memory (read from HBM once) or

@@ -43,7 +43,7 @@ class Outputs(C.Structure):
 
 EXPORTS = ("pm_abi_version", "pm_device_info", "pm_last_cuda_error", "pm_launch_count",
            "pm_workspace_bytes", "pm_analyse_batch", "pm_aperpixmap_batch", "pm_fits_decode_batch",
-           "pm_fits_decode_window_batch", "pm_sky_stats_batch", "pm_clipped_stats_batch", "pm_stats_plan", "pm_gaussfit_batch", "pm_ellipse_sum_batch", "pm_sersicfit_batch",
+           "pm_fits_decode_window_batch", "pm_sky_stats_batch", "pm_clipped_stats_batch", "pm_clipped_stats2_batch", "pm_stats_plan", "pm_gaussfit_batch", "pm_ellipse_sum_batch", "pm_sersicfit_batch",
            "pm_maskstars_workspace_bytes", "pm_maskstars_batch")
 PM_CLIP_COLS, PM_GAUSS_COLS, PM_STAR_COLS = 10, 10, 4
 CLIP_FIELDS = ("count", "mean", "median", "std", "clip_iterations", "clipped_count", "clipped_mean", "clipped_median", "clipped_std", "max")
@@ -85,6 +85,8 @@ def declare(lib):
     lib.pm_ellipse_sum_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_sersicfit_batch.restype = C.c_int
     lib.pm_sersicfit_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pm_clipped_stats2_batch.restype = C.c_int
+    lib.pm_clipped_stats2_batch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_stats_plan.restype = C.c_int
     lib.pm_stats_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pm_gaussfit_batch.restype = C.c_int

@@ -27,8 +27,8 @@ pm_sky_stats_kernel(const T* images, long long B, int n, const double* ellipse, 
     sky_body<T>(images, B, n, ellipse, out, resident);
 }
 template <typename T> __global__ void __launch_bounds__(kThreads, PM_STAT_MIN_CTAS)
-pm_clipstats_kernel(const T* images, long long B, int n, double sigma, int maxiters, double* out, int resident) {
-    clipstats_body<T>(images, B, n, sigma, maxiters, out, resident);
+pm_clipstats_kernel(const T* images, long long B, int n, double sigma, int maxiters, double* out, int resident, int snap_at, double* out_snap) {
+    clipstats_body<T>(images, B, n, sigma, maxiters, out, resident, snap_at, out_snap);
 }
 #endif
 
@@ -146,10 +146,11 @@ int pm_sky_stats_batch(const void* images, int dtype, int64_t B, int n, const do
     return PM_OK;
 }
 
-int pm_clipped_stats_batch(const void* images, int dtype, int64_t B, int n, double sigma, int maxiters, double* out, void* cuda_stream) {
+static int clipped_stats_impl(const void* images, int dtype, int64_t B, int n, double sigma, int maxiters, double* out, int snap_at,
+                              double* out_snap, void* cuda_stream, const char* what) {
     pm_set_error("");
     if (B == 0) return PM_OK;
-    if (bad_images(images, dtype, B, n) || n < 8 || !out || !(sigma > 0.0)) { pm_set_error("bad argument"); return PM_EINVAL; }
+    if (bad_images(images, dtype, B, n) || n < 8 || !out || !(sigma > 0.0) || (out_snap && snap_at < 1)) { pm_set_error("bad argument"); return PM_EINVAL; }
     StatPlan P;
     char err[200];
     int rc = make_plan(B, n, dtype == PM_F32 ? 4 : 8, false, &P, err, sizeof err);
@@ -157,18 +158,28 @@ int pm_clipped_stats_batch(const void* images, int dtype, int64_t B, int n, doub
 #ifndef PM_EMULATE
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaError_t e = dtype == PM_F32
-        ? launch_clustered(pm_clipstats_kernel<float>, P, st, (const float*)images, (long long)B, n, sigma, maxiters, out, P.resident)
-        : launch_clustered(pm_clipstats_kernel<double>, P, st, (const double*)images, (long long)B, n, sigma, maxiters, out, P.resident);
-    if (e != cudaSuccess) { snprintf(err, sizeof err, "pm_clipped_stats_batch: %s", cudaGetErrorString(e)); pm_set_error(err); return PM_ECUDA; }
+        ? launch_clustered(pm_clipstats_kernel<float>, P, st, (const float*)images, (long long)B, n, sigma, maxiters, out, P.resident, snap_at, out_snap)
+        : launch_clustered(pm_clipstats_kernel<double>, P, st, (const double*)images, (long long)B, n, sigma, maxiters, out, P.resident, snap_at, out_snap);
+    if (e != cudaSuccess) { snprintf(err, sizeof err, "%s: %s", what, cudaGetErrorString(e)); pm_set_error(err); return PM_ECUDA; }
 #else
-    (void)cuda_stream;
+    (void)cuda_stream; (void)what;
     for (long long blk = 0; blk < P.grid; blk++) {
-        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)P.grid, kThreads, P.smem, [&]() { clipstats_body<float>((const float*)images, B, n, sigma, maxiters, out, P.resident); });
-        else pm_emul::run_block((int)blk, (int)P.grid, kThreads, P.smem, [&]() { clipstats_body<double>((const double*)images, B, n, sigma, maxiters, out, P.resident); });
+        if (dtype == PM_F32) pm_emul::run_block((int)blk, (int)P.grid, kThreads, P.smem, [&]() { clipstats_body<float>((const float*)images, B, n, sigma, maxiters, out, P.resident, snap_at, out_snap); });
+        else pm_emul::run_block((int)blk, (int)P.grid, kThreads, P.smem, [&]() { clipstats_body<double>((const double*)images, B, n, sigma, maxiters, out, P.resident, snap_at, out_snap); });
     }
 #endif
     pm_count_launch();
     return PM_OK;
+}
+
+int pm_clipped_stats_batch(const void* images, int dtype, int64_t B, int n, double sigma, int maxiters, double* out, void* cuda_stream) {
+    return clipped_stats_impl(images, dtype, B, n, sigma, maxiters, out, 0, nullptr, cuda_stream, "pm_clipped_stats_batch");
+}
+
+int pm_clipped_stats2_batch(const void* images, int dtype, int64_t B, int n, double sigma, int maxiters_first, double* out_first,
+                            double* out_converged, void* cuda_stream) {
+    if (!out_first) { pm_set_error("bad argument"); return PM_EINVAL; }
+    return clipped_stats_impl(images, dtype, B, n, sigma, 0, out_converged, maxiters_first, out_first, cuda_stream, "pm_clipped_stats2_batch");
 }
 
 // what a call would use (tests, bench): cluster size, whether the cutout is resident in shared memory, bytes per CTA

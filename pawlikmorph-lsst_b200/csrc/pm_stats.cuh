@@ -514,8 +514,12 @@ PM_DEV void sky_body(const T* images, long long B, int n, const double* ellipse,
     if (c.cl.size > 1) pm::cluster_sync();      // nobody leaves while its shared memory may still be read
 }
 
+// snap_at > 0 with out_snap: the row as it stands after snap_at rounds (or at convergence, if that comes first) goes to out_snap —
+// sigma_clipped_stats(maxiters=snap_at) and (maxiters=maxiters) of the same image from one sequence of rounds
+// (imageutils.py:62 and :67 need maxiters = 5 and the converged statistics of the same image).
 template <typename T>
-PM_DEV void clipstats_body(const T* images, long long B, int n, double sigma, int maxiters, double* out, int resident) {
+PM_DEV void clipstats_body(const T* images, long long B, int n, double sigma, int maxiters, double* out, int resident,
+                           int snap_at = 0, double* out_snap = nullptr) {
     StatCtx c = stat_begin(n, sizeof(T), false, resident != 0);
     Sh& sh = *c.sh;
     StatScratch& sc = *c.sc;
@@ -536,7 +540,16 @@ PM_DEV void clipstats_body(const T* images, long long B, int n, double sigma, in
         // astropy SigmaClip: bounds median -/+ sigma * std (inclusive) from the surviving values, until a round removes
         // nothing or maxiters rounds are done (maxiters <= 0: until convergence)
         double iters = 0.0, changed = 1.0;
+        bool snapped = false;
+        auto write_row = [&](double* o) {
+            o[0] = all.cnt; o[1] = all.mean; o[2] = all.median; o[3] = all.std; o[4] = iters;
+            o[5] = cur.cnt; o[6] = cur.mean; o[7] = cur.median; o[8] = cur.std; o[9] = all.cnt > 0.0 ? all.vmax : -inf;
+        };
         while (changed != 0.0 && (maxiters <= 0 || iters < (double)maxiters) && cur.cnt > 0.0) {
+            if (out_snap && !snapped && iters >= (double)snap_at) {
+                if (c.cl.rank == 0 && pm::tid() == 0) write_row(out_snap + (size_t)b * kClipCols);
+                snapped = true;
+            }
             iters += 1.0;
             s.set_bounds(fmax(s.lo, cur.median - cur.std * sigma), fmin(s.hi, cur.median + cur.std * sigma));
             const StatOut nxt = stat_set(sh, sc, c.cl, s, cur.median, true);
@@ -544,9 +557,8 @@ PM_DEV void clipstats_body(const T* images, long long B, int n, double sigma, in
             cur = nxt;
         }
         if (c.cl.rank == 0 && pm::tid() == 0) {
-            double* o = out + (size_t)b * kClipCols;
-            o[0] = all.cnt; o[1] = all.mean; o[2] = all.median; o[3] = all.std; o[4] = iters;
-            o[5] = cur.cnt; o[6] = cur.mean; o[7] = cur.median; o[8] = cur.std; o[9] = all.cnt > 0.0 ? all.vmax : -inf;
+            if (out_snap && !snapped) write_row(out_snap + (size_t)b * kClipCols);
+            write_row(out + (size_t)b * kClipCols);
         }
         pm::sync();
     }

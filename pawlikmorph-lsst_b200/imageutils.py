@@ -46,12 +46,13 @@ def _run(images, threshold, npixels, mean, std, seed, want_labels, want_clean, s
     return dict(labels=labels, clean=clean, info=info)
 
 
-def detect_sources_batch(images, nsigma=1.5, npixels=8, want_labels=False, stream=None):
+def detect_sources_batch(images, nsigma=1.5, npixels=8, want_labels=False, stream=None, stats=None):
     """photutils.detect_threshold + detect_sources as skyBackground.py:104-110 / imageutils.py:66-71 call them.
+    stats: the rows of clipped_stats_batch(images, 3.0, None) when the caller has them already.
     Returns dict(labels: CUDA int32 [B, n, n] or None, info: CUDA float64 [B, 4] — column 0 = number of segments)."""
     from .skyBackground import clipped_stats_batch
     images = _prep(images)
-    cs = clipped_stats_batch(images, 3.0, None, stream=stream)
+    cs = stats if stats is not None else clipped_stats_batch(images, 3.0, None, stream=stream)
     thr = (cs[:, 6] + float(nsigma) * cs[:, 8]).contiguous()
     return _run(images, thr, npixels, None, None, 0, want_labels, False, stream)
 
@@ -59,10 +60,9 @@ def detect_sources_batch(images, nsigma=1.5, npixels=8, want_labels=False, strea
 def maskstars_batch(images, seed=0, nsigma=1.5, npixels=8, want_labels=False, stream=None):
     """imageutils.maskstarsSEG for a batch: dict(clean: CUDA tensor like `images`, labels, info [B, 4] = segments kept,
     segments cleaned, pixels replaced, status)."""
-    from .skyBackground import clipped_stats_batch
+    from .skyBackground import clipped_stats_both
     images = _prep(images)
-    c5 = clipped_stats_batch(images, 3.0, 5, stream=stream)              # imageutils.py:62
-    cn = clipped_stats_batch(images, 3.0, None, stream=stream)           # detect_threshold
+    c5, cn = clipped_stats_both(images, 3.0, 5, stream=stream)           # imageutils.py:62 (maxiters 5) and detect_threshold (:67, converged)
     thr = (cn[:, 6] + float(nsigma) * cn[:, 8]).contiguous()
     return _run(images, thr, npixels, c5[:, 6].contiguous(), c5[:, 8].contiguous(), seed, want_labels, True, stream)
 

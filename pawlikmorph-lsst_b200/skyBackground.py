@@ -103,6 +103,25 @@ def clipped_stats_batch(images, sigma=3.0, maxiters=5, stream=None):
     return out
 
 
+def clipped_stats_both(images, sigma=3.0, maxiters=5, stream=None):
+    """(clipped_stats_batch(images, sigma, maxiters), clipped_stats_batch(images, sigma, None)) from one launch: the rounds up to
+    `maxiters` are the first rounds of the converged sequence."""
+    images = _as_cuda(images)
+    B, n = int(images.shape[0]), int(images.shape[1])
+    dev = images.device
+    L = lib()
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st):
+            first = torch.empty((B, _abi.PM_CLIP_COLS), dtype=torch.float64, device=dev)
+            conv = torch.empty((B, _abi.PM_CLIP_COLS), dtype=torch.float64, device=dev)
+            rc = L.pm_clipped_stats2_batch(images.data_ptr(), _abi.PM_F32 if images.dtype == torch.float32 else _abi.PM_F64, B, n,
+                                           float(sigma), int(maxiters), first.data_ptr(), conv.data_ptr(), st.cuda_stream)
+            _abi.check(L, rc, "pm_clipped_stats2_batch")
+            images.record_stream(st)
+    return first, conv
+
+
 def gaussfit_batch(images, stats=None, p0=None, stream=None):
     """skyBackground._gauss2dfit for a batch: CUDA float64 [B, 10], columns `_abi.GAUSS_FIELDS` (raw optimum: apply abs() for
     the np.abs of skyBackground.py:331).  stats: the rows of clipped_stats_batch (median and max feed gaussfitter.moments)."""
@@ -175,8 +194,11 @@ def skybgr_batch(images, large_images=None, seed=0, stream=None):
     if large_images is not None:
         work = maskstars_batch(_as_cuda(large_images), seed=seed, stream=stream)["clean"]             # skyBackground.py:74
     N = int(work.shape[1])
-    nseg = detect_sources_batch(work, stream=stream)["info"][:, 0].cpu().numpy()                      # :104-113
-    fit = gaussfit_batch(images, stream=stream).cpu().numpy()                                        # :117 (on the small cutout)
+    # one pass of clipped statistics serves both: the converged ones are the detection threshold, the unclipped median / maximum of the
+    # same call are gaussfitter.moments' start values (when the source check runs on the large cutout the fit takes its own)
+    cstats = clipped_stats_batch(work, 3.0, None, stream=stream)
+    nseg = detect_sources_batch(work, stream=stream, stats=cstats)["info"][:, 0].cpu().numpy()         # :104-113
+    fit = gaussfit_batch(images, stats=cstats if large_images is None else None, stream=stream).cpu().numpy()   # :117 (on the small cutout)
     status = np.where(nseg > 0, 0, 1).astype(np.int64)
     status[(fit[:, 9] == 2) & (status == 0)] = 3
 

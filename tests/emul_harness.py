@@ -158,6 +158,18 @@ def clipped_stats(images, sigma=3.0, maxiters=5):
     return out
 
 
+def clipped_stats_both(images, sigma=3.0, maxiters=5):
+    """-> ([B, 10] at maxiters, [B, 10] converged) from one run of the two-output entry point."""
+    L = lib()
+    images = np.ascontiguousarray(images)
+    B, n, _ = images.shape
+    first, conv = np.full((B, abi.PM_CLIP_COLS), np.nan), np.full((B, abi.PM_CLIP_COLS), np.nan)
+    rc = L.pm_clipped_stats2_batch(images.ctypes.data, abi.PM_F32 if images.dtype == np.float32 else abi.PM_F64, B, n, float(sigma), int(maxiters),
+                                   first.ctypes.data, conv.ctypes.data, None)
+    abi.check(L, rc, "pm_clipped_stats2_batch")
+    return first, conv
+
+
 def gaussfit(images, p0=None):
     """-> [B, 10] (GAUSS_FIELDS); start values from gaussfitter.moments unless p0 [B, 7] is given."""
     L = lib()

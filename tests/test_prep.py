@@ -124,3 +124,11 @@ def test_philox_stream_is_the_published_one():
     assert [int(v) for v in PO.philox4x32((0xffffffff,) * 4, (0xffffffff, 0xffffffff))] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     v = PO.philox_normal(7, 3, np.arange(200000))
     assert abs(v.mean()) < 0.01 and abs(v.std() - 1.0) < 0.01
+
+
+@pytest.mark.parametrize("k", [1, 5, 40])
+def test_clipped_stats_two_stopping_rules_from_one_run(k):
+    x = _with_stars(3, 96, 9)
+    first, conv = H.clipped_stats_both(x, 3.0, k)
+    assert np.array_equal(first, H.clipped_stats(x, 3.0, k), equal_nan=True)
+    assert np.array_equal(conv, H.clipped_stats(x, 3.0, None), equal_nan=True)
