@@ -129,35 +129,95 @@ template <int BITPIX> __device__ __forceinline__ double stored_at(const unsigned
     return __hiloint2double((int)__byte_perm(q.x, 0, 0x0123), (int)__byte_perm(q.y, 0, 0x0123));
 }
 
+// grid: x over the V-pixel vectors of one window (32-bit index arithmetic, one division per thread), y striding the frames
 template <int BITPIX, typename Out, int V>
 __global__ void __launch_bounds__(256) pm_fits_window_kernel(const unsigned char* __restrict__ raw, double bzero, double bscale,
                                                               long long B, int H, int W, const int* __restrict__ origin, int npix,
                                                               Out* __restrict__ out) {
     const bool plain = bscale == 1.0 && bzero == 0.0;
-    const size_t per = (size_t)npix * npix / V, total = (size_t)B * per, nthreads = (size_t)gridDim.x * blockDim.x;
-    const int rowv = npix / V;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
-        const size_t b = t / per;
-        const int q = (int)(t - b * per), r = q / rowv, c = (q - r * rowv) * V;
-        const size_t src = (b * H + (size_t)(__ldg(origin + 2 * b) + r)) * W + (size_t)(__ldg(origin + 2 * b + 1) + c);
-        double st[V];
-#pragma unroll
-        for (int j = 0; j < V; j++) st[j] = stored_at<BITPIX>(raw, src + j);
+    const bool ints = (BITPIX == 8 || BITPIX == 16) && bscale == 1.0 && bzero == rint(bzero) && fabs(bzero) <= 1073741824.0;
+    const int ibias = ints ? (int)bzero : 0;
+    const unsigned rowv = (unsigned)(npix / V), per = (unsigned)npix * rowv;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= per) return;
+    const unsigned r = q / rowv, c = (q - r * rowv) * V;
+    for (long long b = blockIdx.y; b < B; b += gridDim.y) {
+        const size_t src = ((size_t)b * H + (size_t)(__ldg(origin + 2 * b) + (int)r)) * W + (size_t)(__ldg(origin + 2 * b + 1) + (int)c);
         Out o[V];
+        if (ints) {
+            int si[V];
 #pragma unroll
-        for (int j = 0; j < V; j++) o[j] = (Out)(plain ? st[j] : __dadd_rn(__dmul_rn(st[j], bscale), bzero));
-        Out* dst = out + t * V;
+            for (int j = 0; j < V; j++) si[j] = BITPIX == 8 ? (int)__ldg(raw + src + j) : (int)(short)__byte_perm((unsigned)__ldg((const unsigned short*)raw + src + j), 0, 0x4401);
+#pragma unroll
+            for (int j = 0; j < V; j++) o[j] = (Out)(si[j] + ibias);
+        } else {
+            double st[V];
+#pragma unroll
+            for (int j = 0; j < V; j++) st[j] = stored_at<BITPIX>(raw, src + j);
+#pragma unroll
+            for (int j = 0; j < V; j++) o[j] = (Out)(plain ? st[j] : __dadd_rn(__dmul_rn(st[j], bscale), bzero));
+        }
+        Out* dst = out + ((size_t)b * per + q) * V;
         if constexpr (V == 4 && sizeof(Out) == 4) *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
         else if constexpr (V == 4) { ((double2*)dst)[0] = make_double2(o[0], o[1]); ((double2*)dst)[1] = make_double2(o[2], o[3]); }
         else dst[0] = o[0];
     }
 }
 
+// BITPIX 16 with an integer BZERO (the SDSS frames): eight pixels per thread from five ALIGNED 32-bit words — a window row starts at
+// any even byte, so the 16 bytes a thread needs are funnel-shifted out of the words around them — and two 16-byte stores.
+template <typename Out>
+__global__ void __launch_bounds__(256) pm_fits_window16_kernel(const unsigned char* __restrict__ raw, int ibias, long long B, int H, int W,
+                                                                const int* __restrict__ origin, int npix, Out* __restrict__ out) {
+    const unsigned rowv = (unsigned)(npix / 8), per = (unsigned)npix * rowv;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= per) return;
+    const unsigned r = q / rowv, c = (q - r * rowv) * 8;
+    for (long long b = blockIdx.y; b < B; b += gridDim.y) {
+        const size_t src = ((size_t)b * H + (size_t)(__ldg(origin + 2 * b) + (int)r)) * W + (size_t)(__ldg(origin + 2 * b + 1) + (int)c);
+        const size_t byte = 2 * src;
+        const unsigned* wp = (const unsigned*)(raw + (byte & ~(size_t)3));
+        const unsigned sh = (unsigned)(byte & 2) * 8u;
+        unsigned w[5];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = __ldg(wp + k);
+        w[4] = sh ? __ldg(wp + 4) : 0u;                       // (not touched when the row piece is word aligned: it may end the payload)
+        unsigned p[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) p[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        Out o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = (Out)(stored_int_of<16>(p, j) + ibias);
+        Out* dst = out + ((size_t)b * per + q) * 8;
+        if constexpr (sizeof(Out) == 4) {
+            ((float4*)dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+            ((float4*)dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ((double2*)dst)[j] = make_double2(o[2 * j], o[2 * j + 1]);
+        }
+    }
+}
+
 template <typename Out, int V>
 inline void fits_window_launch(const unsigned char* raw, int bitpix, double bzero, double bscale, long long B, int H, int W,
                                const int* origin, int npix, Out* out, unsigned max_ctas, cudaStream_t st) {
-    const size_t want = ((size_t)B * npix * npix / V + 255) / 256;
-    const unsigned grid = (unsigned)(want < max_ctas ? (want > 0 ? want : 1) : max_ctas);
+    const unsigned per = (unsigned)((size_t)npix * npix / V), gx = (per + 255u) / 256u;
+    unsigned gy = gx ? max_ctas / gx : 1u;
+    gy = gy < 1u ? 1u : gy;
+    gy = (long long)gy > B ? (unsigned)B : gy;
+    gy = gy > 65535u ? 65535u : gy;
+    const dim3 grid(gx, gy, 1);
+    if (V == 4 && bitpix == 16 && npix % 8 == 0 && bscale == 1.0 && bzero == rint(bzero) && fabs(bzero) <= 1073741824.0 &&
+        (((uintptr_t)raw) & 3) == 0) {
+        const unsigned per8 = (unsigned)((size_t)npix * npix / 8), gx8 = (per8 + 255u) / 256u;
+        unsigned gy8 = gx8 ? max_ctas / gx8 : 1u;
+        gy8 = gy8 < 1u ? 1u : gy8;
+        gy8 = (long long)gy8 > B ? (unsigned)B : gy8;
+        gy8 = gy8 > 65535u ? 65535u : gy8;
+        pm_fits_window16_kernel<Out><<<dim3(gx8, gy8, 1), 256, 0, st>>>(raw, (int)bzero, B, H, W, origin, npix, out);
+        return;
+    }
     switch (bitpix) {
         case 8:   pm_fits_window_kernel<8, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;
         case 16:  pm_fits_window_kernel<16, Out, V><<<grid, 256, 0, st>>>(raw, bzero, bscale, B, H, W, origin, npix, out); break;

@@ -58,7 +58,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 gb = Bw * npix * npix * 6 / 1e9
-print(json.dumps({"kernel": "pm_fits_window_kernel<16, float, 4>", "frames": Bw, "frame": [Hh, Ww], "npix": npix, "ms": ms,
+print(json.dumps({"kernel": "pm_fits_window16_kernel<float>", "frames": Bw, "frame": [Hh, Ww], "npix": npix, "ms": ms,
                   "algorithmic_GBps": gb / ms * 1e3, "frac_of_hbm_peak": gb / ms * 1e3 / peak,
                   "note": "algorithmic bytes = window pixels x 6; the 2-byte rows start at odd offsets, so DRAM reads whole sectors"}), flush=True)
 del raw, out, org_d
