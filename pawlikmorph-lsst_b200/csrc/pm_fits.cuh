@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(256) pm_fits_window16_kernel(const unsigned ch
     const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= per) return;
     const unsigned r = q / rowv, c = (q - r * rowv) * 8;
+    const size_t total_bytes = (size_t)B * H * W * 2;
     for (long long b = blockIdx.y; b < B; b += gridDim.y) {
         const size_t src = ((size_t)b * H + (size_t)(__ldg(origin + 2 * b) + (int)r)) * W + (size_t)(__ldg(origin + 2 * b + 1) + (int)c);
         const size_t byte = 2 * src;
@@ -181,7 +182,9 @@ __global__ void __launch_bounds__(256) pm_fits_window16_kernel(const unsigned ch
         unsigned w[5];
 #pragma unroll
         for (int k = 0; k < 4; k++) w[k] = __ldg(wp + k);
-        w[4] = sh ? __ldg(wp + 4) : 0u;                       // (not touched when the row piece is word aligned: it may end the payload)
+        // the fifth word is only needed for a row piece that starts in the middle of a word, and then only its low half: it is not
+        // read when it would start beyond the payload (a window ending on the last pixel of the last frame)
+        w[4] = (sh && (byte & ~(size_t)3) + 16 < total_bytes) ? __ldg(wp + 4) : 0u;
         unsigned p[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) p[k] = __funnelshift_r(w[k], w[k + 1], sh);

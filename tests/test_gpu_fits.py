@@ -39,13 +39,16 @@ def test_payload_host_api_equals_the_float_api():
     assert np.array_equal(a, f)
 
 
-@pytest.mark.parametrize("npix", [20, 7, 36])
+@pytest.mark.parametrize("npix", [20, 7, 36, 32, 24, 8])
 def test_window_decode_every_bitpix_on_the_gpu(npix):
+    """(multiples of 8 take the aligned-word kernel for the 16-bit frames; the last window ends on the last pixel of the payload)"""
     import torch
 
     import pawlikmorph_lsst_b200 as pm
     from tests.fits_cases import window_cases
     org = np.array([[0, 0], [1, 5], [0, 3]], dtype=np.int32)
+    if npix % 8 == 0:
+        org = np.array([[0, 0], [1, 5], [37 - npix, 41 - npix]], dtype=np.int32)
     for bitpix, bzero, bscale, payload, frames in window_cases():
         raw = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
         for dt, npdt in ((torch.float32, np.float32), (torch.float64, np.float64)):
