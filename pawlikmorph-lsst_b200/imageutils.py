@@ -75,18 +75,16 @@ def maskstarsSEG(image, seed=0, device="cuda:0"):
 
 # ---- the star-catalogue path (imageutils.py:94-333): host functions ------------------------------------------------------
 def _circle_mask(shape, centre, radius):
-    """imageutils.py:94-132: boolean disc (x - cx)^2 + (y - cy)^2 <= radius^2 with x the FIRST array axis (the angular factor of
-    the original, theta % 2 pi <= 2 pi, is true everywhere except where theta is NaN)."""
-    x, y = np.ogrid[:shape[0], :shape[1]]
-    cx, cy = centre
-    r2 = (x - cx) * (x - cx) + (y - cy) * (y - cy)
-    theta = np.arctan2(x - cx, y - cy) % (2 * np.pi)
-    return (r2 <= radius * radius) * (theta <= 2. * np.pi)
+    """imageutils.py:94-132: boolean disc about `centre` = (position along axis 0, position along axis 1), boundary included.
+    (Upstream multiplies by an angular mask `theta % 2 pi <= 2 pi`, which holds for every pixel.)"""
+    d0 = np.arange(shape[0], dtype=np.float64)[:, None] - centre[0]
+    d1 = np.arange(shape[1], dtype=np.float64)[None, :] - centre[1]
+    return d0 * d0 + d1 * d1 <= radius * radius
 
 
 def _calculateRadius(y, A, sigma):
-    """imageutils.py:135-165: sigma * sqrt(|2 ln(A / y)|)"""
-    return sigma * np.sqrt(abs(2. * np.log(A / y)))
+    """imageutils.py:135-165: the x at which A exp(-x^2 / (2 sigma^2)) = y, for either order of A and y."""
+    return sigma * np.sqrt(np.abs(2.0 * np.log(A / y)))
 
 
 def _subpixel_disc(shape, pixelPos, radius, subpixels=5):
@@ -111,56 +109,53 @@ def _subpixel_disc(shape, pixelPos, radius, subpixels=5):
 
 
 def _calculateAdaptiveRadius(mask, pixelPos, image, skyCount, sky_err):
-    """imageutils.py:262-333: walk away from the image centre along the star's column; the run of consecutive profile points
-    above mean + sky_err gives the extra radius."""
-    maskedImage = image * ~mask + ((skyCount + 1000) * mask)
-    yinit = maskedImage[int(pixelPos[1]), int(pixelPos[0])]
-    imgsize = image.shape[0]
-    delta = 1 if pixelPos[1] > int(imgsize / 2) else -1
-    if pixelPos[1] >= imgsize - 1 or pixelPos[1] <= 0:
+    """imageutils.py:262-333: the column through the star, read from the star's row away from the image centre for at most half the
+    image (masked pixels count as skyCount + 1000); the length of the first run of consecutive samples above mean + sky_err, minus
+    one, is the extra radius.  0 for a star on the first / last row (and, where upstream fails on an unbound variable because no
+    sample exceeds the threshold, 0 as well)."""
+    side = image.shape[0]
+    x, y = int(pixelPos[0]), int(pixelPos[1])
+    if pixelPos[1] >= side - 1 or pixelPos[1] <= 0:
         return 0
-    ypos = int(pixelPos[1]) + delta
-    ys = [yinit]
-    for _ in range(int(imgsize / 2)):
-        ys.append(maskedImage[ypos, int(pixelPos[0])])
-        ypos += delta
-        if ypos >= imgsize or ypos < 0:
-            break
-    thres = np.mean(ys) + sky_err
-    arr = np.where(ys > thres)[0]
-    i = 0                                   # (upstream leaves `i` unbound when nothing exceeds the threshold: UnboundLocalError)
-    for i, val in enumerate(arr):
-        if i + 1 > arr.shape[0] - 1:
-            break
-        if val + 1 != arr[i + 1]:
-            break
-    return i
+    direction = 1 if pixelPos[1] > int(side / 2) else -1
+    rows = y + direction * np.arange(0, int(side / 2) + 1)
+    rows = rows[(rows >= 0) & (rows < side)]
+    profile = np.where(mask[rows, x], skyCount + 1000, image[rows, x])
+    above = np.flatnonzero(profile > profile.mean() + sky_err)
+    if above.size == 0:
+        return 0
+    gaps = np.flatnonzero(np.diff(above) != 1)
+    return int(gaps[0]) if gaps.size else int(above.size - 1)
+
+
+def _sky_magnitude(header, skyCount):
+    """The asinh magnitude of the sky level from the SDSS photometric header cards (imageutils.py:199-214;
+    https://classic.sdss.org/dr7/algorithms/fluxcal.html#counts2mag).  KeyError when a card is missing."""
+    counts = skyCount - header["SOFTBIAS"]
+    flux_ratio = (counts / header["EXPTIME"]) * 10 ** (0.4 * (header["PHT_AA"] + header["PHT_KK"] * header["AIRMASS"]))
+    b = header["PHT_B"]
+    return -(2.5 / np.log(10.)) * (np.arcsinh(flux_ratio / (2 * b)) + np.log(b)), counts
 
 
 def maskstarsPSF(image, objs, header, skyCount, numSigmas=5., adaptive=True, sky_err=0.0):
     """imageutils.py:168-259: mask (True = keep) of the catalogue stars `objs` ([ra, dec, type, psfMag_r] rows): for each a disc of
     numSigmas * sigma_PSF * sqrt(|2 ln(psfMag / skyMag)|) pixels about its position, the sky magnitude from the SDSS photometric
-    header cards (asinh magnitudes).  header: mapping with PSF_S1, PSF_S2, EXPTIME, PHT_AA, PHT_KK, AIRMASS, SOFTBIAS, PHT_B
-    (KeyError when one is missing, which main.py:389-391 catches) and the WCS cards `image.sky_to_pixel` understands (TAN).
-    With no objects the mask is all ones, like upstream."""
+    header cards.  header: mapping with PSF_S1, PSF_S2, EXPTIME, PHT_AA, PHT_KK, AIRMASS, SOFTBIAS, PHT_B (KeyError when one is
+    missing, which main.py:389-391 catches) and the WCS cards `image.sky_to_pixel` understands (TAN).  With no objects the mask is
+    all ones (of the image's type), like upstream.  adaptive: grow each disc by `_calculateAdaptiveRadius` (a subpixel-sampled disc;
+    main.py:387 never asks for it)."""
     from .image import sky_to_pixel
-    sigma1, sigma2 = header["PSF_S1"], header["PSF_S2"]
-    expTime, aa, kk = header["EXPTIME"], header["PHT_AA"], header["PHT_KK"]
-    airMass, softwareBias, b = header["AIRMASS"], header["SOFTBIAS"], header["PHT_B"]
-    skyCount = skyCount - softwareBias
-    factor = 0.4 * (aa + kk * airMass)
-    skyFluxRatio = (skyCount / expTime) * 10 ** factor
-    skyMag = -(2.5 / np.log(10.)) * (np.arcsinh(skyFluxRatio / (2 * b)) + np.log(b))
+    psf_sigma = max(header["PSF_S1"], header["PSF_S2"])
+    sky_mag, counts = _sky_magnitude(header, skyCount)
     image = np.asarray(image)
     if len(objs) == 0:
         return np.ones_like(image)
-    starmask = np.zeros_like(image)
-    for obj in objs:
-        pixelPos = sky_to_pixel(header, obj[0], obj[1])
-        sigma = max(sigma1, sigma2)
-        radius = numSigmas * _calculateRadius(skyMag, obj[3], sigma)
-        starmask = np.logical_or(starmask, _circle_mask(starmask.shape, (pixelPos[1], pixelPos[0]), radius))
+    covered = np.zeros(image.shape, dtype=bool)
+    for ra, dec, _kind, mag in objs:
+        x, y = sky_to_pixel(header, ra, dec)
+        radius = numSigmas * _calculateRadius(sky_mag, mag, psf_sigma)
+        covered |= _circle_mask(image.shape, (y, x), radius)
         if adaptive:
-            extra = _calculateAdaptiveRadius(starmask, pixelPos, image, skyCount, sky_err)
-            starmask = np.logical_or(starmask, _subpixel_disc(image.shape, pixelPos, radius + extra))
-    return ~starmask
+            extra = _calculateAdaptiveRadius(covered, (x, y), image, counts, sky_err)
+            covered |= _subpixel_disc(image.shape, (x, y), radius + extra) > 0
+    return ~covered
