@@ -87,7 +87,7 @@ template <typename T> struct StatSet {      // pixels of this CTA's rows that be
 // together (unconditionally: the pixels outside the region are few).  Membership in [klo, khi] is one unsigned
 // compare of key - klo against khi - klo.  kFull: n is a multiple of 32 * kStatGroup (no bounds checks at all).
 constexpr int kStatGroup = 8;
-template <typename T, bool kFull, bool kMask, typename F> PM_DEV void stat_for_each_impl(const StatSet<T>& s, F&& f) {
+template <typename T, bool kFull, bool kMask, bool kSparse, typename F> PM_DEV void stat_for_each_impl(const StatSet<T>& s, F&& f) {
     typedef typename StatSet<T>::K K;
     const K klo = s.klo, span = s.khi - s.klo;        // callers guarantee klo <= khi
     for (int r = pm::warp(); r < s.rows; r += kWarps) {
@@ -103,21 +103,39 @@ template <typename T, bool kFull, bool kMask, typename F> PM_DEV void stat_for_e
                 xv[j] = ok ? row[wi * 32] : (T)0;
                 bits[j] = !ok ? 0u : kMask ? mrow[wi] >> pm::lane() : 1u;
             }
+            if (kSparse || kMask) {
+                // membership of the eight pixels first, ONE branch for the group: in the select passes hardly any pixel is a member;
+                // with a region plane it also pays in the dense passes (measured: sky 0.92 -> 1.00 M cutouts/s), without one it costs 15 %
+                K key[kStatGroup];
+                unsigned member = 0u;
 #pragma unroll
-            for (int j = 0; j < kStatGroup; j++) {
-                const K key = stat_key(xv[j]);
-                if ((!kMask && kFull ? true : (bits[j] & 1u) != 0u) && (K)(key - klo) <= span) f(xv[j], key);     // NaNs sort outside every range
+                for (int j = 0; j < kStatGroup; j++) {
+                    key[j] = stat_key(xv[j]);
+                    const bool in = (!kMask && kFull ? true : (bits[j] & 1u) != 0u) && (K)(key[j] - klo) <= span;
+                    member |= (in ? 1u : 0u) << j;
+                }
+                if (member) {
+#pragma unroll
+                    for (int j = 0; j < kStatGroup; j++)
+                        if ((member >> j) & 1u) f(xv[j], key[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kStatGroup; j++) {
+                    const K key = stat_key(xv[j]);
+                    if ((!kMask && kFull ? true : (bits[j] & 1u) != 0u) && (K)(key - klo) <= span) f(xv[j], key);     // NaNs sort outside every range
+                }
             }
         }
     }
 }
-template <typename T, typename F> PM_DEV void stat_for_each(const StatSet<T>& s, F&& f) {
+template <typename T, bool kSparse = false, typename F> PM_DEV void stat_for_each(const StatSet<T>& s, F&& f) {
     if (s.klo > s.khi) return;                        // empty range
     const bool full = s.n % (32 * kStatGroup) == 0;
     if (s.mask) {
-        if (full) stat_for_each_impl<T, true, true>(s, f); else stat_for_each_impl<T, false, true>(s, f);
+        if (full) stat_for_each_impl<T, true, true, kSparse>(s, f); else stat_for_each_impl<T, false, true, kSparse>(s, f);
     } else {
-        if (full) stat_for_each_impl<T, true, false>(s, f); else stat_for_each_impl<T, false, false>(s, f);
+        if (full) stat_for_each_impl<T, true, false, kSparse>(s, f); else stat_for_each_impl<T, false, false, kSparse>(s, f);
     }
 }
 
@@ -327,7 +345,7 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
                 sub.khi = s.khi < phi ? s.khi : phi;
             }
             const unsigned bmask = (1u << bits) - 1u;
-            stat_for_each(sub, [&](T, K key) { pm::atomic_add(&hist[(unsigned)(key >> shr) & bmask], 1u); });
+            stat_for_each<T, true>(sub, [&](T, K key) { pm::atomic_add(&hist[(unsigned)(key >> shr) & bmask], 1u); });
             pm::sync();
             stat_coarse_sums(sc, cl.hsel);
             stat_pass_barrier(cl);
@@ -356,7 +374,7 @@ template <typename T> PM_DEV StatOut stat_set(Sh& sh, StatScratch& sc, StatCl& c
             const K plo = (K)(prefix << rem), phi = (K)(plo | (K)((((K)1) << rem) - (K)1));
             sub.klo = s.klo > plo ? s.klo : plo;
             sub.khi = s.khi < phi ? s.khi : phi;
-            stat_for_each(sub, [&](T, K key) { sc.list[pm::atomic_add(&sc.nlist, 1u)] = (unsigned long long)key; });
+            stat_for_each<T, true>(sub, [&](T, K key) { sc.list[pm::atomic_add(&sc.nlist, 1u)] = (unsigned long long)key; });
             pm::sync();
             const unsigned m = sc.nlist;                       // == loc.count
             for (unsigned i = (unsigned)pm::tid(); i < m; i += (unsigned)kThreads) {
